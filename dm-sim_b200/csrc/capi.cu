@@ -1,0 +1,770 @@
+// dm-sim_b200/csrc/capi.cu -- the C-ABI (include/dmsim_b200.h): state ownership, CUDA-graph executor,
+// NCCL qubit-remap exchange, result readback.  Replaces Simulation::{ctor,upload,sim,measure}
+// (reference src/dmsim_nvgpu_omp.cuh:196-549).  There is no CPU fallback: every compute entry point
+// fails with DMB_ECUDA when no usable GPU / driver is present.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/dmsim_b200.h"
+#include "kernels.cuh"
+#include "plan.hpp"
+
+using namespace dmb;
+
+// ------------------------------------------------------------------------------------------------
+// errors / options
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                             \
+    do                                                                                                       \
+    {                                                                                                        \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(DMB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" +  \
+                                       std::to_string(__LINE__) + ")");                                      \
+    } while (0)
+
+static PlanOptions g_opt;
+static int g_use_graph = 1;
+static bool g_opt_init = false;
+static void init_options()
+{
+    if (g_opt_init) return;
+    g_opt_init = true;
+    if (const char* e = getenv("DMB_TILE_BITS")) g_opt.tile_bits = atoi(e);
+    if (const char* e = getenv("DMB_LOW_BITS")) g_opt.low_bits = atoi(e);
+    if (const char* e = getenv("DMB_MIN_TILES_LOG2")) g_opt.min_tiles_log2 = atoi(e);
+    if (const char* e = getenv("DMB_GRAPH")) g_use_graph = atoi(e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily so that single-GPU users never need it
+// ------------------------------------------------------------------------------------------------
+namespace
+{
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct Nccl
+{
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+Nccl g_nccl;
+const int kNcclDouble = 8; // ncclFloat64 in ncclDataType_t
+
+bool load_nccl(std::string& why)
+{
+    if (g_nccl.lib) return true;
+    const char* names[] = {getenv("DMB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names)
+    {
+        if (!nm) continue;
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib)
+    {
+        why = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+        return false;
+    }
+#define SYM(field, name)                                                              \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name);                               \
+    if (!g_nccl.field) { why = std::string("missing NCCL symbol ") + name; return false; }
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return true;
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// the simulation object
+// ------------------------------------------------------------------------------------------------
+struct dmb_sim
+{
+    int n = 0, g = 0, world = 1, rank = 0, device = 0;
+    int N = 0, M = 0;
+    size_t shard_elems = 0;
+    double2* buf[2] = {nullptr, nullptr};
+    int cur = 0;
+    std::vector<int> layout; // physical bit of logical bit
+    bool conj_flag = false;  // stored array = conj(state), see Plan::conj_start
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<cudaEvent_t> ev_comm; // pairs around exchanges
+
+    // circuit
+    std::vector<dmb_gate> gates;
+    std::vector<double> mats;
+    bool have_circuit = false;
+    Plan plan;
+    std::vector<int> plan_layout; // layout the plan was made for
+    bool plan_conj = false;
+    DevOp* d_ops = nullptr;
+    size_t d_ops_cap = 0;
+    std::vector<size_t> op_offset; // per step
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_cur = -1;
+    uint64_t h2d_bytes = 0;
+
+    // scratch for results
+    double* d_scratch = nullptr;
+    size_t d_scratch_bytes = 0;
+
+    ncclComm_t comm = nullptr;
+};
+
+static LayoutArgs layout_args(const dmb_sim* s)
+{
+    LayoutArgs L;
+    memset(&L, 0, sizeof(L));
+    L.n = s->n; L.M = s->M; L.rank = s->rank; L.conj = s->conj_flag ? 1 : 0;
+    for (int l = 0; l < s->N; l++) L.phys[l] = (unsigned char)s->layout[l];
+    return L;
+}
+
+static int ensure_scratch(dmb_sim* s, size_t bytes)
+{
+    if (s->d_scratch_bytes >= bytes) return DMB_OK;
+    if (s->d_scratch) cudaFree(s->d_scratch);
+    s->d_scratch = nullptr; s->d_scratch_bytes = 0;
+    CU(cudaMalloc(&s->d_scratch, bytes));
+    s->d_scratch_bytes = bytes;
+    return DMB_OK;
+}
+
+static int ensure_second_buffer(dmb_sim* s)
+{
+    if (s->buf[1]) return DMB_OK;
+    CU(cudaMalloc(&s->buf[1], s->shard_elems * sizeof(double2)));
+    return DMB_OK;
+}
+
+static void drop_graph(dmb_sim* s)
+{
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    s->graph_exec = nullptr;
+    s->graph_cur = -1;
+}
+
+extern "C" {
+
+const char* dmb_last_error(void) { return g_err.c_str(); }
+const char* dmb_version(void) { return "dmsim-b200 0.1 (sm_100a)"; }
+
+int dmb_set_option(const char* name, int64_t value)
+{
+    init_options();
+    if (!name) return fail(DMB_EINVAL, "null option name");
+    if (!strcmp(name, "tile_bits")) g_opt.tile_bits = (int)value;
+    else if (!strcmp(name, "low_bits")) g_opt.low_bits = (int)value;
+    else if (!strcmp(name, "min_tiles_log2")) g_opt.min_tiles_log2 = (int)value;
+    else if (!strcmp(name, "graph")) g_use_graph = (int)value;
+    else return fail(DMB_EINVAL, std::string("unknown option ") + name);
+    return DMB_OK;
+}
+
+int dmb_create(int n_qubits, int world_size, int rank, int device, dmb_handle* out)
+{
+    init_options();
+    if (!out) return fail(DMB_EINVAL, "null out handle");
+    *out = nullptr;
+    if (n_qubits < 1 || n_qubits > 20) return fail(DMB_EINVAL, "n_qubits must be in [1, 20]");
+    int g = 0;
+    while ((1 << g) < world_size) g++;
+    // reference ctor (:218-229): n_gpus must be a power of two and divide 2^n
+    if (world_size < 1 || (1 << g) != world_size) return fail(DMB_EINVAL, "world_size must be a power of two");
+    if (g > n_qubits) return fail(DMB_EINVAL, "world_size must divide 2^n_qubits");
+    if (rank < 0 || rank >= world_size) return fail(DMB_EINVAL, "rank out of range");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(DMB_ECUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(e) +
+                                   " (this engine has no CPU fallback)");
+    if (device < 0) CU(cudaGetDevice(&device));
+    if (device >= ndev) return fail(DMB_EINVAL, "device index out of range");
+    CU(cudaSetDevice(device));
+    dmb_sim* s = new dmb_sim;
+    s->n = n_qubits; s->g = g; s->world = world_size; s->rank = rank; s->device = device;
+    s->N = 2 * n_qubits; s->M = s->N - g;
+    s->shard_elems = (size_t)1 << s->M;
+    cudaError_t ea = cudaMalloc(&s->buf[0], s->shard_elems * sizeof(double2));
+    if (ea != cudaSuccess)
+    {
+        delete s;
+        return fail(DMB_ENOMEM, std::string("cudaMalloc of the state shard failed: ") + cudaGetErrorString(ea));
+    }
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s->ev_begin));
+    CU(cudaEventCreate(&s->ev_end));
+    s->layout.resize(s->N);
+    *out = s;
+    return dmb_reset_dm(s);
+}
+
+int dmb_destroy(dmb_handle s)
+{
+    if (!s) return DMB_OK;
+    cudaSetDevice(s->device);
+    drop_graph(s);
+    if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+    for (auto ev : s->ev_comm) cudaEventDestroy(ev);
+    if (s->ev_begin) cudaEventDestroy(s->ev_begin);
+    if (s->ev_end) cudaEventDestroy(s->ev_end);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->buf[0]) cudaFree(s->buf[0]);
+    if (s->buf[1]) cudaFree(s->buf[1]);
+    if (s->d_ops) cudaFree(s->d_ops);
+    if (s->d_scratch) cudaFree(s->d_scratch);
+    delete s;
+    return DMB_OK;
+}
+
+int dmb_reset_dm(dmb_handle s)
+{
+    if (!s) return fail(DMB_EINVAL, "null handle");
+    CU(cudaSetDevice(s->device));
+    for (int l = 0; l < s->N; l++) s->layout[l] = l;
+    s->conj_flag = false;
+    s->cur = 0;
+    launch_init_state(s->buf[0], s->shard_elems, s->rank == 0, s->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->stream));
+    return DMB_OK;
+}
+
+int dmb_set_dm(dmb_handle s, const double* real, const double* imag)
+{
+    if (!s || !real || !imag) return fail(DMB_EINVAL, "null argument");
+    if (s->world != 1) return fail(DMB_ESTATE, "dmb_set_dm needs world_size == 1");
+    CU(cudaSetDevice(s->device));
+    for (int l = 0; l < s->N; l++) s->layout[l] = l;
+    s->conj_flag = false;
+    const unsigned long long total = 1ull << s->N;
+    const unsigned long long chunk = std::min<unsigned long long>(total, 1ull << 24);
+    int rc = ensure_scratch(s, chunk * 2 * sizeof(double));
+    if (rc) return rc;
+    const LayoutArgs L = layout_args(s);
+    double* d_re = s->d_scratch;
+    double* d_im = s->d_scratch + chunk;
+    for (unsigned long long first = 0; first < total; first += chunk)
+    {
+        CU(cudaMemcpyAsync(d_re, real + first, chunk * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(d_im, imag + first, chunk * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        launch_scatter_split(s->buf[s->cur], L, first, chunk, d_re, d_im, s->stream);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return DMB_OK;
+}
+
+// ---- circuit ----------------------------------------------------------------------------------
+static void encode_op(const TileOp& t, DevOp& d)
+{
+    memset(&d, 0, sizeof(d));
+    d.cls = t.cls; d.j0 = t.j0; d.j1 = t.j1;
+    const cplx one(1.0, 0.0);
+    auto put = [&](int i, cplx v) { d.m[i] = make_double2(v.real(), v.imag()); };
+    switch (t.cls)
+    {
+    case CLS_DENSE2:
+        for (int i = 0; i < 16; i++) put(i, t.m[i]);
+        break;
+    case CLS_DENSE1:
+        for (int i = 0; i < 4; i++) put(i, t.m[i]);
+        break;
+    case CLS_DIAG2:
+    {
+        int skip = 0;
+        for (int r = 0; r < 4; r++)
+        {
+            put(r, t.m[r * 5]);
+            if (t.m[r * 5] == one) skip |= 1 << r;
+        }
+        d.aux = skip << 8;
+        break;
+    }
+    case CLS_DIAG1:
+    {
+        int skip = 0;
+        for (int r = 0; r < 2; r++)
+        {
+            put(r, t.m[r * 3]);
+            if (t.m[r * 3] == one) skip |= 1 << r;
+        }
+        d.aux = skip << 8;
+        break;
+    }
+    case CLS_MONO2:
+    {
+        int src[4];
+        classify(2, t.m, src);
+        int aux = 0, skip = 0;
+        bool unit = true;
+        for (int r = 0; r < 4; r++)
+        {
+            const cplx ph = t.m[r * 4 + src[r]];
+            put(r, ph);
+            aux |= src[r] << (2 * r);
+            if (ph != one) unit = false;
+            if (src[r] == r && ph == one) skip |= 1 << r;
+        }
+        d.aux = aux | (skip << 8) | ((unit ? 1 : 0) << 12);
+        break;
+    }
+    case CLS_MONO1:
+    {
+        put(0, t.m[1]);
+        put(1, t.m[2]);
+        const bool unit = (t.m[1] == one && t.m[2] == one);
+        d.aux = (unit ? 1 : 0) << 12;
+        break;
+    }
+    default:
+        break;
+    }
+}
+
+static int build_plan(dmb_sim* s)
+{
+    try
+    {
+        s->plan = make_plan(s->n, s->world, s->gates.data(), s->gates.size(), s->mats.data(), s->mats.size() / 32,
+                            s->layout, g_opt, s->conj_flag);
+    }
+    catch (const std::invalid_argument& e)
+    {
+        return fail(DMB_EINVAL, e.what());
+    }
+    catch (const std::exception& e)
+    {
+        return fail(DMB_ESTATE, e.what());
+    }
+    s->plan_layout = s->layout;
+    s->plan_conj = s->conj_flag;
+    drop_graph(s);
+    // device op table: one contiguous upload (the reference does 3 CUDA calls per gate per GPU, :112-163)
+    std::vector<DevOp> host_ops;
+    s->op_offset.assign(s->plan.steps.size(), 0);
+    for (size_t i = 0; i < s->plan.steps.size(); i++)
+    {
+        s->op_offset[i] = host_ops.size();
+        if (s->plan.steps[i].kind != 0) continue;
+        for (const TileOp& t : s->plan.steps[i].sweep.ops)
+        {
+            DevOp d;
+            encode_op(t, d);
+            host_ops.push_back(d);
+        }
+    }
+    CU(cudaSetDevice(s->device));
+    if (host_ops.size() > s->d_ops_cap)
+    {
+        if (s->d_ops) cudaFree(s->d_ops);
+        s->d_ops = nullptr;
+        s->d_ops_cap = 0;
+        CU(cudaMalloc(&s->d_ops, host_ops.size() * sizeof(DevOp)));
+        s->d_ops_cap = host_ops.size();
+    }
+    s->h2d_bytes = host_ops.size() * sizeof(DevOp);
+    if (!host_ops.empty())
+    {
+        CU(cudaMemcpyAsync(s->d_ops, host_ops.data(), host_ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return DMB_OK;
+}
+
+int dmb_set_circuit(dmb_handle s, const dmb_gate* gates, size_t n_gates, const double* mats, size_t n_mats)
+{
+    if (!s) return fail(DMB_EINVAL, "null handle");
+    if (n_gates && !gates) return fail(DMB_EINVAL, "null gate list");
+    s->gates.assign(gates, gates + n_gates);
+    s->mats.assign(mats ? mats : nullptr, mats ? mats + 32 * n_mats : nullptr);
+    s->have_circuit = false;
+    int rc = build_plan(s);
+    if (rc) return rc;
+    s->have_circuit = true;
+    return DMB_OK;
+}
+
+int dmb_clear_circuit(dmb_handle s)
+{
+    if (!s) return fail(DMB_EINVAL, "null handle");
+    s->gates.clear();
+    s->mats.clear();
+    s->have_circuit = false;
+    drop_graph(s);
+    return DMB_OK;
+}
+
+// ---- execution --------------------------------------------------------------------------------
+static void fill_sweep_args(const dmb_sim* s, const Sweep& sw, size_t op_off, const double2* in, double2* out, SweepArgs& a)
+{
+    memset(&a, 0, sizeof(a));
+    a.in = in; a.out = out;
+    a.ops = s->d_ops + op_off;
+    a.n_ops = (int)sw.ops.size();
+    a.k = sw.k;
+    a.n_comp = s->M - sw.k;
+    a.n_tiles = 1ull << a.n_comp;
+    // load: loop bit i <-> tile-local bit i <-> physical in_pos[i] (ascending by construction)
+    for (int i = 0; i < sw.k; i++) a.gin[i] = (unsigned char)sw.in_pos[i];
+    // store: enumerate in ascending output position
+    std::vector<int> ord(sw.k);
+    for (int i = 0; i < sw.k; i++) ord[i] = i;
+    std::sort(ord.begin(), ord.end(), [&](int x, int y) { return sw.out_pos[x] < sw.out_pos[y]; });
+    for (int i = 0; i < sw.k; i++)
+    {
+        a.gout[i] = (unsigned char)sw.out_pos[ord[i]];
+        a.sout[i] = (unsigned char)ord[i];
+    }
+    std::vector<char> used_in(s->M, 0), used_out(s->M, 0);
+    for (int i = 0; i < sw.k; i++) { used_in[sw.in_pos[i]] = 1; used_out[sw.out_pos[i]] = 1; }
+    int ci = 0, co = 0;
+    for (int p = 0; p < s->M; p++)
+    {
+        if (!used_in[p]) a.cin[ci++] = (unsigned char)p;
+        if (!used_out[p]) a.cout[co++] = (unsigned char)p;
+    }
+}
+
+// enqueue every step of the plan on s->stream; cur is updated as buffers flip
+static int enqueue_steps(dmb_sim* s, int& cur, uint64_t& launches, bool allow_exchange)
+{
+    size_t comm_idx = 0;
+    for (size_t i = 0; i < s->plan.steps.size(); i++)
+    {
+        const Step& st = s->plan.steps[i];
+        if (st.kind == 0)
+        {
+            const Sweep& sw = st.sweep;
+            double2* in = s->buf[cur];
+            double2* out = in;
+            if (sw.out_of_place)
+            {
+                int rc = ensure_second_buffer(s);
+                if (rc) return rc;
+                out = s->buf[cur ^ 1];
+            }
+            SweepArgs a;
+            fill_sweep_args(s, sw, s->op_offset[i], in, out, a);
+            const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)sweep_max_grid(sw.k));
+            launch_sweep(a, grid, s->stream);
+            CU(cudaGetLastError());
+            launches++;
+            if (sw.out_of_place) cur ^= 1;
+        }
+        else
+        {
+            if (!allow_exchange || !s->comm) return fail(DMB_ECOMM, "plan needs a qubit-remap exchange but no communicator is attached (dmb_comm_init)");
+            int rc = ensure_second_buffer(s);
+            if (rc) return rc;
+            const int P = s->world;
+            const size_t chunk = s->shard_elems / P; // complex elements per peer
+            const double2* src = s->buf[cur];
+            double2* dst = s->buf[cur ^ 1];
+            if (s->ev_comm.size() < 2 * (comm_idx + 1))
+            {
+                cudaEvent_t a_, b_;
+                CU(cudaEventCreate(&a_));
+                CU(cudaEventCreate(&b_));
+                s->ev_comm.push_back(a_);
+                s->ev_comm.push_back(b_);
+            }
+            CU(cudaEventRecord(s->ev_comm[2 * comm_idx], s->stream));
+            CU(cudaMemcpyAsync(dst + (size_t)s->rank * chunk, src + (size_t)s->rank * chunk, chunk * sizeof(double2),
+                               cudaMemcpyDeviceToDevice, s->stream));
+            int nr = g_nccl.GroupStart();
+            for (int p = 0; p < P && nr == 0; p++)
+            {
+                if (p == s->rank) continue;
+                nr = g_nccl.Send(src + (size_t)p * chunk, chunk * 2, kNcclDouble, p, s->comm, s->stream);
+                if (nr == 0) nr = g_nccl.Recv(dst + (size_t)p * chunk, chunk * 2, kNcclDouble, p, s->comm, s->stream);
+            }
+            const int ne = g_nccl.GroupEnd();
+            if (nr == 0) nr = ne;
+            if (nr != 0) return fail(DMB_ECOMM, std::string("NCCL exchange failed: ") + g_nccl.GetErrorString(nr));
+            CU(cudaEventRecord(s->ev_comm[2 * comm_idx + 1], s->stream));
+            comm_idx++;
+            launches += 1;
+            cur ^= 1;
+        }
+    }
+    return DMB_OK;
+}
+
+int dmb_run(dmb_handle s, dmb_stats* stats)
+{
+    if (!s) return fail(DMB_EINVAL, "null handle");
+    if (!s->have_circuit) return fail(DMB_ESTATE, "dmb_run before dmb_set_circuit");
+    CU(cudaSetDevice(s->device));
+    if (s->plan_layout != s->layout || s->plan_conj != s->conj_flag)
+    {
+        int rc = build_plan(s); // state layout changed since planning (reset / previous run): re-plan
+        if (rc) return rc;
+    }
+    uint64_t launches = 0;
+    const bool graphable = g_use_graph && s->plan.n_exchanges == 0 && s->plan.n_sweeps > 1;
+    int cur = s->cur;
+    if (graphable)
+    {
+        if (!s->graph_exec || s->graph_cur != s->cur)
+        {
+            drop_graph(s);
+            for (const Step& st : s->plan.steps)
+                if (st.kind == 0 && st.sweep.out_of_place)
+                {
+                    int rc = ensure_second_buffer(s);
+                    if (rc) return rc;
+                }
+            for (const Step& st : s->plan.steps)
+                if (st.kind == 0) sweep_max_grid(st.sweep.k); // attribute setup must not happen inside capture
+            cudaGraph_t graph = nullptr;
+            CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+            int c2 = s->cur;
+            uint64_t l2 = 0;
+            int rc = enqueue_steps(s, c2, l2, false);
+            cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            CU(ce);
+            CU(cudaGraphInstantiate(&s->graph_exec, graph, 0));
+            cudaGraphDestroy(graph);
+            s->graph_cur = s->cur;
+        }
+        CU(cudaEventRecord(s->ev_begin, s->stream));
+        CU(cudaGraphLaunch(s->graph_exec, s->stream));
+        CU(cudaEventRecord(s->ev_end, s->stream));
+        launches = s->plan.n_sweeps;
+        for (const Step& st : s->plan.steps)
+            if (st.kind == 0 && st.sweep.out_of_place) cur ^= 1;
+    }
+    else
+    {
+        CU(cudaEventRecord(s->ev_begin, s->stream));
+        int rc = enqueue_steps(s, cur, launches, true);
+        if (rc) return rc;
+        CU(cudaEventRecord(s->ev_end, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    s->cur = cur;
+    s->layout = s->plan.end_layout;
+    s->conj_flag = s->plan.conj_end;
+    if (stats)
+    {
+        memset(stats, 0, sizeof(*stats));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->ev_begin, s->ev_end));
+        stats->sim_ms = ms;
+        double comm = 0;
+        for (size_t i = 0; i < s->plan.n_exchanges && !graphable; i++)
+        {
+            float c = 0;
+            CU(cudaEventElapsedTime(&c, s->ev_comm[2 * i], s->ev_comm[2 * i + 1]));
+            comm += c;
+        }
+        stats->comm_ms = comm;
+        stats->comp_ms = stats->sim_ms - comm;
+        stats->n_gates = s->plan.n_gates;
+        stats->n_primitives = s->plan.n_primitives;
+        stats->n_blocks = s->plan.n_blocks;
+        stats->n_sweeps = s->plan.n_sweeps;
+        stats->n_exchanges = s->plan.n_exchanges;
+        stats->n_launches = launches;
+        stats->sweep_bytes = 32ull * s->shard_elems;
+        stats->exchange_bytes = s->plan.n_exchanges * (uint64_t)(s->world - 1) * (s->shard_elems / s->world) * 16ull;
+    }
+    return DMB_OK;
+}
+
+// ---- results ----------------------------------------------------------------------------------
+int dmb_get_dm(dmb_handle s, double* real, double* imag)
+{
+    if (!s || !real || !imag) return fail(DMB_EINVAL, "null argument");
+    if (s->world != 1) return fail(DMB_ESTATE, "dmb_get_dm needs world_size == 1 (use dmb_get_shard)");
+    CU(cudaSetDevice(s->device));
+    const unsigned long long total = 1ull << s->N;
+    const unsigned long long chunk = std::min<unsigned long long>(total, 1ull << 24);
+    int rc = ensure_scratch(s, chunk * 2 * sizeof(double));
+    if (rc) return rc;
+    const LayoutArgs L = layout_args(s);
+    double* d_re = s->d_scratch;
+    double* d_im = s->d_scratch + chunk;
+    for (unsigned long long first = 0; first < total; first += chunk)
+    {
+        launch_gather_split(s->buf[s->cur], L, first, chunk, d_re, d_im, s->stream);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(real + first, d_re, chunk * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(imag + first, d_im, chunk * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return DMB_OK;
+}
+
+int dmb_get_diag(dmb_handle s, double* diag)
+{
+    if (!s || !diag) return fail(DMB_EINVAL, "null argument");
+    CU(cudaSetDevice(s->device));
+    const size_t dim = (size_t)1 << s->n;
+    int rc = ensure_scratch(s, dim * sizeof(double));
+    if (rc) return rc;
+    launch_diag(s->buf[s->cur], layout_args(s), s->d_scratch, nullptr, s->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(diag, s->d_scratch, dim * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return DMB_OK;
+}
+
+static int reduce_scalar(dmb_sim* s, bool purity, double* out)
+{
+    if (!s || !out) return fail(DMB_EINVAL, "null argument");
+    CU(cudaSetDevice(s->device));
+    int rc = ensure_scratch(s, sizeof(double));
+    if (rc) return rc;
+    CU(cudaMemsetAsync(s->d_scratch, 0, sizeof(double), s->stream));
+    if (purity) launch_purity(s->buf[s->cur], s->shard_elems, s->d_scratch, s->stream);
+    else launch_trace(s->buf[s->cur], layout_args(s), s->d_scratch, s->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, s->d_scratch, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return DMB_OK;
+}
+int dmb_trace(dmb_handle s, double* trace) { return reduce_scalar(s, false, trace); }
+int dmb_purity(dmb_handle s, double* purity) { return reduce_scalar(s, true, purity); }
+
+int dmb_sample(dmb_handle s, const double* r, size_t n, uint64_t* out, double* total)
+{
+    if (!s || (n && (!r || !out))) return fail(DMB_EINVAL, "null argument");
+    if (s->world != 1) return fail(DMB_ESTATE, "dmb_sample needs world_size == 1");
+    CU(cudaSetDevice(s->device));
+    const size_t dim = (size_t)1 << s->n;
+    // scratch: p[dim] | scan[dim+1] | r[n] | out[n]
+    const size_t bytes = (2 * dim + 1 + n) * sizeof(double) + n * sizeof(unsigned long long);
+    int rc = ensure_scratch(s, bytes);
+    if (rc) return rc;
+    double* d_p = s->d_scratch;
+    double* d_scan = d_p + dim;
+    double* d_r = d_scan + dim + 1;
+    unsigned long long* d_out = reinterpret_cast<unsigned long long*>(d_r + n);
+    launch_diag(s->buf[s->cur], layout_args(s), nullptr, d_p, s->stream);
+    launch_scan(d_p, d_scan, dim, s->stream);
+    if (n)
+    {
+        CU(cudaMemcpyAsync(d_r, r, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        launch_sample(d_scan, dim, d_r, n, d_out, s->stream);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out, d_out, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (total) CU(cudaMemcpyAsync(total, d_scan + dim, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    return DMB_OK;
+}
+
+int dmb_measure(dmb_handle s, unsigned seed, size_t repetition, uint64_t* out, double* total)
+{
+    // reference measure() :534-539: srand(RAND_SEED); r = rand()/RAND_MAX per shot
+    std::vector<double> r(repetition);
+    srand(seed);
+    for (size_t i = 0; i < repetition; i++) r[i] = (double)rand() / (double)RAND_MAX;
+    return dmb_sample(s, r.data(), repetition, out, total);
+}
+
+int dmb_get_shard(dmb_handle s, double* interleaved, int32_t* phys_of_logical)
+{
+    if (!s) return fail(DMB_EINVAL, "null handle");
+    CU(cudaSetDevice(s->device));
+    if (interleaved)
+    {
+        CU(cudaMemcpyAsync(interleaved, s->buf[s->cur], s->shard_elems * sizeof(double2), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    if (phys_of_logical)
+        for (int l = 0; l < s->N; l++) phys_of_logical[l] = s->layout[l];
+    return DMB_OK;
+}
+
+// ---- multi-GPU --------------------------------------------------------------------------------
+int dmb_comm_unique_id(uint8_t id[128])
+{
+    std::string why;
+    if (!load_nccl(why)) return fail(DMB_ECOMM, why);
+    ncclUniqueId u;
+    int rc = g_nccl.GetUniqueId(&u);
+    if (rc) return fail(DMB_ECOMM, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc));
+    memcpy(id, u.internal, 128);
+    return DMB_OK;
+}
+
+int dmb_comm_init(dmb_handle s, const uint8_t id[128])
+{
+    if (!s || !id) return fail(DMB_EINVAL, "null argument");
+    std::string why;
+    if (!load_nccl(why)) return fail(DMB_ECOMM, why);
+    CU(cudaSetDevice(s->device));
+    ncclUniqueId u;
+    memcpy(u.internal, id, 128);
+    int rc = g_nccl.CommInitRank(&s->comm, s->world, u, s->rank);
+    if (rc) return fail(DMB_ECOMM, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc));
+    return DMB_OK;
+}
+
+// ---- planner introspection (host only) ----------------------------------------------------------
+int64_t dmb_plan_json(int n_qubits, int world_size, const dmb_gate* gates, size_t n_gates, const double* mats,
+                      size_t n_mats, const int32_t* start_layout, int conj_state, char* out, size_t cap)
+{
+    init_options();
+    try
+    {
+        std::vector<int> start;
+        if (start_layout) start.assign(start_layout, start_layout + 2 * n_qubits);
+        Plan p = make_plan(n_qubits, world_size, gates, n_gates, mats, n_mats, start, g_opt, conj_state != 0);
+        std::string js = plan_to_json(p);
+        if (out && cap > 0)
+        {
+            const size_t ncopy = std::min(cap - 1, js.size());
+            memcpy(out, js.data(), ncopy);
+            out[ncopy] = 0;
+        }
+        return (int64_t)js.size() + 1;
+    }
+    catch (const std::invalid_argument& e)
+    {
+        return fail(DMB_EINVAL, e.what());
+    }
+    catch (const std::exception& e)
+    {
+        return fail(DMB_ESTATE, e.what());
+    }
+}
+
+} // extern "C"

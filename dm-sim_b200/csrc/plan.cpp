@@ -1,0 +1,767 @@
+// dm-sim_b200/csrc/plan.cpp -- expansion, fusion and tile scheduling (host only; see plan.hpp).
+#include "plan.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+#include <stdexcept>
+
+namespace dmb
+{
+static const double kPI = 3.14159265358979323846;  // reference src/config.hpp:55
+static const double kS2I = 0.70710678118654752440; // reference src/config.hpp:57
+
+static const char* kOpNames[] = {"U3", "U2", "U1", "CX", "ID", "X", "Y", "Z", "H", "S",
+                                 "SDG", "T", "TDG", "RX", "RY", "RZ", "CZ", "CY", "SWAP", "CH",
+                                 "CCX", "CSWAP", "CRX", "CRY", "CRZ", "CU1", "CU3", "RXX", "RZZ", "RCCX",
+                                 "RC3X", "C3X", "C3SQRTX", "C4X", "R", "SRN", "W", "RYY"};
+
+const char* op_name(int op)
+{
+    if (op >= 0 && op < DMB_OP_COUNT) return kOpNames[op];
+    if (op == DMB_OP_C1) return "C1";
+    if (op == DMB_OP_C2) return "C2";
+    return "?";
+}
+
+// ------------------------------------------------------------------------------------------------
+// Expansion: every Gate becomes the primitive sequence the reference executes for it.
+// Matrices are built from the same real expressions as the reference bodies so that the entries
+// agree to the last bit before fusion (reference lines cited per primitive).
+// ------------------------------------------------------------------------------------------------
+namespace
+{
+struct Expander
+{
+    int n;
+    std::vector<Block>& out;
+
+    void one(int q, cplx a, cplx b, cplx c, cplx d)
+    {
+        Block k;
+        k.nq = 1;
+        k.q[0] = q;
+        k.m[0] = a; k.m[1] = b; k.m[2] = c; k.m[3] = d;
+        out.push_back(k);
+    }
+    // CX_GATE :1132-1168: swap (ctrl=1,tgt=0) <-> (ctrl=1,tgt=1); index = 2*bit(ctrl)+bit(tgt)
+    void cx(int c, int t)
+    {
+        Block k;
+        k.nq = 2;
+        k.q[0] = c; k.q[1] = t;
+        for (auto& e : k.m) e = 0;
+        k.m[0] = 1; k.m[5] = 1; k.m[11] = 1; k.m[14] = 1;
+        out.push_back(k);
+    }
+    void x(int q) { one(q, 0, 1, 1, 0); }                                   // :1175-1187
+    void y(int q) { one(q, 0, cplx(0, -1), cplx(0, 1), 0); }                // :1196-1209
+    void z(int q) { one(q, 1, 0, 0, -1); }                                  // :1216-1225
+    void h(int q) { one(q, kS2I, kS2I, kS2I, -kS2I); }                      // :1232-1245
+    void s(int q) { one(q, 1, 0, 0, cplx(0, 1)); }                          // :1299-1307
+    void sdg(int q) { one(q, 1, 0, 0, cplx(0, -1)); }                       // :1314-1322
+    void t(int q) { one(q, 1, 0, 0, cplx(kS2I, kS2I)); }                    // :1329-1337
+    void tdg(int q) { one(q, 1, 0, 0, cplx(kS2I, -kS2I)); }                 // :1344-1352
+    void r(double p, int q) { one(q, 1, 0, 0, cplx(0, p)); }                // R_GATE :1283-1292 (v1 *= i*p)
+    void w(int q) { one(q, kS2I, cplx(0, -kS2I), cplx(0, -kS2I), kS2I); }   // :1787-1799
+    void u1(double l, int q) { one(q, 1, 0, 0, cplx(cos(l), sin(l))); }     // :1381-1397
+    void u2(double p, double l, int q)                                      // :1404-1418
+    {
+        one(q, kS2I, cplx(-kS2I * cos(l), -kS2I * sin(l)), cplx(kS2I * cos(p), kS2I * sin(p)),
+            cplx(kS2I * cos(p + l), kS2I * sin(p + l)));
+    }
+    void u3(double th, double p, double l, int q)                           // :1425-1440
+    {
+        one(q, cos(th / 2.), cplx(-cos(l) * sin(th / 2.), -sin(l) * sin(th / 2.)),
+            cplx(cos(p) * sin(th / 2.), sin(p) * sin(th / 2.)),
+            cplx(cos(p + l) * cos(th / 2.), sin(p + l) * cos(th / 2.)));
+    }
+    void rx(double th, int q)                                               // :1444-1459
+    {
+        double c = cos(th / 2.0), ms = -sin(th / 2.0);
+        one(q, c, cplx(0, ms), cplx(0, ms), c);
+    }
+    void ry(double th, int q)                                               // :1463-1481
+    {
+        double c = cos(th / 2.0), s_ = sin(th / 2.0);
+        one(q, c, -s_, s_, c);
+    }
+    void rz(double p, int q) { u1(p, q); }                                  // :1485-1489 (== U1)
+    void srn(int q)                                                         // :1253-1266
+    {
+        Block k;
+        k.nq = 1; k.q[0] = q; k.srn = true;
+        out.push_back(k);
+    }
+    // ---- composites :1493-1780, :1803-1813 ----
+    void cz(int a, int b) { h(b); cx(a, b); h(b); }
+    void cy(int a, int b) { sdg(b); cx(a, b); s(b); }
+    void swap(int a, int b) { cx(a, b); cx(b, a); cx(a, b); }
+    void ch(int a, int b)
+    {
+        h(b); sdg(b); cx(a, b); h(b); t(b); cx(a, b); t(b); h(b); s(b); x(b); s(a);
+    }
+    void crz(double l, int a, int b) { u1(l / 2, b); cx(a, b); u1(-l / 2, b); cx(a, b); }
+    void cu1(double l, int a, int b) { u1(l / 2, a); cx(a, b); u1(-l / 2, b); cx(a, b); u1(l / 2, b); }
+    void cu3(double th, double p, double l, int c, int t_)
+    {
+        double t1 = (l - p) / 2, t2 = th / 2, t3 = -(p + l) / 2;
+        u1(-t3, c); u1(t1, t_); cx(c, t_); u3(-t2, 0, t3, t_); cx(c, t_); u3(t2, p, 0, t_);
+    }
+    void ccx(int a, int b, int c)
+    {
+        h(c); cx(b, c); tdg(c); cx(a, c); t(c); cx(b, c); tdg(c); cx(a, c);
+        t(b); t(c); h(c); cx(a, b); t(a); tdg(b); cx(a, b);
+    }
+    void cswap(int a, int b, int c) { cx(c, b); ccx(a, b, c); cx(c, b); }
+    void crx(double l, int a, int b)
+    {
+        u1(kPI / 2, b); cx(a, b); u3(-l / 2, 0, 0, b); cx(a, b); u3(l / 2, -kPI / 2, 0, b);
+    }
+    void cry(double l, int a, int b) { u3(l / 2, 0, 0, b); cx(a, b); u3(-l / 2, 0, 0, b); cx(a, b); }
+    void rxx(double th, int a, int b)
+    {
+        u3(kPI / 2, th, 0, a); h(b); cx(a, b); u1(-th, b); cx(a, b); h(b); u2(-kPI, kPI - th, a);
+    }
+    void rzz(double th, int a, int b) { cx(a, b); u1(th, b); cx(a, b); }
+    void rccx(int a, int b, int c)
+    {
+        u2(0, kPI, c); u1(kPI / 4, c); cx(b, c); u1(-kPI / 4, c); cx(a, c); u1(kPI / 4, c); cx(b, c);
+        u1(-kPI / 4, c); u2(0, kPI, c);
+    }
+    void rc3x(int a, int b, int c, int d)
+    {
+        u2(0, kPI, d); u1(kPI / 4, d); cx(c, d); u1(-kPI / 4, d); u2(0, kPI, d); cx(a, d); u1(kPI / 4, d);
+        cx(b, d); u1(-kPI / 4, d); cx(a, d); u1(kPI / 4, d); cx(b, d); u1(-kPI / 4, d); u2(0, kPI, d);
+        u1(kPI / 4, d); cx(c, d); u1(-kPI / 4, d); u2(0, kPI, d);
+    }
+    void hcu1h(double ang, int ctl, int d) { h(d); cu1(ang, ctl, d); h(d); }
+    void c3x_like(double ang, int a, int b, int c, int d) // C3X :1698-1728, C3SQRTX :1733-1763
+    {
+        hcu1h(-ang, a, d); cx(a, b); hcu1h(ang, b, d); cx(a, b); hcu1h(-ang, b, d); cx(b, c);
+        hcu1h(ang, c, d); cx(a, c); hcu1h(-ang, c, d); cx(b, c); hcu1h(ang, c, d); cx(a, c);
+        hcu1h(-ang, c, d);
+    }
+    void c4x(int a, int b, int c, int d, int e)
+    {
+        h(e); cu1(-kPI / 2, d, e); h(e);
+        c3x_like(kPI / 4, a, b, c, d);
+        h(d); cu1(kPI / 4, d, e); h(d);
+        c3x_like(kPI / 4, a, b, c, d);
+        c3x_like(kPI / 8, a, b, c, e);
+    }
+    void ryy(double th, int a, int b)
+    {
+        rx(kPI / 2, a); rx(kPI / 2, b); cx(a, b); rz(th, b); cx(a, b); rx(-kPI / 2, a); rx(-kPI / 2, b);
+    }
+};
+
+int arity(int op)
+{
+    switch (op)
+    {
+    case DMB_OP_CX: case DMB_OP_CZ: case DMB_OP_CY: case DMB_OP_SWAP: case DMB_OP_CH: case DMB_OP_CRX:
+    case DMB_OP_CRY: case DMB_OP_CRZ: case DMB_OP_CU1: case DMB_OP_CU3: case DMB_OP_RXX: case DMB_OP_RZZ:
+    case DMB_OP_RYY: case DMB_OP_C2:
+        return 2;
+    case DMB_OP_CCX: case DMB_OP_CSWAP: case DMB_OP_RCCX:
+        return 3;
+    case DMB_OP_RC3X: case DMB_OP_C3X: case DMB_OP_C3SQRTX:
+        return 4;
+    case DMB_OP_C4X:
+        return 5;
+    default:
+        return 1;
+    }
+}
+} // namespace
+
+void expand_gates(int n_qubits, const dmb_gate* gates, size_t n_gates, const double* mats, size_t n_mats,
+                  std::vector<Block>& prims)
+{
+    Expander E{n_qubits, prims};
+    for (size_t i = 0; i < n_gates; i++)
+    {
+        const dmb_gate& g = gates[i];
+        const bool known = (g.op >= 0 && g.op < DMB_OP_COUNT) || g.op == DMB_OP_C1 || g.op == DMB_OP_C2;
+        if (!known) throw std::invalid_argument("gate " + std::to_string(i) + ": unknown op " + std::to_string(g.op));
+        // append() asserts every qb < n_qubits (reference :334-338), used or not
+        for (int k = 0; k < 5; k++)
+            if (g.qb[k] < 0 || g.qb[k] >= n_qubits)
+                throw std::invalid_argument("gate " + std::to_string(i) + " (" + op_name(g.op) + "): qubit index " +
+                                            std::to_string(g.qb[k]) + " out of range");
+        const int ar = arity(g.op);
+        for (int a = 0; a < ar; a++)
+            for (int b = a + 1; b < ar; b++)
+                if (g.qb[a] == g.qb[b])
+                    throw std::invalid_argument("gate " + std::to_string(i) + " (" + op_name(g.op) +
+                                                "): repeated qubit operand"); // reference asserts ctrl != qubit (:1051,:1139)
+        const int q0 = g.qb[0], q1 = g.qb[1], q2 = g.qb[2], q3 = g.qb[3], q4 = g.qb[4];
+        // which Gate field feeds which parameter: *_OP wrappers :1821-2008
+        switch (g.op)
+        {
+        case DMB_OP_U3: E.u3(g.theta, g.phi, g.lambda, q0); break;
+        case DMB_OP_U2: E.u2(g.phi, g.lambda, q0); break;
+        case DMB_OP_U1: E.u1(g.lambda, q0); break;
+        case DMB_OP_CX: E.cx(q0, q1); break;
+        case DMB_OP_ID: break;
+        case DMB_OP_X: E.x(q0); break;
+        case DMB_OP_Y: E.y(q0); break;
+        case DMB_OP_Z: E.z(q0); break;
+        case DMB_OP_H: E.h(q0); break;
+        case DMB_OP_S: E.s(q0); break;
+        case DMB_OP_SDG: E.sdg(q0); break;
+        case DMB_OP_T: E.t(q0); break;
+        case DMB_OP_TDG: E.tdg(q0); break;
+        case DMB_OP_RX: E.rx(g.theta, q0); break;
+        case DMB_OP_RY: E.ry(g.theta, q0); break;
+        case DMB_OP_RZ: E.rz(g.phi, q0); break;
+        case DMB_OP_CZ: E.cz(q0, q1); break;
+        case DMB_OP_CY: E.cy(q0, q1); break;
+        case DMB_OP_SWAP: E.swap(q0, q1); break;
+        case DMB_OP_CH: E.ch(q0, q1); break;
+        case DMB_OP_CCX: E.ccx(q0, q1, q2); break;
+        case DMB_OP_CSWAP: E.cswap(q0, q1, q2); break;
+        case DMB_OP_CRX: E.crx(g.lambda, q0, q1); break;
+        case DMB_OP_CRY: E.cry(g.lambda, q0, q1); break;
+        case DMB_OP_CRZ: E.crz(g.lambda, q0, q1); break;
+        case DMB_OP_CU1: E.cu1(g.lambda, q0, q1); break;
+        case DMB_OP_CU3: E.cu3(g.theta, g.phi, g.lambda, q0, q1); break;
+        case DMB_OP_RXX: E.rxx(g.theta, q0, q1); break;
+        case DMB_OP_RZZ: E.rzz(g.theta, q0, q1); break;
+        case DMB_OP_RCCX: E.rccx(q0, q1, q2); break;
+        case DMB_OP_RC3X: E.rc3x(q0, q1, q2, q3); break;
+        case DMB_OP_C3X: E.c3x_like(kPI / 4, q0, q1, q2, q3); break;
+        case DMB_OP_C3SQRTX: E.c3x_like(kPI / 8, q0, q1, q2, q3); break;
+        case DMB_OP_C4X: E.c4x(q0, q1, q2, q3, q4); break;
+        case DMB_OP_R: E.r(g.theta, q0); break;
+        case DMB_OP_SRN: E.srn(q0); break;
+        case DMB_OP_W: E.w(q0); break;
+        case DMB_OP_RYY: E.ryy(g.theta, q0, q1); break;
+        case DMB_OP_C1:
+        case DMB_OP_C2:
+        {
+            if (!mats || g.mat < 0 || (size_t)g.mat >= n_mats)
+                throw std::invalid_argument("gate " + std::to_string(i) + ": matrix index out of range");
+            const double* m = mats + 32 * (size_t)g.mat;
+            Block k;
+            k.nq = g.op == DMB_OP_C1 ? 1 : 2;
+            k.q[0] = q0;
+            k.q[1] = q1;
+            const int cnt = k.nq == 1 ? 4 : 16;
+            for (int e = 0; e < cnt; e++) k.m[e] = cplx(m[2 * e], m[2 * e + 1]);
+            prims.push_back(k);
+            break;
+        }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fusion
+// ------------------------------------------------------------------------------------------------
+namespace
+{
+void mat4_mul(const cplx* a, const cplx* b, cplx* c) // c = a*b (4x4)
+{
+    cplx t[16];
+    for (int r = 0; r < 4; r++)
+        for (int col = 0; col < 4; col++)
+        {
+            cplx s = 0;
+            for (int k = 0; k < 4; k++) s += a[r * 4 + k] * b[k * 4 + col];
+            t[r * 4 + col] = s;
+        }
+    memcpy(c, t, sizeof(t));
+}
+void mat2_mul(const cplx* a, const cplx* b, cplx* c)
+{
+    cplx t[4];
+    t[0] = a[0] * b[0] + a[1] * b[2];
+    t[1] = a[0] * b[1] + a[1] * b[3];
+    t[2] = a[2] * b[0] + a[3] * b[2];
+    t[3] = a[2] * b[1] + a[3] * b[3];
+    memcpy(c, t, sizeof(t));
+}
+// 2x2 u acting on the MSB (hi=true) or LSB factor of a 2-qubit index, as a 4x4
+void embed1(const cplx* u, bool hi, cplx* o)
+{
+    for (int i = 0; i < 16; i++) o[i] = 0;
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++)
+        {
+            int rh = r >> 1, rl = r & 1, ch = c >> 1, cl = c & 1;
+            if (hi) { if (rl == cl) o[r * 4 + c] = u[rh * 2 + ch]; }
+            else    { if (rh == ch) o[r * 4 + c] = u[rl * 2 + cl]; }
+        }
+}
+// same operator with the two qubits' roles exchanged (index bit swap)
+void swap_roles(const cplx* m, cplx* o)
+{
+    static const int p[4] = {0, 2, 1, 3};
+    cplx t[16];
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) t[p[r] * 4 + p[c]] = m[r * 4 + c];
+    memcpy(o, t, sizeof(t));
+}
+bool is_identity2(const cplx* u) { return u[0] == cplx(1) && u[3] == cplx(1) && u[1] == cplx(0) && u[2] == cplx(0); }
+} // namespace
+
+void fuse_blocks(int n, const std::vector<Block>& prims, std::vector<Block>& blocks)
+{
+    struct Pend { bool have = false; cplx u[4]; int weight = 0; };
+    std::vector<Pend> pend(n);
+    std::vector<int> open(n, -1);       // index into work[] of the open 2-qubit block on this qubit
+    std::vector<Block> work;
+
+    auto close_block = [&](int idx) {
+        if (idx < 0) return;
+        blocks.push_back(work[idx]);
+        open[work[idx].q[0]] = -1;
+        open[work[idx].q[1]] = -1;
+    };
+    auto flush_pending = [&](int q) {
+        if (!pend[q].have) return;
+        Block b;
+        b.nq = 1; b.q[0] = q; b.weight = pend[q].weight;
+        memcpy(b.m, pend[q].u, sizeof(cplx) * 4);
+        blocks.push_back(b);
+        pend[q].have = false; pend[q].weight = 0;
+    };
+
+    for (const Block& p : prims)
+    {
+        if (p.srn)
+        {
+            // SRN conjugates amplitudes (v0' = (v0 + conj(v1))/2), so it does not commute with complex-linear
+            // ops on OTHER qubits either: it is a barrier for the whole circuit.
+            for (int q = 0; q < n; q++)
+            {
+                close_block(open[q]);
+                flush_pending(q);
+            }
+            blocks.push_back(p);
+            continue;
+        }
+        if (p.nq == 1)
+        {
+            const int q = p.q[0];
+            if (open[q] >= 0)
+            {
+                Block& b = work[open[q]];
+                cplx e[16];
+                embed1(p.m, b.q[0] == q, e);
+                mat4_mul(e, b.m, b.m);
+                b.weight += p.weight;
+            }
+            else if (pend[q].have)
+            {
+                mat2_mul(p.m, pend[q].u, pend[q].u);
+                pend[q].weight += p.weight;
+            }
+            else
+            {
+                pend[q].have = true;
+                memcpy(pend[q].u, p.m, sizeof(cplx) * 4);
+                pend[q].weight = p.weight;
+            }
+            continue;
+        }
+        const int a = p.q[0], b_ = p.q[1];
+        if (open[a] >= 0 && open[a] == open[b_])
+        {
+            Block& b = work[open[a]];
+            cplx e[16];
+            if (b.q[0] == a) memcpy(e, p.m, sizeof(e));
+            else swap_roles(p.m, e);
+            mat4_mul(e, b.m, b.m);
+            b.weight += p.weight;
+            continue;
+        }
+        close_block(open[a]);
+        close_block(open[b_]);
+        Block nb = p;
+        for (int side = 0; side < 2; side++)
+        {
+            const int q = side == 0 ? a : b_;
+            if (!pend[q].have) continue;
+            if (!is_identity2(pend[q].u))
+            {
+                cplx e[16];
+                embed1(pend[q].u, side == 0, e);
+                mat4_mul(nb.m, e, nb.m);
+            }
+            nb.weight += pend[q].weight;
+            pend[q].have = false; pend[q].weight = 0;
+        }
+        work.push_back(nb);
+        open[a] = open[b_] = (int)work.size() - 1;
+    }
+    for (int q = 0; q < n; q++)
+    {
+        if (open[q] >= 0) close_block(open[q]);
+        flush_pending(q);
+    }
+}
+
+int classify(int nb, const cplx* m, int* src_out)
+{
+    int src[4] = {0, 1, 2, 3};
+    const double eps = 1e-15;
+    auto nz = [&](cplx v) { return std::abs(v.real()) > eps || std::abs(v.imag()) > eps; };
+    const int d = nb == 1 ? 2 : 4;
+    bool diag = true, mono = true;
+    for (int r = 0; r < d; r++)
+    {
+        int cnt = 0, where = -1;
+        for (int c = 0; c < d; c++)
+            if (nz(m[r * d + c]))
+            {
+                cnt++; where = c;
+                if (c != r) diag = false;
+            }
+        if (cnt > 1) mono = false;
+        if (cnt == 0) where = r; // zero row: treated as a zero phase on itself
+        src[r] = where;
+    }
+    if (mono)
+    {
+        // must be a permutation of columns (a zero row/col would make it singular; treat as dense then)
+        int seen = 0;
+        for (int r = 0; r < d; r++) seen |= 1 << src[r];
+        if (seen != (1 << d) - 1) mono = false;
+    }
+    if (src_out)
+        for (int r = 0; r < d; r++) src_out[r] = src[r];
+    if (nb == 1) return diag ? CLS_DIAG1 : (mono ? CLS_MONO1 : CLS_DENSE1);
+    return diag ? CLS_DIAG2 : (mono ? CLS_MONO2 : CLS_DENSE2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scheduling on the 2n-bit flat index
+// ------------------------------------------------------------------------------------------------
+namespace
+{
+struct FlatOp
+{
+    int nb;
+    int bit[2]; // logical bits of the 2n-bit index; bit[0] carries the matrix MSB
+    cplx m[16];
+    bool srn;
+    int weight;
+    int side; // 0 = L (row bits), 1 = R (column bits)
+    bool done = false;
+};
+
+struct Candidate
+{
+    std::vector<int> tile_logical; // logical bits in the tile, in order of admission
+    std::vector<int> picked;       // indices into ops, in execution order
+    long score = 0;
+};
+} // namespace
+
+Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, const double* mats, size_t n_mats,
+               const std::vector<int>& start_layout, const PlanOptions& opt, bool conj_state)
+{
+    if (n < 1 || n > 20) throw std::invalid_argument("n_qubits must be in [1, 20]");
+    int g = 0;
+    while ((1 << g) < world_size) g++;
+    if ((1 << g) != world_size) throw std::invalid_argument("world_size must be a power of two");
+    const int N = 2 * n, M = N - g;
+    if (g > n) throw std::invalid_argument("world_size must divide 2^n_qubits"); // reference :218-229
+    if (g > 0 && M - g < 0) throw std::invalid_argument("too many ranks for this state");
+
+    Plan plan;
+    plan.n = n; plan.g = g;
+    plan.n_gates = n_gates;
+    std::vector<Block> prims, blocks;
+    expand_gates(n, gates, n_gates, mats, n_mats, prims);
+    plan.n_primitives = prims.size();
+    fuse_blocks(n, prims, blocks);
+    plan.n_blocks = blocks.size();
+
+    // mirror: L part on bit q, R part (conjugated) on bit q+n.  SRN is real-linear and self-conjugate.
+    std::vector<FlatOp> ops;
+    ops.reserve(blocks.size() * 2);
+    for (const Block& b : blocks)
+        if (b.srn) plan.has_srn = true;
+    // With SRN in the circuit the run is strictly "all L parts, then all R parts" in program order
+    // (X = F_R F_L M0 with F_R = T F T, T = conjugate transpose), every SRN being a full barrier.
+    for (int pass = 0; pass < (plan.has_srn ? 2 : 1); pass++)
+    for (const Block& b : blocks)
+    {
+        for (int side = (plan.has_srn ? pass : 0); side < (plan.has_srn ? pass + 1 : 2); side++)
+        {
+            FlatOp f;
+            f.nb = b.nq; f.srn = b.srn; f.weight = b.weight; f.side = side;
+            f.bit[0] = b.q[0] + side * n;
+            f.bit[1] = b.nq == 2 ? b.q[1] + side * n : 0;
+            const int cnt = b.nq == 1 ? 4 : 16;
+            // on a conjugated store (conj_state) E acts as conj(E): conj(E conj(x)) = conj(E) x
+            for (int e = 0; e < cnt; e++) f.m[e] = ((side == 1) != conj_state) ? std::conj(b.m[e]) : b.m[e];
+            ops.push_back(f);
+        }
+    }
+
+    std::vector<int> phys(N);
+    if (start_layout.empty())
+        for (int l = 0; l < N; l++) phys[l] = l;
+    else
+    {
+        if ((int)start_layout.size() != N) throw std::invalid_argument("start_layout must have 2n entries");
+        phys = start_layout;
+    }
+    plan.start_layout = phys;
+
+    const int kmax = std::max(1, std::min(std::min(opt.tile_bits, 12), M));
+    const int lowb = std::max(0, std::min(opt.low_bits, kmax));
+
+    size_t n_pending = ops.size();
+    size_t first_pending = 0;
+    std::vector<int> logical_at(N);
+
+    auto build_candidate = [&](int strategy) {
+        Candidate c;
+        std::vector<char> in_tile(N, 0), blocked(N, 0);
+        for (int l = 0; l < N; l++)
+        {
+            if (phys[l] >= M) blocked[l] = 1; // rank bits: not addressable inside a shard
+            if (phys[l] < lowb) { in_tile[l] = 1; c.tile_logical.push_back(l); }
+        }
+        int tile_cnt = (int)c.tile_logical.size();
+        int n_free_bits = 0;
+        for (int l = 0; l < N; l++) n_free_bits += !blocked[l];
+        auto visit = [&](size_t i) {
+            FlatOp& f = ops[i];
+            if (f.done) return;
+            bool blk = false;
+            int need = 0;
+            for (int b = 0; b < f.nb; b++)
+            {
+                if (blocked[f.bit[b]]) blk = true;
+                else if (!in_tile[f.bit[b]]) need++;
+            }
+            if (!blk && tile_cnt + need <= kmax)
+            {
+                for (int b = 0; b < f.nb; b++)
+                    if (!in_tile[f.bit[b]]) { in_tile[f.bit[b]] = 1; c.tile_logical.push_back(f.bit[b]); tile_cnt++; }
+                c.picked.push_back((int)i);
+                c.score += f.weight;
+            }
+            else
+                for (int b = 0; b < f.nb; b++)
+                    if (!blocked[f.bit[b]]) { blocked[f.bit[b]] = 1; n_free_bits--; }
+        };
+        // strategy 0: program order (L and R interleaved); 1: all L parts first; 2: all R parts first
+        if (plan.has_srn)
+        {
+            // strict sequence order; an SRN may only run once everything before it has, and fences what follows
+            bool all_prior = true;
+            for (size_t i = first_pending; i < ops.size() && n_free_bits > 0; i++)
+            {
+                if (ops[i].done) continue;
+                if (ops[i].srn && !all_prior) break;
+                const size_t before = c.picked.size();
+                visit(i);
+                const bool took = c.picked.size() > before;
+                if (!took) all_prior = false;
+                if (ops[i].srn && !took) break;
+            }
+        }
+        else if (strategy == 0)
+        {
+            for (size_t i = first_pending; i < ops.size() && n_free_bits > 0; i++) visit(i);
+        }
+        else
+        {
+            const int first_side = strategy == 1 ? 0 : 1;
+            for (int pass = 0; pass < 2; pass++)
+            {
+                const int side = pass == 0 ? first_side : 1 - first_side;
+                for (size_t i = first_pending; i < ops.size() && n_free_bits > 0; i++)
+                    if (ops[i].side == side) visit(i);
+            }
+        }
+        return c;
+    };
+
+    auto emit_sweep = [&](const std::vector<int>& tile_logical_in, const std::vector<int>& picked,
+                          const std::vector<std::pair<int, int>>& moves /* logical -> new phys */) {
+        // pad the tile with the lowest free physical bits: longer contiguous runs, fewer larger tiles --
+        // but keep at least 2^min_tiles_log2 tiles when the state is small.
+        std::vector<int> tile_logical = tile_logical_in;
+        std::vector<char> used(N, 0);
+        for (int l : tile_logical) used[phys[l]] = 1;
+        for (int l = 0; l < N; l++) logical_at[phys[l]] = l;
+        int want = std::max((int)tile_logical.size(), std::min(kmax, M - opt.min_tiles_log2));
+        want = std::min(want, M);
+        for (int p = 0; p < M && (int)tile_logical.size() < want; p++)
+            if (!used[p]) { used[p] = 1; tile_logical.push_back(logical_at[p]); }
+        Step st;
+        st.kind = 0;
+        Sweep& sw = st.sweep;
+        sw.k = (int)tile_logical.size();
+        std::vector<int> order = tile_logical;
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return phys[a] < phys[b]; });
+        std::vector<int> local_of(N, -1);
+        for (int j = 0; j < sw.k; j++) { local_of[order[j]] = j; sw.in_pos.push_back(phys[order[j]]); }
+        for (int i : picked)
+        {
+            FlatOp& f = ops[i];
+            TileOp t;
+            t.nb = f.nb;
+            t.j0 = local_of[f.bit[0]];
+            t.j1 = f.nb == 2 ? local_of[f.bit[1]] : 0;
+            t.weight = f.weight;
+            memcpy(t.m, f.m, sizeof(t.m));
+            t.cls = f.srn ? (int)CLS_SRN1 : classify(f.nb, f.m, nullptr);
+            sw.ops.push_back(t);
+            sw.weight += f.weight;
+            f.done = true;
+            n_pending--;
+        }
+        for (auto& mv : moves) phys[mv.first] = mv.second;
+        for (int j = 0; j < sw.k; j++) sw.out_pos.push_back(phys[order[j]]);
+        sw.out_of_place = !moves.empty();
+        plan.steps.push_back(st);
+        plan.n_sweeps++;
+        while (first_pending < ops.size() && ops[first_pending].done) first_pending++;
+    };
+
+    while (n_pending > 0)
+    {
+        Candidate best;
+        bool have = false;
+        for (int s = 0; s < (plan.has_srn ? 1 : 3); s++)
+        {
+            Candidate c = build_candidate(s);
+            if (!have || c.score > best.score ||
+                (c.score == best.score && c.tile_logical.size() < best.tile_logical.size()))
+            {
+                best = c; have = true;
+            }
+        }
+        if (!best.picked.empty())
+        {
+            emit_sweep(best.tile_logical, best.picked, {});
+            continue;
+        }
+        // Stuck: every pending op needs a rank bit.  Qubit remap: pick the g local logical bits with the
+        // least pending work, move them to physical [M-g, M) (permuting sweep), then exchange.
+        if (g == 0) throw std::logic_error("scheduler stuck without rank bits");
+        std::vector<long> pending_w(N, 0);
+        for (size_t i = first_pending; i < ops.size(); i++)
+            if (!ops[i].done)
+                for (int b = 0; b < ops[i].nb; b++) pending_w[ops[i].bit[b]] += ops[i].weight;
+        // keep the partners of frontier ops that wait on a rank bit local, or the remap cannot unblock them
+        {
+            std::vector<char> seen(N, 0);
+            for (size_t i = first_pending; i < ops.size(); i++)
+            {
+                if (ops[i].done) continue;
+                bool frontier = true, on_rank = false;
+                for (int b = 0; b < ops[i].nb; b++)
+                {
+                    if (seen[ops[i].bit[b]]) frontier = false;
+                    if (phys[ops[i].bit[b]] >= M) on_rank = true;
+                }
+                if (frontier && on_rank)
+                    for (int b = 0; b < ops[i].nb; b++) pending_w[ops[i].bit[b]] += (long)1 << 40;
+                for (int b = 0; b < ops[i].nb; b++) seen[ops[i].bit[b]] = 1;
+            }
+        }
+        std::vector<int> locals;
+        for (int l = 0; l < N; l++)
+            if (phys[l] < M) locals.push_back(l);
+        std::stable_sort(locals.begin(), locals.end(), [&](int a, int b) {
+            if (pending_w[a] != pending_w[b]) return pending_w[a] < pending_w[b];
+            return phys[a] > phys[b];
+        });
+        std::vector<int> chosen(locals.begin(), locals.begin() + g);
+        // positions: chosen not already in [M-g, M) pair up with top-local bits not chosen
+        for (int l = 0; l < N; l++) logical_at[phys[l]] = l;
+        std::vector<int> a_only, b_only;
+        std::vector<char> is_chosen(N, 0);
+        for (int l : chosen) is_chosen[l] = 1;
+        for (int l : chosen)
+            if (phys[l] < M - g) a_only.push_back(l);
+        for (int p = M - g; p < M; p++)
+            if (!is_chosen[logical_at[p]]) b_only.push_back(logical_at[p]);
+        if (!a_only.empty())
+        {
+            std::vector<int> tile;
+            for (int l = 0; l < N; l++)
+                if (phys[l] < lowb) tile.push_back(l);
+            std::vector<std::pair<int, int>> moves;
+            for (size_t i = 0; i < a_only.size(); i++)
+            {
+                for (int l : {a_only[i], b_only[i]})
+                    if (std::find(tile.begin(), tile.end(), l) == tile.end()) tile.push_back(l);
+                moves.push_back({a_only[i], phys[b_only[i]]});
+                moves.push_back({b_only[i], phys[a_only[i]]});
+            }
+            if ((int)tile.size() > kmax) throw std::logic_error("remap permutation does not fit one tile");
+            emit_sweep(tile, {}, moves);
+        }
+        Step ex;
+        ex.kind = 1;
+        plan.steps.push_back(ex);
+        plan.n_exchanges++;
+        for (int l = 0; l < N; l++)
+        {
+            if (phys[l] >= M) phys[l] -= g;
+            else if (phys[l] >= M - g) phys[l] += g;
+        }
+    }
+    plan.conj_start = plan.conj_end = conj_state;
+    if (plan.has_srn)
+    {
+        for (int l = 0; l < n; l++) std::swap(phys[l], phys[l + n]);
+        plan.conj_end = !conj_state;
+    }
+    plan.end_layout = phys;
+    return plan;
+}
+
+// ------------------------------------------------------------------------------------------------
+std::string plan_to_json(const Plan& p)
+{
+    std::ostringstream o;
+    char buf[64];
+    auto num = [&](double v) { snprintf(buf, sizeof(buf), "%.17g", v); return std::string(buf); };
+    auto ivec = [&](const std::vector<int>& v) {
+        std::string s = "[";
+        for (size_t i = 0; i < v.size(); i++) s += (i ? "," : "") + std::to_string(v[i]);
+        return s + "]";
+    };
+    o << "{\"n\":" << p.n << ",\"g\":" << p.g << ",\"n_gates\":" << p.n_gates << ",\"n_primitives\":" << p.n_primitives
+      << ",\"n_blocks\":" << p.n_blocks << ",\"n_sweeps\":" << p.n_sweeps << ",\"n_exchanges\":" << p.n_exchanges
+      << ",\"has_srn\":" << (p.has_srn ? "true" : "false") << ",\"conj_start\":" << (p.conj_start ? "true" : "false")
+      << ",\"conj_end\":" << (p.conj_end ? "true" : "false") << ",\"start_layout\":" << ivec(p.start_layout)
+      << ",\"end_layout\":" << ivec(p.end_layout) << ",\"steps\":[";
+    for (size_t s = 0; s < p.steps.size(); s++)
+    {
+        const Step& st = p.steps[s];
+        if (s) o << ",";
+        if (st.kind == 1) { o << "{\"kind\":\"exchange\"}"; continue; }
+        const Sweep& sw = st.sweep;
+        o << "{\"kind\":\"sweep\",\"k\":" << sw.k << ",\"in_pos\":" << ivec(sw.in_pos) << ",\"out_pos\":" << ivec(sw.out_pos)
+          << ",\"out_of_place\":" << (sw.out_of_place ? "true" : "false") << ",\"weight\":" << sw.weight << ",\"ops\":[";
+        for (size_t i = 0; i < sw.ops.size(); i++)
+        {
+            const TileOp& t = sw.ops[i];
+            if (i) o << ",";
+            o << "{\"cls\":" << t.cls << ",\"nb\":" << t.nb << ",\"j0\":" << t.j0 << ",\"j1\":" << t.j1 << ",\"m\":[";
+            const int cnt = t.nb == 1 ? 4 : 16;
+            for (int e = 0; e < cnt; e++) o << (e ? "," : "") << num(t.m[e].real()) << "," << num(t.m[e].imag());
+            o << "]}";
+        }
+        o << "]}";
+    }
+    o << "]}";
+    return o.str();
+}
+} // namespace dmb

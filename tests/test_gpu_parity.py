@@ -1,0 +1,200 @@
+"""-m gpu: the CUDA path (through the C-ABI) against the oracle, 1e-12 absolute on every element."""
+import numpy as np
+import pytest
+
+from helpers import each_op_once, random_gates, to_complex
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12  # BASELINE.json north_star: elements and diagonal within 1e-12 absolute, trace within 1e-12 of 1
+
+
+def run_gpu(dm, n, gates, n_gpus=1):
+    sim = dm.Simulation(n, n_gpus)
+    rec, mats = dm.pack_gates(gates)
+    dm._check(dm.lib().dmb_set_circuit(sim._h, rec.ctypes.data, len(rec), mats.ctypes.data if mats.size else None,
+                                       mats.size // 32))
+    sim._uploaded = True
+    sim.run()
+    return sim
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
+def test_random_circuits_all_ops(dm, oracle_mod, n):
+    rng = np.random.default_rng(100 + n)
+    gates = random_gates(n, 60, rng)
+    sim = run_gpu(dm, n, gates)
+    re, im = sim.get_dm()
+    ore, oim = oracle_mod.Oracle(n).sim(gates).dm()
+    assert np.abs(re - ore).max() < TOL and np.abs(im - oim).max() < TOL
+    assert abs(sim.trace() - 1.0) < TOL
+    assert np.abs(sim.diag() - np.diagonal(ore)).max() < TOL
+
+
+@pytest.mark.parametrize("n", [5, 8])
+def test_each_op_alone(dm, oracle_mod, n):
+    """One op per run, after a scrambling prefix, so a wrong op cannot hide behind the others."""
+    rng = np.random.default_rng(7)
+    prefix = random_gates(n, 12, rng, names=["U3", "CX", "H", "T"], with_raw=False)
+    for g in each_op_once(n, rng):
+        gates = prefix + [g]
+        sim = run_gpu(dm, n, gates)
+        re, im = sim.get_dm()
+        ore, oim = oracle_mod.Oracle(n).sim(gates).dm()
+        err = max(np.abs(re - ore).max(), np.abs(im - oim).max())
+        assert err < TOL, f"op {g[0]} on {g[1]}: {err}"
+
+
+def test_srn_single_run(dm, oracle_mod):
+    """SRN is real-linear, not a matrix (reference :1253-1266)."""
+    n = 4
+    gates = [("H", [0], 0, 0, 0), ("U3", [1], 0.3, 0.2, 0.1), ("SRN", [1], 0, 0, 0), ("CX", [1, 2], 0, 0, 0),
+             ("SRN", [0], 0, 0, 0)]
+    sim = run_gpu(dm, n, gates)
+    re, im = sim.get_dm()
+    ore, oim = oracle_mod.Oracle(n).sim(gates).dm()
+    assert max(np.abs(re - ore).max(), np.abs(im - oim).max()) < TOL
+
+
+def test_adder_n10(dm, oracle_mod):
+    """example/adder_n10: deterministic outcome 0b1000000010 (README.md:235-244) and the full 16 MiB matrix."""
+    import importlib
+    circuits = importlib.import_module("dm-sim_b200.circuits")
+    gates = circuits.adder_n10()
+    sim = run_gpu(dm, 10, gates)
+    assert sim.last_stats["n_gates"] == 30 and sim.last_stats["n_primitives"] == 142
+    res = sim.measure(5, seed=1)
+    assert res == [0b1000000010] * 5
+    re, im = sim.get_dm()
+    ore, oim = oracle_mod.Oracle(10).sim(gates).dm()
+    assert max(np.abs(re - ore).max(), np.abs(im - oim).max()) < TOL
+
+
+def test_continuation_across_runs(dm, oracle_mod):
+    """State persists across run(); clear_circuit keeps it (reference README.md:206-210)."""
+    n = 6
+    rng = np.random.default_rng(3)
+    a, b = random_gates(n, 20, rng), random_gates(n, 20, rng)
+    sim = dm.Simulation(n, 1)
+    for part in (a, b):
+        for g in part:
+            sim.append(dm.Gate(g[0], *(list(g[1]) + [0] * (5 - len(g[1]))), theta=g[2], phi=g[3], lam=g[4],
+                               matrix=g[5] if len(g) > 5 else None))
+        sim.upload()
+        sim.run()
+        sim.clear_circuit()
+    re, im = sim.get_dm()
+    ore, oim = oracle_mod.Oracle(n).sim(a + b).dm()
+    assert max(np.abs(re - ore).max(), np.abs(im - oim).max()) < TOL
+    sim.reset()
+    d = sim.diag()
+    assert d[0] == 1.0 and np.abs(d[1:]).max() == 0.0
+
+
+def test_sampling_matches_reference_rule(dm, oracle_mod):
+    n = 8
+    rng = np.random.default_rng(11)
+    gates = random_gates(n, 40, rng)
+    sim = run_gpu(dm, n, gates)
+    o = oracle_mod.Oracle(n).sim(gates)
+    r = rng.uniform(0, 1, size=500)
+    r[:3] = [0.0, 1.0, 0.999999999999]
+    got, total = sim.sample(r)
+    want = o.sample_with_r(r)
+    # a draw within 1e-12 of a bin edge may legitimately land in the neighbouring bin
+    scan = np.concatenate([[0.0], np.cumsum(np.abs(o.diag()))])
+    near_edge = np.min(np.abs(scan[None, :] - r[:, None]), axis=1) < 1e-12
+    assert np.all((got == want) | near_edge)
+    assert abs(total - scan[-1]) < TOL
+    # measure() with the reference's generator
+    m_gpu = sim.measure(20, seed=1234)
+    m_ref, _ = o.measure(20, seed=1234)
+    assert m_gpu == [int(x) for x in m_ref]
+
+
+def test_purity_and_set_dm(dm):
+    n = 5
+    rng = np.random.default_rng(5)
+    dim = 1 << n
+    a = rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))
+    rho = a @ a.conj().T
+    rho /= np.trace(rho).real
+    sim = dm.Simulation(n, 1)
+    stored = rho.T  # the engine stores rho^T, [col][row]
+    sim.set_dm(np.ascontiguousarray(stored.real), np.ascontiguousarray(stored.imag))
+    assert abs(sim.trace() - 1.0) < TOL
+    assert abs(sim.purity() - np.sum(np.abs(rho) ** 2)) < 1e-12
+    re, im = sim.get_dm()
+    assert np.array_equal(re, stored.real) and np.array_equal(im, stored.imag)
+
+
+def test_mixed_state_gate_application(dm, oracle_mod):
+    """Gates on a non-pure, non-trivial state (set_dm / set_state on both sides)."""
+    n = 5
+    rng = np.random.default_rng(6)
+    dim = 1 << n
+    a = rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))
+    rho = a @ a.conj().T
+    rho /= np.trace(rho).real
+    stored = np.ascontiguousarray(rho.T)
+    gates = random_gates(n, 30, rng)
+    sim = dm.Simulation(n, 1)
+    sim.set_dm(np.ascontiguousarray(stored.real), np.ascontiguousarray(stored.imag))
+    rec, mats = dm.pack_gates(gates)
+    dm._check(dm.lib().dmb_set_circuit(sim._h, rec.ctypes.data, len(rec), mats.ctypes.data if mats.size else None,
+                                       mats.size // 32))
+    sim._uploaded = True
+    sim.run()
+    re, im = sim.get_dm()
+    o = oracle_mod.Oracle(n)
+    o.lib.orc_set_state(o.h, np.ascontiguousarray(stored.real).ctypes.data, np.ascontiguousarray(stored.imag).ctypes.data)
+    ore, oim = o.sim(gates).dm()
+    assert max(np.abs(re - ore).max(), np.abs(im - oim).max()) < TOL
+
+
+@pytest.mark.parametrize("opts", [dict(tile_bits=12, low_bits=3), dict(tile_bits=8, low_bits=2),
+                                  dict(tile_bits=10, low_bits=5), dict(tile_bits=6, low_bits=0)])
+def test_tile_geometries(dm, oracle_mod, opts):
+    """Same circuit under different tile sizes / contiguous-run lengths (many sweeps, arbitrary tile bit sets)."""
+    n = 9
+    rng = np.random.default_rng(21)
+    gates = random_gates(n, 80, rng)
+    try:
+        for k, v in opts.items():
+            dm.set_option(k, v)
+        dm.set_option("min_tiles_log2", 4)
+        sim = run_gpu(dm, n, gates)
+        re, im = sim.get_dm()
+    finally:
+        dm.set_option("tile_bits", 12); dm.set_option("low_bits", 3); dm.set_option("min_tiles_log2", 10)
+    ore, oim = oracle_mod.Oracle(n).sim(gates).dm()
+    assert max(np.abs(re - ore).max(), np.abs(im - oim).max()) < TOL
+
+
+def test_graph_and_stream_paths_agree(dm):
+    n = 8
+    rng = np.random.default_rng(31)
+    gates = random_gates(n, 50, rng)
+    outs = []
+    for graph in (1, 0):
+        dm.set_option("graph", graph)
+        dm.set_option("tile_bits", 8)
+        try:
+            sim = run_gpu(dm, n, gates)
+            outs.append(sim.get_dm())
+        finally:
+            dm.set_option("graph", 1); dm.set_option("tile_bits", 12)
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_large_n13_properties_and_parity(dm, oracle_mod):
+    """n = 13 (1 GiB state): full-matrix parity on a short circuit (oracle needs ~4 GiB and a few seconds)."""
+    n = 13
+    rng = np.random.default_rng(41)
+    gates = random_gates(n, 24, rng, names=["U3", "CX", "H", "T", "RZ", "CU1", "C1", "C2"], with_raw=False)
+    sim = run_gpu(dm, n, gates)
+    assert abs(sim.trace() - 1.0) < TOL
+    assert abs(sim.purity() - 1.0) < 1e-11  # unitary circuit from a pure state
+    re, im = sim.get_dm()
+    ore, oim = oracle_mod.Oracle(n).sim(gates).dm()
+    assert max(np.abs(re - ore).max(), np.abs(im - oim).max()) < TOL
+    assert np.abs(re - re.T).max() < TOL and np.abs(im + im.T).max() < TOL  # Hermitian
