@@ -93,6 +93,10 @@ def workload(name):
         return 10, circuits.adder_n10()
     if fam == "random_c1c2":
         return n, circuits.random_c1c2(n, 256)
+    if fam == "single":   # one gate = one sweep with 2 ops: the memory pipeline of the sweep kernel
+        return n, [("H", [5], 0.0, 0.0, 0.0)]
+    if fam == "hlayer":   # one dense 1-qubit gate per qubit
+        return n, [("H", [q], 0.0, 0.0, 0.0) for q in range(n)]
     raise SystemExit(f"unknown workload {name}")
 
 

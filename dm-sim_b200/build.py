@@ -38,8 +38,8 @@ def _run(cmd, verbose):
 
 
 def core_sources():
-    srcs = [os.path.join(CSRC, f) for f in ("plan.cpp", "kernels.cu", "capi.cu")]
-    hdrs = [os.path.join(CSRC, f) for f in ("plan.hpp", "kernels.cuh")] + [os.path.join(ROOT, "include", "dmsim_b200.h")]
+    srcs = [os.path.join(CSRC, f) for f in ("plan.cpp", "encode.cpp", "kernels.cu", "capi.cu")]
+    hdrs = [os.path.join(CSRC, f) for f in ("plan.hpp", "kernels.cuh", "devop.hpp", "encode.hpp")] + [os.path.join(ROOT, "include", "dmsim_b200.h")]
     return srcs, hdrs
 
 

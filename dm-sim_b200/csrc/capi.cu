@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/dmsim_b200.h"
+#include "encode.hpp"
 #include "kernels.cuh"
 #include "plan.hpp"
 
@@ -130,7 +131,11 @@ struct dmb_sim
     bool plan_conj = false;
     DevOp* d_ops = nullptr;
     size_t d_ops_cap = 0;
-    std::vector<size_t> op_offset; // per step
+    std::vector<size_t> op_offset;    // per step: first DevOp
+    std::vector<size_t> group_offset; // per step: first DevGroup
+    std::vector<int> n_dev_ops, n_dev_groups;
+    DevGroup* d_groups = nullptr;
+    size_t d_groups_cap = 0;
     cudaGraphExec_t graph_exec = nullptr;
     int graph_cur = -1;
     uint64_t h2d_bytes = 0;
@@ -243,6 +248,7 @@ int dmb_destroy(dmb_handle s)
     if (s->buf[0]) cudaFree(s->buf[0]);
     if (s->buf[1]) cudaFree(s->buf[1]);
     if (s->d_ops) cudaFree(s->d_ops);
+    if (s->d_groups) cudaFree(s->d_groups);
     if (s->d_scratch) cudaFree(s->d_scratch);
     delete s;
     return DMB_OK;
@@ -287,72 +293,6 @@ int dmb_set_dm(dmb_handle s, const double* real, const double* imag)
 }
 
 // ---- circuit ----------------------------------------------------------------------------------
-static void encode_op(const TileOp& t, DevOp& d)
-{
-    memset(&d, 0, sizeof(d));
-    d.cls = t.cls; d.j0 = t.j0; d.j1 = t.j1;
-    const cplx one(1.0, 0.0);
-    auto put = [&](int i, cplx v) { d.m[i] = make_double2(v.real(), v.imag()); };
-    switch (t.cls)
-    {
-    case CLS_DENSE2:
-        for (int i = 0; i < 16; i++) put(i, t.m[i]);
-        break;
-    case CLS_DENSE1:
-        for (int i = 0; i < 4; i++) put(i, t.m[i]);
-        break;
-    case CLS_DIAG2:
-    {
-        int skip = 0;
-        for (int r = 0; r < 4; r++)
-        {
-            put(r, t.m[r * 5]);
-            if (t.m[r * 5] == one) skip |= 1 << r;
-        }
-        d.aux = skip << 8;
-        break;
-    }
-    case CLS_DIAG1:
-    {
-        int skip = 0;
-        for (int r = 0; r < 2; r++)
-        {
-            put(r, t.m[r * 3]);
-            if (t.m[r * 3] == one) skip |= 1 << r;
-        }
-        d.aux = skip << 8;
-        break;
-    }
-    case CLS_MONO2:
-    {
-        int src[4];
-        classify(2, t.m, src);
-        int aux = 0, skip = 0;
-        bool unit = true;
-        for (int r = 0; r < 4; r++)
-        {
-            const cplx ph = t.m[r * 4 + src[r]];
-            put(r, ph);
-            aux |= src[r] << (2 * r);
-            if (ph != one) unit = false;
-            if (src[r] == r && ph == one) skip |= 1 << r;
-        }
-        d.aux = aux | (skip << 8) | ((unit ? 1 : 0) << 12);
-        break;
-    }
-    case CLS_MONO1:
-    {
-        put(0, t.m[1]);
-        put(1, t.m[2]);
-        const bool unit = (t.m[1] == one && t.m[2] == one);
-        d.aux = (unit ? 1 : 0) << 12;
-        break;
-    }
-    default:
-        break;
-    }
-}
-
 static int build_plan(dmb_sim* s)
 {
     try
@@ -371,19 +311,25 @@ static int build_plan(dmb_sim* s)
     s->plan_layout = s->layout;
     s->plan_conj = s->conj_flag;
     drop_graph(s);
-    // device op table: one contiguous upload (the reference does 3 CUDA calls per gate per GPU, :112-163)
+    // device op / group tables: one contiguous upload each (the reference does 3 CUDA calls per gate per GPU, :112-163)
     std::vector<DevOp> host_ops;
-    s->op_offset.assign(s->plan.steps.size(), 0);
-    for (size_t i = 0; i < s->plan.steps.size(); i++)
+    std::vector<DevGroup> host_groups;
+    const size_t nsteps = s->plan.steps.size();
+    s->op_offset.assign(nsteps, 0);
+    s->group_offset.assign(nsteps, 0);
+    s->n_dev_ops.assign(nsteps, 0);
+    s->n_dev_groups.assign(nsteps, 0);
+    EncodedSweep enc;
+    for (size_t i = 0; i < nsteps; i++)
     {
         s->op_offset[i] = host_ops.size();
+        s->group_offset[i] = host_groups.size();
         if (s->plan.steps[i].kind != 0) continue;
-        for (const TileOp& t : s->plan.steps[i].sweep.ops)
-        {
-            DevOp d;
-            encode_op(t, d);
-            host_ops.push_back(d);
-        }
+        encode_sweep(s->plan.steps[i].sweep, enc);
+        s->n_dev_ops[i] = (int)enc.ops.size();
+        s->n_dev_groups[i] = (int)enc.groups.size();
+        host_ops.insert(host_ops.end(), enc.ops.begin(), enc.ops.end());
+        host_groups.insert(host_groups.end(), enc.groups.begin(), enc.groups.end());
     }
     CU(cudaSetDevice(s->device));
     if (host_ops.size() > s->d_ops_cap)
@@ -394,10 +340,20 @@ static int build_plan(dmb_sim* s)
         CU(cudaMalloc(&s->d_ops, host_ops.size() * sizeof(DevOp)));
         s->d_ops_cap = host_ops.size();
     }
-    s->h2d_bytes = host_ops.size() * sizeof(DevOp);
+    if (host_groups.size() > s->d_groups_cap)
+    {
+        if (s->d_groups) cudaFree(s->d_groups);
+        s->d_groups = nullptr;
+        s->d_groups_cap = 0;
+        CU(cudaMalloc(&s->d_groups, host_groups.size() * sizeof(DevGroup)));
+        s->d_groups_cap = host_groups.size();
+    }
+    s->h2d_bytes = host_ops.size() * sizeof(DevOp) + host_groups.size() * sizeof(DevGroup);
     if (!host_ops.empty())
     {
         CU(cudaMemcpyAsync(s->d_ops, host_ops.data(), host_ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->d_groups, host_groups.data(), host_groups.size() * sizeof(DevGroup), cudaMemcpyHostToDevice,
+                           s->stream));
         CU(cudaStreamSynchronize(s->stream));
     }
     return DMB_OK;
@@ -427,34 +383,17 @@ int dmb_clear_circuit(dmb_handle s)
 }
 
 // ---- execution --------------------------------------------------------------------------------
-static void fill_sweep_args(const dmb_sim* s, const Sweep& sw, size_t op_off, const double2* in, double2* out, SweepArgs& a)
+static void fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, double2* out, SweepArgs& a)
 {
     memset(&a, 0, sizeof(a));
-    a.in = in; a.out = out;
-    a.ops = s->d_ops + op_off;
-    a.n_ops = (int)sw.ops.size();
-    a.k = sw.k;
-    a.n_comp = s->M - sw.k;
-    a.n_tiles = 1ull << a.n_comp;
-    // load: loop bit i <-> tile-local bit i <-> physical in_pos[i] (ascending by construction)
-    for (int i = 0; i < sw.k; i++) a.gin[i] = (unsigned char)sw.in_pos[i];
-    // store: enumerate in ascending output position
-    std::vector<int> ord(sw.k);
-    for (int i = 0; i < sw.k; i++) ord[i] = i;
-    std::sort(ord.begin(), ord.end(), [&](int x, int y) { return sw.out_pos[x] < sw.out_pos[y]; });
-    for (int i = 0; i < sw.k; i++)
-    {
-        a.gout[i] = (unsigned char)sw.out_pos[ord[i]];
-        a.sout[i] = (unsigned char)ord[i];
-    }
-    std::vector<char> used_in(s->M, 0), used_out(s->M, 0);
-    for (int i = 0; i < sw.k; i++) { used_in[sw.in_pos[i]] = 1; used_out[sw.out_pos[i]] = 1; }
-    int ci = 0, co = 0;
-    for (int p = 0; p < s->M; p++)
-    {
-        if (!used_in[p]) a.cin[ci++] = (unsigned char)p;
-        if (!used_out[p]) a.cout[co++] = (unsigned char)p;
-    }
+    const Sweep& sw = s->plan.steps[step].sweep;
+    fill_sweep_tables(sw, s->M, a);
+    a.in = in;
+    a.out = out;
+    a.ops = s->d_ops + s->op_offset[step];
+    a.groups = s->d_groups + s->group_offset[step];
+    a.n_ops = s->n_dev_ops[step];
+    a.n_groups = s->n_dev_groups[step];
 }
 
 // enqueue every step of the plan on s->stream; cur is updated as buffers flip
@@ -476,8 +415,8 @@ static int enqueue_steps(dmb_sim* s, int& cur, uint64_t& launches, bool allow_ex
                 out = s->buf[cur ^ 1];
             }
             SweepArgs a;
-            fill_sweep_args(s, sw, s->op_offset[i], in, out, a);
-            const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)sweep_max_grid(sw.k));
+            fill_sweep_args(s, i, in, out, a);
+            const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)sweep_max_grid(a));
             launch_sweep(a, grid, s->stream);
             CU(cudaGetLastError());
             launches++;
@@ -546,8 +485,7 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
                     int rc = ensure_second_buffer(s);
                     if (rc) return rc;
                 }
-            for (const Step& st : s->plan.steps)
-                if (st.kind == 0) sweep_max_grid(st.sweep.k); // attribute setup must not happen inside capture
+            sweep_setup(); // attribute setup must not happen inside capture
             cudaGraph_t graph = nullptr;
             CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
             int c2 = s->cur;
@@ -748,7 +686,18 @@ int64_t dmb_plan_json(int n_qubits, int world_size, const dmb_gate* gates, size_
         std::vector<int> start;
         if (start_layout) start.assign(start_layout, start_layout + 2 * n_qubits);
         Plan p = make_plan(n_qubits, world_size, gates, n_gates, mats, n_mats, start, g_opt, conj_state != 0);
-        std::string js = plan_to_json(p);
+        std::vector<std::string> extra(p.steps.size());
+        for (size_t i = 0; i < p.steps.size(); i++)
+        {
+            if (p.steps[i].kind != 0) continue;
+            EncodedSweep enc;
+            encode_sweep(p.steps[i].sweep, enc);
+            SweepArgs a;
+            memset(&a, 0, sizeof(a));
+            fill_sweep_tables(p.steps[i].sweep, 2 * n_qubits - p.g, a);
+            extra[i] = encoded_to_json(enc, a);
+        }
+        std::string js = plan_to_json(p, &extra);
         if (out && cap > 0)
         {
             const size_t ncopy = std::min(cap - 1, js.size());

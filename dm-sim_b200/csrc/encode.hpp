@@ -1,0 +1,21 @@
+// dm-sim_b200/csrc/encode.hpp -- host encoder of planned sweeps into device tables (see encode.cpp).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "devop.hpp"
+#include "plan.hpp"
+
+namespace dmb
+{
+struct EncodedSweep
+{
+    std::vector<DevOp> ops;
+    std::vector<DevGroup> groups;
+};
+void encode_sweep(const Sweep& sw, EncodedSweep& out);
+// fills k, n_comp, n_tiles and every address table of `a` (pointers / counts are the caller's job)
+void fill_sweep_tables(const Sweep& sw, int M, SweepArgs& a);
+// JSON text of the device tables of one sweep (for the CPU test-suite's kernel-indexing emulator)
+std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a);
+} // namespace dmb

@@ -18,12 +18,6 @@ namespace dmb
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned swz(unsigned e) { return e ^ ((e >> 3) & 7u); }
 
-__device__ __forceinline__ unsigned insert0(unsigned x, int pos)
-{
-    const unsigned low = x & ((1u << pos) - 1u);
-    return ((x >> pos) << (pos + 1)) | low;
-}
-
 __device__ __forceinline__ double2 cmul(double2 a, double2 b)
 {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -46,134 +40,112 @@ __device__ __forceinline__ void st_stream(double2* p, double2 v)
 }
 
 // ------------------------------------------------------------------------------------------------
-// op bodies: every thread of the CTA walks the pairs / quads of the tile
+// op bodies.  A warp owns the sub-tile selected by its group's warp bits and walks the op's work items
+// (pairs / quads): item = lane + 32*iter, tile index = lane_tab[lane] ^ iter_tab[iter] ^ wpart ^ off[member]
+// (every term pre-swizzled by the host encoder).  Ops, tables and matrices are read from shared memory.
 // ------------------------------------------------------------------------------------------------
-template <int NT>
-__device__ __forceinline__ void op_dense2(double2* tile, const DevOp* __restrict__ op, int k, int t)
+__device__ __forceinline__ const double2* op_m(const DevOp* op) { return reinterpret_cast<const double2*>(op->m); }
+
+__device__ __forceinline__ void w_dense2(double2* tile, const DevOp* op, unsigned base, int n_iter)
 {
-    const int j0 = op->j0, j1 = op->j1;
-    const int lo = min(j0, j1), hi = max(j0, j1);
-    const unsigned b0 = 1u << j0, b1 = 1u << j1;
     double2 m[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) m[i] = __ldg(&op->m[i]);
-    const unsigned nquads = 1u << (k - 2);
-    for (unsigned g = t; g < nquads; g += NT)
+    for (int i = 0; i < 16; i++) m[i] = op_m(op)[i];
+    const unsigned o1 = op->off[1], o2 = op->off[2], o3 = op->off[3];
+    for (int it = 0; it < n_iter; it++)
     {
-        const unsigned x = insert0(insert0(g, lo), hi);
-        const unsigned i0 = swz(x), i1 = swz(x | b1), i2 = swz(x | b0), i3 = swz(x | b0 | b1);
+        const unsigned i0 = base ^ op->iter_tab[it];
+        const unsigned i1 = i0 ^ o1, i2 = i0 ^ o2, i3 = i0 ^ o3;
         const double2 v0 = tile[i0], v1 = tile[i1], v2 = tile[i2], v3 = tile[i3];
-        double2 o0 = cfma(m[3], v3, cfma(m[2], v2, cfma(m[1], v1, cmul(m[0], v0))));
-        double2 o1 = cfma(m[7], v3, cfma(m[6], v2, cfma(m[5], v1, cmul(m[4], v0))));
-        double2 o2 = cfma(m[11], v3, cfma(m[10], v2, cfma(m[9], v1, cmul(m[8], v0))));
-        double2 o3 = cfma(m[15], v3, cfma(m[14], v2, cfma(m[13], v1, cmul(m[12], v0))));
-        tile[i0] = o0; tile[i1] = o1; tile[i2] = o2; tile[i3] = o3;
+        tile[i0] = cfma(m[3], v3, cfma(m[2], v2, cfma(m[1], v1, cmul(m[0], v0))));
+        tile[i1] = cfma(m[7], v3, cfma(m[6], v2, cfma(m[5], v1, cmul(m[4], v0))));
+        tile[i2] = cfma(m[11], v3, cfma(m[10], v2, cfma(m[9], v1, cmul(m[8], v0))));
+        tile[i3] = cfma(m[15], v3, cfma(m[14], v2, cfma(m[13], v1, cmul(m[12], v0))));
     }
 }
 
-template <int NT>
-__device__ __forceinline__ void op_mono2(double2* tile, const DevOp* __restrict__ op, int k, int t)
+__device__ __forceinline__ void w_mono2(double2* tile, const DevOp* op, unsigned base, int n_iter)
 {
-    const int j0 = op->j0, j1 = op->j1, aux = op->aux;
-    const int lo = min(j0, j1), hi = max(j0, j1);
-    const unsigned b0 = 1u << j0, b1 = 1u << j1;
+    const int aux = op->aux;
+    const int skip = (aux >> 8) & 15;
+    const bool unit = (aux >> 12) & 1;
     unsigned off[4], soff[4];
     double2 ph[4];
 #pragma unroll
     for (int r = 0; r < 4; r++)
     {
-        off[r] = ((r & 2) ? b0 : 0u) | ((r & 1) ? b1 : 0u);
-        const int s = (aux >> (2 * r)) & 3;
-        soff[r] = ((s & 2) ? b0 : 0u) | ((s & 1) ? b1 : 0u);
-        ph[r] = __ldg(&op->m[r]);
+        off[r] = op->off[r];
+        soff[r] = op->off[(aux >> (2 * r)) & 3];
+        ph[r] = op_m(op)[r];
     }
-    const int skip = (aux >> 8) & 15;
-    const bool unit = (aux >> 12) & 1;
-    const unsigned nquads = 1u << (k - 2);
-    for (unsigned g = t; g < nquads; g += NT)
+    for (int it = 0; it < n_iter; it++)
     {
-        const unsigned x = insert0(insert0(g, lo), hi);
+        const unsigned x = base ^ op->iter_tab[it];
         double2 v[4];
 #pragma unroll
         for (int r = 0; r < 4; r++)
-            if (!((skip >> r) & 1)) v[r] = tile[swz(x | soff[r])];
+            if (!((skip >> r) & 1)) v[r] = tile[x ^ soff[r]];
 #pragma unroll
         for (int r = 0; r < 4; r++)
-            if (!((skip >> r) & 1)) tile[swz(x | off[r])] = unit ? v[r] : cmul(ph[r], v[r]);
+            if (!((skip >> r) & 1)) tile[x ^ off[r]] = unit ? v[r] : cmul(ph[r], v[r]);
     }
 }
 
-template <int NT>
-__device__ __forceinline__ void op_diag2(double2* tile, const DevOp* __restrict__ op, int k, int t)
+__device__ __forceinline__ void w_diag2(double2* tile, const DevOp* op, unsigned base, int n_iter)
 {
-    const int j0 = op->j0, j1 = op->j1, aux = op->aux;
-    const int lo = min(j0, j1), hi = max(j0, j1);
-    const unsigned b0 = 1u << j0, b1 = 1u << j1;
-    const int skip = (aux >> 8) & 15;
-    const unsigned nquads = 1u << (k - 2);
+    const int skip = (op->aux >> 8) & 15;
 #pragma unroll
     for (int r = 0; r < 4; r++)
     {
         if ((skip >> r) & 1) continue;
-        const double2 d = __ldg(&op->m[r]);
-        const unsigned o = ((r & 2) ? b0 : 0u) | ((r & 1) ? b1 : 0u);
-        for (unsigned g = t; g < nquads; g += NT)
+        const double2 d = op_m(op)[r];
+        const unsigned b = base ^ op->off[r];
+        for (int it = 0; it < n_iter; it++)
         {
-            const unsigned i = swz(insert0(insert0(g, lo), hi) | o);
+            const unsigned i = b ^ op->iter_tab[it];
             tile[i] = cmul(d, tile[i]);
         }
     }
 }
 
-template <int NT>
-__device__ __forceinline__ void op_dense1(double2* tile, const DevOp* __restrict__ op, int k, int t)
+__device__ __forceinline__ void w_dense1(double2* tile, const DevOp* op, unsigned base, int n_iter)
 {
-    const int j = op->j0;
-    const unsigned b = 1u << j;
-    const double2 m0 = __ldg(&op->m[0]), m1 = __ldg(&op->m[1]), m2 = __ldg(&op->m[2]), m3 = __ldg(&op->m[3]);
-    const unsigned npairs = 1u << (k - 1);
-    for (unsigned g = t; g < npairs; g += NT)
+    const double2 m0 = op_m(op)[0], m1 = op_m(op)[1], m2 = op_m(op)[2], m3 = op_m(op)[3];
+    const unsigned o1 = op->off[1];
+    for (int it = 0; it < n_iter; it++)
     {
-        const unsigned x = insert0(g, j);
-        const unsigned i0 = swz(x), i1 = swz(x | b);
+        const unsigned i0 = base ^ op->iter_tab[it], i1 = i0 ^ o1;
         const double2 v0 = tile[i0], v1 = tile[i1];
         tile[i0] = cfma(m1, v1, cmul(m0, v0));
         tile[i1] = cfma(m3, v1, cmul(m2, v0));
     }
 }
 
-template <int NT>
-__device__ __forceinline__ void op_diag1(double2* tile, const DevOp* __restrict__ op, int k, int t)
+__device__ __forceinline__ void w_diag1(double2* tile, const DevOp* op, unsigned base, int n_iter)
 {
-    const int j = op->j0, aux = op->aux;
-    const unsigned b = 1u << j;
-    const int skip = (aux >> 8) & 3;
-    const unsigned npairs = 1u << (k - 1);
+    const int skip = (op->aux >> 8) & 3;
 #pragma unroll
     for (int r = 0; r < 2; r++)
     {
         if ((skip >> r) & 1) continue;
-        const double2 d = __ldg(&op->m[r]);
-        for (unsigned g = t; g < npairs; g += NT)
+        const double2 d = op_m(op)[r];
+        const unsigned b = base ^ op->off[r];
+        for (int it = 0; it < n_iter; it++)
         {
-            const unsigned i = swz(insert0(g, j) | (r ? b : 0u));
+            const unsigned i = b ^ op->iter_tab[it];
             tile[i] = cmul(d, tile[i]);
         }
     }
 }
 
-template <int NT>
-__device__ __forceinline__ void op_mono1(double2* tile, const DevOp* __restrict__ op, int k, int t)
+__device__ __forceinline__ void w_mono1(double2* tile, const DevOp* op, unsigned base, int n_iter)
 {
-    const int j = op->j0;
-    const unsigned b = 1u << j;
-    const double2 m0 = __ldg(&op->m[0]), m1 = __ldg(&op->m[1]);
+    const double2 m0 = op_m(op)[0], m1 = op_m(op)[1];
     const bool unit = (op->aux >> 12) & 1;
-    const unsigned npairs = 1u << (k - 1);
-    for (unsigned g = t; g < npairs; g += NT)
+    const unsigned o1 = op->off[1];
+    for (int it = 0; it < n_iter; it++)
     {
-        const unsigned x = insert0(g, j);
-        const unsigned i0 = swz(x), i1 = swz(x | b);
+        const unsigned i0 = base ^ op->iter_tab[it], i1 = i0 ^ o1;
         const double2 v0 = tile[i0], v1 = tile[i1];
         tile[i0] = unit ? v1 : cmul(m0, v1);
         tile[i1] = unit ? v0 : cmul(m1, v0);
@@ -181,16 +153,12 @@ __device__ __forceinline__ void op_mono1(double2* tile, const DevOp* __restrict_
 }
 
 // reference SRN_GATE (:1253-1266): re0'=re1'=(re0+re1)/2, im0'=(im0-im1)/2, im1'=(-im0+im1)/2
-template <int NT>
-__device__ __forceinline__ void op_srn1(double2* tile, const DevOp* __restrict__ op, int k, int t)
+__device__ __forceinline__ void w_srn1(double2* tile, const DevOp* op, unsigned base, int n_iter)
 {
-    const int j = op->j0;
-    const unsigned b = 1u << j;
-    const unsigned npairs = 1u << (k - 1);
-    for (unsigned g = t; g < npairs; g += NT)
+    const unsigned o1 = op->off[1];
+    for (int it = 0; it < n_iter; it++)
     {
-        const unsigned x = insert0(g, j);
-        const unsigned i0 = swz(x), i1 = swz(x | b);
+        const unsigned i0 = base ^ op->iter_tab[it], i1 = i0 ^ o1;
         const double2 v0 = tile[i0], v1 = tile[i1];
         const double re = 0.5 * (v0.x + v1.x);
         tile[i0] = make_double2(re, 0.5 * (v0.y - v1.y));
@@ -199,19 +167,36 @@ __device__ __forceinline__ void op_srn1(double2* tile, const DevOp* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// the sweep kernel
+// the sweep kernel: persistent CTAs, 2 per SM; shared memory = [tile | op table | group table]
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTileThreads, 2) sweep_kernel(const __grid_constant__ SweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* tile = reinterpret_cast<double2*>(smem_raw);
-    constexpr int NT = kTileThreads;
-    const int t = threadIdx.x;
     const int k = a.k;
     const unsigned tile_elems = 1u << k;
-    const int klo = k < 8 ? k : 8;
+    double2* tile = reinterpret_cast<double2*>(smem_raw);
+    DevOp* s_ops = reinterpret_cast<DevOp*>(smem_raw + (size_t)16 * tile_elems);
+    DevGroup* s_groups = reinterpret_cast<DevGroup*>(s_ops + a.n_ops);
+    constexpr int NT = kTileThreads;
+    const int t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
 
-    // per-thread part of the address maps (low 8 loop bits come from the thread index)
+    // stage the op / group tables once per CTA (every tile runs the same program)
+    {
+        const int4* src = reinterpret_cast<const int4*>(a.ops);
+        int4* dst = reinterpret_cast<int4*>(s_ops);
+        const int n16 = a.n_ops * (int)(sizeof(DevOp) / 16);
+        for (int i = t; i < n16; i += NT) dst[i] = __ldg(src + i);
+        const int4* gsrc = reinterpret_cast<const int4*>(a.groups);
+        int4* gdst = reinterpret_cast<int4*>(s_groups);
+        const int g16 = a.n_groups * (int)(sizeof(DevGroup) / 16);
+        for (int i = t; i < g16; i += NT) gdst[i] = __ldg(gsrc + i);
+    }
+
+    // per-thread part of the address maps (the low 8 loop bits come from the thread index)
+    const int klo = k < 8 ? k : 8;
+    const int n_it = k <= 8 ? 1 : (1 << (k - 8));
+    const bool t_active = (unsigned)t < tile_elems;
     unsigned long long g_in_lo = 0, g_out_lo = 0;
     unsigned s_out_lo = 0;
     for (int i = 0; i < klo; i++)
@@ -221,6 +206,11 @@ __global__ void __launch_bounds__(kTileThreads, 2) sweep_kernel(const __grid_con
         g_out_lo |= bit << a.gout[i];
         s_out_lo |= (unsigned)bit << a.sout[i];
     }
+    s_out_lo = swz(s_out_lo);
+    const unsigned s_in = swz((unsigned)t);
+    const double2* __restrict__ gin = reinterpret_cast<const double2*>(a.in);
+    double2* __restrict__ gout = reinterpret_cast<double2*>(a.out);
+    __syncthreads();
 
     for (unsigned long long tile_id = blockIdx.x; tile_id < a.n_tiles; tile_id += gridDim.x)
     {
@@ -231,81 +221,91 @@ __global__ void __launch_bounds__(kTileThreads, 2) sweep_kernel(const __grid_con
             base_in |= bit << a.cin[i];
             base_out |= bit << a.cout[i];
         }
-        // ---- load: 128-bit async copies, >= 2^low_bits * 16 B contiguous per run ----
-        for (unsigned f = t; f < tile_elems; f += NT)
+        // ---- load: 128-bit async copies straight into the swizzled tile; runs of >= 2^low_bits * 16 B ----
+        if (t_active)
         {
-            unsigned long long g = base_in | g_in_lo;
-            const unsigned hi = f >> 8;
-            for (int i = 8; i < k; i++) g |= (unsigned long long)((hi >> (i - 8)) & 1u) << a.gin[i];
-            cp_async16(&tile[swz(f)], a.in + g);
+            const double2* src = gin + (base_in | g_in_lo);
+#pragma unroll
+            for (int it = 0; it < 16; it++)
+                if (it < n_it) cp_async16(&tile[(it << 8) | s_in], src + a.hin[it]);
         }
         cp_async_wait_all();
         __syncthreads();
 
-        // ---- apply the sweep's ops on the staged tile ----
-        for (int o = 0; o < a.n_ops; o++)
+        // ---- apply the sweep's ops: warp-local groups, CTA barrier only between groups ----
+        for (int gi = 0; gi < a.n_groups; gi++)
         {
-            const DevOp* op = a.ops + o;
-            switch (__ldg(&op->cls))
+            const DevGroup* grp = s_groups + gi;
+            if (warp < grp->n_warps)
             {
-            case CLS_DENSE2: op_dense2<NT>(tile, op, k, t); break;
-            case CLS_MONO2: op_mono2<NT>(tile, op, k, t); break;
-            case CLS_DIAG2: op_diag2<NT>(tile, op, k, t); break;
-            case CLS_DENSE1: op_dense1<NT>(tile, op, k, t); break;
-            case CLS_DIAG1: op_diag1<NT>(tile, op, k, t); break;
-            case CLS_MONO1: op_mono1<NT>(tile, op, k, t); break;
-            case CLS_SRN1: op_srn1<NT>(tile, op, k, t); break;
-            default: break;
+                const unsigned wpart = grp->wtab[warp];
+                const int last = grp->first + grp->count;
+                for (int o = grp->first; o < last; o++)
+                {
+                    const DevOp* op = s_ops + o;
+                    if (lane < op->n_active)
+                    {
+                        const unsigned base = op->lane_tab[lane] ^ wpart;
+                        const int n_iter = op->n_iter;
+                        switch (op->cls)
+                        {
+                        case CLS_DENSE2: w_dense2(tile, op, base, n_iter); break;
+                        case CLS_MONO2: w_mono2(tile, op, base, n_iter); break;
+                        case CLS_DIAG2: w_diag2(tile, op, base, n_iter); break;
+                        case CLS_DENSE1: w_dense1(tile, op, base, n_iter); break;
+                        case CLS_DIAG1: w_diag1(tile, op, base, n_iter); break;
+                        case CLS_MONO1: w_mono1(tile, op, base, n_iter); break;
+                        case CLS_SRN1: w_srn1(tile, op, base, n_iter); break;
+                        default: break;
+                        }
+                    }
+                    __syncwarp();
+                }
             }
             __syncthreads();
         }
 
-        // ---- store ----
-        for (unsigned f = t; f < tile_elems; f += NT)
+        // ---- store (streaming, evict-first) ----
+        if (t_active)
         {
-            unsigned long long g = base_out | g_out_lo;
-            unsigned e = s_out_lo;
-            const unsigned hi = f >> 8;
-            for (int i = 8; i < k; i++)
-            {
-                const unsigned bit = (hi >> (i - 8)) & 1u;
-                g |= (unsigned long long)bit << a.gout[i];
-                e |= bit << a.sout[i];
-            }
-            st_stream(a.out + g, tile[swz(e)]);
+            double2* dst = gout + (base_out | g_out_lo);
+#pragma unroll
+            for (int it = 0; it < 16; it++)
+                if (it < n_it) st_stream(dst + a.hout[it], tile[s_out_lo ^ a.hs[it]]);
         }
         __syncthreads();
     }
 }
 
 static int g_num_sms = 0;
-static int g_grid_for_k[kMaxTileBits + 1];
 
-int sweep_max_grid(int k)
+void sweep_setup()
 {
-    if (g_num_sms == 0)
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << kMaxTileBits));
-        for (int i = 0; i <= kMaxTileBits; i++) g_grid_for_k[i] = 0;
-    }
-    if (k < 0) k = 0;
-    if (k > kMaxTileBits) k = kMaxTileBits;
-    if (g_grid_for_k[k] == 0)
-    {
-        int occ = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel, kTileThreads, (size_t)16 << k);
-        if (occ < 1) occ = 1;
-        g_grid_for_k[k] = g_num_sms * occ;
-    }
-    return g_grid_for_k[k];
+    if (g_num_sms) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    const int max_smem = (16 << kMaxTileBits) + kMaxOpsPerSweep * (int)(sizeof(DevOp) + sizeof(DevGroup));
+    cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+}
+
+size_t sweep_smem_bytes(const SweepArgs& a)
+{
+    return ((size_t)16 << a.k) + (size_t)a.n_ops * sizeof(DevOp) + (size_t)a.n_groups * sizeof(DevGroup);
+}
+
+int sweep_max_grid(const SweepArgs& a)
+{
+    sweep_setup();
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel, kTileThreads, sweep_smem_bytes(a));
+    if (occ < 1) occ = 1;
+    return g_num_sms * occ;
 }
 
 void launch_sweep(const SweepArgs& a, int grid, cudaStream_t s)
 {
-    sweep_kernel<<<grid, kTileThreads, (size_t)16 << a.k, s>>>(a);
+    sweep_kernel<<<grid, kTileThreads, sweep_smem_bytes(a), s>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -3,37 +3,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "devop.hpp"
+
 namespace dmb
 {
-// One op of a sweep as the device sees it.  272 bytes, 16-byte aligned.
-struct __align__(16) DevOp
-{
-    int cls;      // OpClass
-    int j0, j1;   // tile-local bit positions (j0 = matrix MSB for 2-bit ops)
-    int aux;      // MONO2: src[r] in bits 2r..2r+1, skip-row mask in bits 8..11; DIAG*: skip mask in bits 8..11
-    double2 m[16];
-};
-
-constexpr int kMaxTileBits = 12;
-constexpr int kTileThreads = 256;
-
-// Kernel parameter block of one sweep (passed by value, lives in the constant bank).
-struct SweepArgs
-{
-    const double2* in;
-    double2* out;
-    const DevOp* ops;
-    int n_ops;
-    int k;                        // tile bits
-    int n_comp;                   // M - k
-    unsigned long long n_tiles;   // 2^(M-k)
-    unsigned char gin[kMaxTileBits];   // loop bit i -> physical bit when loading (ascending); smem bit = i
-    unsigned char gout[kMaxTileBits];  // loop bit i -> physical bit when storing (ascending)
-    unsigned char sout[kMaxTileBits];  // loop bit i -> tile-local (smem) bit when storing
-    unsigned char cin[40];        // physical bits enumerated by the tile id when loading (ascending)
-    unsigned char cout[40];       // ... when storing
-};
-
 struct LayoutArgs
 {
     int n;                  // qubits
@@ -43,8 +16,10 @@ struct LayoutArgs
     unsigned char phys[40]; // physical bit of logical bit l
 };
 
+size_t sweep_smem_bytes(const SweepArgs& a);
 void launch_sweep(const SweepArgs& a, int grid, cudaStream_t s);
-int sweep_max_grid(int k); // resident CTAs for tile size 2^k (SMs * occupancy)
+int sweep_max_grid(const SweepArgs& a); // resident CTAs for this sweep's shared-memory footprint (SMs * occupancy)
+void sweep_setup();                     // one-time function attributes (must not run inside a stream capture)
 
 void launch_init_state(double2* buf, size_t n_elems, bool owns_origin, cudaStream_t s);
 void launch_diag(const double2* buf, const LayoutArgs& L, double* out_real, double* out_abs, cudaStream_t s);

@@ -544,7 +544,7 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
                 if (blocked[f.bit[b]]) blk = true;
                 else if (!in_tile[f.bit[b]]) need++;
             }
-            if (!blk && tile_cnt + need <= kmax)
+            if (!blk && tile_cnt + need <= kmax && (int)c.picked.size() < opt.max_ops)
             {
                 for (int b = 0; b < f.nb; b++)
                     if (!in_tile[f.bit[b]]) { in_tile[f.bit[b]] = 1; c.tile_logical.push_back(f.bit[b]); tile_cnt++; }
@@ -608,7 +608,13 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
         std::sort(order.begin(), order.end(), [&](int a, int b) { return phys[a] < phys[b]; });
         std::vector<int> local_of(N, -1);
         for (int j = 0; j < sw.k; j++) { local_of[order[j]] = j; sw.in_pos.push_back(phys[order[j]]); }
-        for (int i : picked)
+        // L parts (row bits) and R parts (column bits) commute: run all L parts first, so that each half leaves
+        // the other half's tile bits untouched (long barrier-free warp groups in the kernel)
+        std::vector<int> ordered;
+        for (int side = 0; side < 2; side++)
+            for (int i : picked)
+                if (ops[i].side == side) ordered.push_back(i);
+        for (int i : ordered)
         {
             FlatOp& f = ops[i];
             TileOp t;
@@ -727,7 +733,7 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
 }
 
 // ------------------------------------------------------------------------------------------------
-std::string plan_to_json(const Plan& p)
+std::string plan_to_json(const Plan& p, const std::vector<std::string>* extra)
 {
     std::ostringstream o;
     char buf[64];
@@ -749,7 +755,9 @@ std::string plan_to_json(const Plan& p)
         if (st.kind == 1) { o << "{\"kind\":\"exchange\"}"; continue; }
         const Sweep& sw = st.sweep;
         o << "{\"kind\":\"sweep\",\"k\":" << sw.k << ",\"in_pos\":" << ivec(sw.in_pos) << ",\"out_pos\":" << ivec(sw.out_pos)
-          << ",\"out_of_place\":" << (sw.out_of_place ? "true" : "false") << ",\"weight\":" << sw.weight << ",\"ops\":[";
+          << ",\"out_of_place\":" << (sw.out_of_place ? "true" : "false") << ",\"weight\":" << sw.weight;
+        if (extra && s < extra->size() && !(*extra)[s].empty()) o << ",\"dev\":" << (*extra)[s];
+        o << ",\"ops\":[";
         for (size_t i = 0; i < sw.ops.size(); i++)
         {
             const TileOp& t = sw.ops[i];

@@ -75,6 +75,7 @@ struct PlanOptions
     int tile_bits = 12; // max k (2^12 complex FP64 = 64 KiB of shared memory)
     int low_bits = 3;   // physical bits 0..low_bits-1 are always tile bits (2^3 * 16 B = 128 B runs)
     int min_tiles_log2 = 10; // prefer >= 2^10 tiles when the state is small (keeps 148 SMs busy)
+    int max_ops = 112;       // ops per sweep (the kernel keeps the sweep's op table in shared memory)
 };
 
 struct Plan
@@ -98,7 +99,8 @@ void expand_gates(int n_qubits, const dmb_gate* gates, size_t n_gates, const dou
 void fuse_blocks(int n_qubits, const std::vector<Block>& prims, std::vector<Block>& blocks);
 Plan make_plan(int n_qubits, int world_size, const dmb_gate* gates, size_t n_gates, const double* mats,
                size_t n_mats, const std::vector<int>& start_layout, const PlanOptions& opt, bool conj_state = false);
-std::string plan_to_json(const Plan& p);
+// extra (optional): one JSON object text per step, spliced into sweep steps as "dev": {...}
+std::string plan_to_json(const Plan& p, const std::vector<std::string>* extra = nullptr);
 
 // classify a 2x2 / 4x4 matrix; for MONO fills src[] (column of the single non-zero of each row)
 int classify(int nb, const cplx* m, int* src);

@@ -146,7 +146,8 @@ def test_mixed_state_gate_application(dm, oracle_mod):
     sim.run()
     re, im = sim.get_dm()
     o = oracle_mod.Oracle(n)
-    o.lib.orc_set_state(o.h, np.ascontiguousarray(stored.real).ctypes.data, np.ascontiguousarray(stored.imag).ctypes.data)
+    sre, sim_ = np.ascontiguousarray(stored.real), np.ascontiguousarray(stored.imag)  # keep alive across the call
+    o.lib.orc_set_state(o.h, sre.ctypes.data, sim_.ctypes.data)
     ore, oim = o.sim(gates).dm()
     assert max(np.abs(re - ore).max(), np.abs(im - oim).max()) < TOL
 
