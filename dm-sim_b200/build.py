@@ -38,7 +38,7 @@ def _run(cmd, verbose):
 
 
 def core_sources():
-    srcs = [os.path.join(CSRC, f) for f in ("plan.cpp", "encode.cpp", "kernels.cu", "capi.cu")]
+    srcs = [os.path.join(CSRC, f) for f in ("plan.cpp", "encode.cpp", "kernels.cu", "sweep_kernel.cu", "capi.cu")]
     hdrs = [os.path.join(CSRC, f) for f in ("plan.hpp", "kernels.cuh", "devop.hpp", "encode.hpp")] + [os.path.join(ROOT, "include", "dmsim_b200.h")]
     return srcs, hdrs
 

@@ -132,10 +132,11 @@ struct dmb_sim
     DevOp* d_ops = nullptr;
     size_t d_ops_cap = 0;
     std::vector<size_t> op_offset;    // per step: first DevOp
-    std::vector<size_t> group_offset; // per step: first DevGroup
-    std::vector<int> n_dev_ops, n_dev_groups;
+    std::vector<size_t> round_offset, group_offset; // per step: first DevRound / DevGroup
+    std::vector<int> n_dev_ops, n_dev_rounds, n_dev_groups;
+    DevRound* d_rounds = nullptr;
     DevGroup* d_groups = nullptr;
-    size_t d_groups_cap = 0;
+    size_t d_rounds_cap = 0, d_groups_cap = 0;
     cudaGraphExec_t graph_exec = nullptr;
     int graph_cur = -1;
     uint64_t h2d_bytes = 0;
@@ -248,6 +249,7 @@ int dmb_destroy(dmb_handle s)
     if (s->buf[0]) cudaFree(s->buf[0]);
     if (s->buf[1]) cudaFree(s->buf[1]);
     if (s->d_ops) cudaFree(s->d_ops);
+    if (s->d_rounds) cudaFree(s->d_rounds);
     if (s->d_groups) cudaFree(s->d_groups);
     if (s->d_scratch) cudaFree(s->d_scratch);
     delete s;
@@ -313,22 +315,28 @@ static int build_plan(dmb_sim* s)
     drop_graph(s);
     // device op / group tables: one contiguous upload each (the reference does 3 CUDA calls per gate per GPU, :112-163)
     std::vector<DevOp> host_ops;
+    std::vector<DevRound> host_rounds;
     std::vector<DevGroup> host_groups;
     const size_t nsteps = s->plan.steps.size();
     s->op_offset.assign(nsteps, 0);
+    s->round_offset.assign(nsteps, 0);
     s->group_offset.assign(nsteps, 0);
     s->n_dev_ops.assign(nsteps, 0);
+    s->n_dev_rounds.assign(nsteps, 0);
     s->n_dev_groups.assign(nsteps, 0);
     EncodedSweep enc;
     for (size_t i = 0; i < nsteps; i++)
     {
         s->op_offset[i] = host_ops.size();
+        s->round_offset[i] = host_rounds.size();
         s->group_offset[i] = host_groups.size();
         if (s->plan.steps[i].kind != 0) continue;
         encode_sweep(s->plan.steps[i].sweep, enc);
         s->n_dev_ops[i] = (int)enc.ops.size();
+        s->n_dev_rounds[i] = (int)enc.rounds.size();
         s->n_dev_groups[i] = (int)enc.groups.size();
         host_ops.insert(host_ops.end(), enc.ops.begin(), enc.ops.end());
+        host_rounds.insert(host_rounds.end(), enc.rounds.begin(), enc.rounds.end());
         host_groups.insert(host_groups.end(), enc.groups.begin(), enc.groups.end());
     }
     CU(cudaSetDevice(s->device));
@@ -340,6 +348,14 @@ static int build_plan(dmb_sim* s)
         CU(cudaMalloc(&s->d_ops, host_ops.size() * sizeof(DevOp)));
         s->d_ops_cap = host_ops.size();
     }
+    if (host_rounds.size() > s->d_rounds_cap)
+    {
+        if (s->d_rounds) cudaFree(s->d_rounds);
+        s->d_rounds = nullptr;
+        s->d_rounds_cap = 0;
+        CU(cudaMalloc(&s->d_rounds, host_rounds.size() * sizeof(DevRound)));
+        s->d_rounds_cap = host_rounds.size();
+    }
     if (host_groups.size() > s->d_groups_cap)
     {
         if (s->d_groups) cudaFree(s->d_groups);
@@ -348,10 +364,12 @@ static int build_plan(dmb_sim* s)
         CU(cudaMalloc(&s->d_groups, host_groups.size() * sizeof(DevGroup)));
         s->d_groups_cap = host_groups.size();
     }
-    s->h2d_bytes = host_ops.size() * sizeof(DevOp) + host_groups.size() * sizeof(DevGroup);
+    s->h2d_bytes = host_ops.size() * sizeof(DevOp) + host_rounds.size() * sizeof(DevRound) + host_groups.size() * sizeof(DevGroup);
     if (!host_ops.empty())
     {
         CU(cudaMemcpyAsync(s->d_ops, host_ops.data(), host_ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->d_rounds, host_rounds.data(), host_rounds.size() * sizeof(DevRound), cudaMemcpyHostToDevice,
+                           s->stream));
         CU(cudaMemcpyAsync(s->d_groups, host_groups.data(), host_groups.size() * sizeof(DevGroup), cudaMemcpyHostToDevice,
                            s->stream));
         CU(cudaStreamSynchronize(s->stream));
@@ -391,8 +409,10 @@ static void fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, do
     a.in = in;
     a.out = out;
     a.ops = s->d_ops + s->op_offset[step];
+    a.rounds = s->d_rounds + s->round_offset[step];
     a.groups = s->d_groups + s->group_offset[step];
     a.n_ops = s->n_dev_ops[step];
+    a.n_rounds = s->n_dev_rounds[step];
     a.n_groups = s->n_dev_groups[step];
 }
 

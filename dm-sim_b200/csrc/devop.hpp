@@ -6,42 +6,68 @@
 namespace dmb
 {
 constexpr int kMaxTileBits = 12;  // 2^12 complex FP64 = 64 KiB of shared memory per CTA
-constexpr int kTileThreads = 256; // 8 warps
+constexpr int kTileThreads = 256; // 8 warps; 2-3 CTAs per SM overlap each other's load / compute / store phases
+constexpr int kThreadBits = 8;    // log2(kTileThreads)
 constexpr int kWarpBits = 3;      // log2(warps per CTA)
+constexpr int kRegBits = 3;       // a lane keeps 2^3 tile elements (32 registers) resident per round
 constexpr int kMaxOpsPerSweep = 112;
 
-// XOR swizzle of the shared-memory tile (element = 16 B): low 3 element bits ^= bits 3..5, so that 8 lanes of an
-// LDS.128 phase hit 8 different 16-byte bank groups both for unit-stride and for stride-2/4/8 element patterns.
+// XOR swizzle of the shared-memory tile (element = 16 B): low 3 element bits ^= bits 3..5, so that the 8 lanes of
+// an LDS.128 phase hit 8 different 16-byte bank groups for unit-stride as well as stride-2/4/8 element patterns.
 // GF(2)-linear: swz(a ^ b) == swz(a) ^ swz(b) -- the encoder pre-swizzles every index contribution.
 inline unsigned swz_host(unsigned e) { return e ^ ((e >> 3) & 7u); }
 
-// One op of a sweep as the device sees it (368 bytes).  Work items (pairs for 1-bit ops, quads for 2-bit ops) of
-// a warp's sub-tile are enumerated as item = lane + 32*iter; the tile index of member c of an item is
-//     lane_tab[lane] ^ iter_tab[iter] ^ wtab[warp] ^ off[c]          (all already swizzled)
+// Register-level op codes (what the device switches on).  Two-bit ops are canonicalised by the encoder so that
+// the matrix MSB sits on the HIGHER register bit; `pos` then selects one of the pairs (1,0) (2,0) (2,1).
+enum RegOpCode : int32_t
+{
+    RC_DENSE1 = 0, // m[0..3]
+    RC_DIAG1 = 1,  // m[0..1], skip mask in aux bits 8..9
+    RC_MONO1 = 2,  // out0 = m0*v1, out1 = m1*v0 (aux bit 12: unit phases)
+    RC_SRN1 = 3,   // reference SRN_GATE (:1253-1266)
+    RC_DENSE2 = 4, // m[0..15]
+    RC_DIAG2 = 5,  // m[0..3], skip mask in aux bits 8..11
+    RC_PERM2 = 6,  // monomial with a row permutation from {CX(msb ctrl), CX(lsb ctrl), SWAP}: aux bits 0..1 = which,
+                   // m[0..3] = row phases, aux bit 12: unit phases
+    RC_DIAG3 = 7   // product of consecutive diagonal ops of a round: v[c] *= m[c] for the 8 registers, skip mask in
+                   // aux bits 0..7 (entries equal to 1)
+};
+
+// One op of a round (272 bytes), applied to the lane's 2^kRegBits resident elements.
 struct alignas(16) DevOp
 {
-    int32_t cls;      // OpClass
-    int32_t aux;      // MONO2: src[r] in bits 2r..2r+1; skip-row mask in bits 8..11; unit-phase flag bit 12
+    int32_t code; // RegOpCode
+    int32_t aux;
+    int32_t pos;  // 1-bit ops: register bit 0..2; 2-bit ops: 0 -> (1,0), 1 -> (2,0), 2 -> (2,1)  (msb, lsb)
+    int32_t pad;
+    double m[32]; // up to 16 complex entries (re, im)
+};
+static_assert(sizeof(DevOp) == 272, "DevOp layout");
+
+// A round: the lane loads the 2^kRegBits elements  base ^ roff[c]  (base = lane_tab[lane] ^ iter_tab[iter] ^
+// wtab[warp], everything pre-swizzled), applies ops [first, first+count) in registers and stores them back:
+// ONE shared-memory round trip for `count` ops.
+struct alignas(16) DevRound
+{
+    int32_t first, count;
     int32_t n_iter;   // iterations per lane
-    int32_t n_active; // active lanes (32 unless the sub-tile has fewer items)
-    double m[32];     // up to 16 complex entries (re, im); layout per class as in plan.hpp
+    int32_t n_active; // active lanes (32 unless the sub-tile has fewer work items)
     uint16_t lane_tab[32];
     uint16_t iter_tab[8];
-    uint16_t off[4];
-    uint16_t pad[4];
+    uint16_t roff[8];
 };
-static_assert(sizeof(DevOp) == 368, "DevOp layout");
+static_assert(sizeof(DevRound) == 112, "DevRound layout");
 
-// A run of consecutive ops that leave kWarpBits tile bits untouched: warp w owns the sub-tile where those bits
+// A run of consecutive rounds that leave kWarpBits tile bits untouched: warp w owns the sub-tile where those bits
 // equal w and runs the whole group with __syncwarp() only; CTA barriers happen between groups.
 struct alignas(16) DevGroup
 {
-    int32_t first, count; // ops [first, first+count) of the sweep
-    int32_t n_warps;      // 8, or 1 when the tile is too small to split
+    int32_t first, count; // rounds [first, first+count) of the sweep
+    int32_t n_warps;      // 2^kWarpBits, or 1 when the tile is too small to split
     int32_t pad;
-    uint16_t wtab[8];     // swizzled tile-index contribution of the warp
+    uint16_t wtab[16];    // swizzled tile-index contribution of the warp
 };
-static_assert(sizeof(DevGroup) == 32, "DevGroup layout");
+static_assert(sizeof(DevGroup) == 48, "DevGroup layout");
 
 // Kernel parameter block of one sweep (by value -> constant bank; the per-iteration tables become immediate
 // constant operands of the unrolled load / store loops).
@@ -50,17 +76,18 @@ struct SweepArgs
     const void* in;   // double2*
     void* out;        // double2*
     const DevOp* ops; // device copies
+    const DevRound* rounds;
     const DevGroup* groups;
-    int n_ops, n_groups;
+    int n_ops, n_rounds, n_groups;
     int k;                      // tile bits
     int n_comp;                 // M - k
     unsigned long long n_tiles; // 2^(M-k)
     unsigned long long hin[16];  // element offset contributed by iteration `it` when loading
     unsigned long long hout[16]; // ... when storing
     unsigned short hs[16];       // swizzled smem index contributed by iteration `it` when storing
-    unsigned char gin[8];        // physical bit of loop bit i (< 8) when loading
-    unsigned char gout[8];       // ... when storing
-    unsigned char sout[8];       // tile-local bit of loop bit i (< 8) when storing
+    unsigned char gin[12];       // physical bit of loop bit i (< kThreadBits) when loading
+    unsigned char gout[12];      // ... when storing
+    unsigned char sout[12];      // tile-local bit of loop bit i (< kThreadBits) when storing
     unsigned char cin[40];       // physical bits enumerated by the tile id when loading (ascending)
     unsigned char cout[40];      // ... when storing
 };

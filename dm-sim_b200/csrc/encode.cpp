@@ -1,11 +1,11 @@
-// dm-sim_b200/csrc/encode.cpp -- turns a planned Sweep into what sweep_kernel consumes: device ops with
-// pre-swizzled index tables, warp groups, and the load/store address tables of the kernel parameter block.
-// Pure host code (system compiler).
+// dm-sim_b200/csrc/encode.cpp -- turns a planned Sweep into what sweep_kernel consumes: warp groups, register
+// rounds with pre-swizzled index tables, canonicalised register-level ops, and the load/store address tables of
+// the kernel parameter block.  Pure host code (system compiler).
 #include "encode.hpp"
 
 #include <algorithm>
-#include <cstring>
 #include <cstdio>
+#include <cstring>
 #include <sstream>
 
 namespace dmb
@@ -25,96 +25,237 @@ void put(DevOp& d, int i, cplx v)
     d.m[2 * i + 1] = v.imag();
 }
 
-// class-specific payload (which matrix entries the device reads, skip masks)
-void encode_payload(const TileOp& t, DevOp& d)
+// same 4x4 operator with the roles of its two bits exchanged (index bit swap)
+void swap_roles(const cplx* m, cplx* o)
 {
+    static const int p[4] = {0, 2, 1, 3};
+    cplx t[16];
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) t[p[r] * 4 + p[c]] = m[r * 4 + c];
+    memcpy(o, t, sizeof(t));
+}
+
+// register-level op from a tile op whose bits sit on register bits p0 (matrix MSB) and p1
+DevOp make_reg_op(const TileOp& t, int p0, int p1)
+{
+    DevOp d;
+    memset(&d, 0, sizeof(d));
     const cplx one(1.0, 0.0);
-    switch (t.cls)
+    if (t.cls == CLS_SRN1)
     {
-    case CLS_DENSE2:
-        for (int i = 0; i < 16; i++) put(d, i, t.m[i]);
-        break;
-    case CLS_DENSE1:
-        for (int i = 0; i < 4; i++) put(d, i, t.m[i]);
-        break;
-    case CLS_DIAG2:
+        d.code = RC_SRN1;
+        d.pos = p0;
+        return d;
+    }
+    if (t.nb == 1)
     {
+        d.pos = p0;
+        const int cls = classify(1, t.m, nullptr);
+        if (cls == CLS_DIAG1)
+        {
+            d.code = RC_DIAG1;
+            int skip = 0;
+            for (int r = 0; r < 2; r++)
+            {
+                put(d, r, t.m[r * 3]);
+                if (t.m[r * 3] == one) skip |= 1 << r;
+            }
+            d.aux = skip << 8;
+        }
+        else if (cls == CLS_MONO1)
+        {
+            d.code = RC_MONO1;
+            put(d, 0, t.m[1]);
+            put(d, 1, t.m[2]);
+            d.aux = ((t.m[1] == one && t.m[2] == one) ? 1 : 0) << 12;
+        }
+        else
+        {
+            d.code = RC_DENSE1;
+            for (int i = 0; i < 4; i++) put(d, i, t.m[i]);
+        }
+        return d;
+    }
+    cplx m[16];
+    if (p0 > p1) memcpy(m, t.m, sizeof(m));
+    else { swap_roles(t.m, m); std::swap(p0, p1); }
+    d.pos = (p0 == 1) ? 0 : (p1 == 0 ? 1 : 2); // (1,0) (2,0) (2,1)
+    int src[4];
+    const int cls = classify(2, m, src);
+    if (cls == CLS_DIAG2)
+    {
+        d.code = RC_DIAG2;
         int skip = 0;
         for (int r = 0; r < 4; r++)
         {
-            put(d, r, t.m[r * 5]);
-            if (t.m[r * 5] == one) skip |= 1 << r;
+            put(d, r, m[r * 5]);
+            if (m[r * 5] == one) skip |= 1 << r;
         }
         d.aux = skip << 8;
-        break;
+        return d;
     }
-    case CLS_DIAG1:
+    if (cls == CLS_MONO2)
     {
-        int skip = 0;
-        for (int r = 0; r < 2; r++)
+        static const int perms[3][4] = {{0, 1, 3, 2}, {0, 3, 2, 1}, {0, 2, 1, 3}};
+        for (int w = 0; w < 3; w++)
+            if (src[0] == perms[w][0] && src[1] == perms[w][1] && src[2] == perms[w][2] && src[3] == perms[w][3])
+            {
+                d.code = RC_PERM2;
+                bool unit = true;
+                for (int r = 0; r < 4; r++)
+                {
+                    put(d, r, m[r * 4 + src[r]]);
+                    if (m[r * 4 + src[r]] != one) unit = false;
+                }
+                d.aux = w | ((unit ? 1 : 0) << 12);
+                return d;
+            }
+    }
+    d.code = RC_DENSE2;
+    for (int i = 0; i < 16; i++) put(d, i, m[i]);
+    return d;
+}
+} // namespace
+
+namespace
+{
+struct RoundPlan
+{
+    std::vector<int> ops;   // indices into sw.ops, execution order
+    unsigned touched = 0;   // tile bits its ops act on
+};
+
+// Splits the sweep's op list into register rounds.  Like the tile scheduler one level up: pick <= R register bits by
+// gain (how much of the remaining list becomes executable: per-bit program order, diagonal ops hop over skipped
+// diagonal ops), run everything that fits, repeat.  Sweeps containing SRN (a full barrier) keep strict list order.
+std::vector<RoundPlan> plan_rounds(const Sweep& sw, int R)
+{
+    const int n = (int)sw.ops.size();
+    std::vector<char> done(n, 0), diag(n, 0);
+    bool has_srn = false;
+    for (int i = 0; i < n; i++)
+    {
+        const TileOp& t = sw.ops[i];
+        if (t.cls == CLS_SRN1) has_srn = true;
+        else
         {
-            put(d, r, t.m[r * 3]);
-            if (t.m[r * 3] == one) skip |= 1 << r;
+            const int c = classify(t.nb, t.m, nullptr);
+            diag[i] = (c == CLS_DIAG1 || c == CLS_DIAG2);
         }
-        d.aux = skip << 8;
-        break;
     }
-    case CLS_MONO2:
+    auto bits_of = [&](int i) {
+        unsigned m = 1u << sw.ops[i].j0;
+        if (sw.ops[i].nb == 2) m |= 1u << sw.ops[i].j1;
+        return m;
+    };
+    std::vector<RoundPlan> rounds;
+    int first = 0, left = n;
+    if (has_srn)
     {
-        int src[4];
-        classify(2, t.m, src);
-        int aux = 0, skip = 0;
-        bool unit = true;
-        for (int r = 0; r < 4; r++)
+        while (first < n)
         {
-            const cplx ph = t.m[r * 4 + src[r]];
-            put(d, r, ph);
-            aux |= src[r] << (2 * r);
-            if (ph != one) unit = false;
-            if (src[r] == r && ph == one) skip |= 1 << r;
+            RoundPlan rp;
+            while (first < n && __builtin_popcount(rp.touched | bits_of(first)) <= R)
+            {
+                rp.touched |= bits_of(first);
+                rp.ops.push_back(first++);
+            }
+            rounds.push_back(rp);
         }
-        d.aux = aux | (skip << 8) | ((unit ? 1 : 0) << 12);
-        break;
+        return rounds;
     }
-    case CLS_MONO1:
+    // which ops run with the register bit set `rb` fixed
+    auto scan = [&](unsigned rb, std::vector<int>* picked) {
+        unsigned soft = 0, hard = 0; // bits with a skipped diagonal / non-diagonal op
+        int score = 0;
+        for (int i = first; i < n && (hard & rb) != rb; i++)
+        {
+            if (done[i]) continue;
+            const unsigned m = bits_of(i);
+            const bool ok = (m & ~rb) == 0 && !(m & hard) && (diag[i] || !(m & soft));
+            if (ok)
+            {
+                score += sw.ops[i].weight > 0 ? 1 : 1;
+                if (picked) picked->push_back(i);
+            }
+            else if (diag[i]) soft |= m;
+            else hard |= m;
+        }
+        return score;
+    };
+    while (left > 0)
     {
-        put(d, 0, t.m[1]);
-        put(d, 1, t.m[2]);
-        const bool unit = (t.m[1] == one && t.m[2] == one);
-        d.aux = (unit ? 1 : 0) << 12;
-        break;
+        while (first < n && done[first]) first++;
+        unsigned rb = 0;
+        int cur = 0;
+        while (__builtin_popcount(rb) < R)
+        {
+            const int room = R - __builtin_popcount(rb);
+            std::vector<unsigned> cands;
+            int looked = 0;
+            for (int i = first; i < n && looked < 96; i++)
+            {
+                if (done[i]) continue;
+                looked++;
+                const unsigned miss = bits_of(i) & ~rb;
+                if (!miss || __builtin_popcount(miss) > room) continue;
+                if (std::find(cands.begin(), cands.end(), miss) == cands.end()) cands.push_back(miss);
+            }
+            int best_gain = 0, best = -1;
+            double best_rate = 0;
+            for (size_t c = 0; c < cands.size(); c++)
+            {
+                const int gain = scan(rb | cands[c], nullptr) - cur;
+                const double rate = (double)gain / __builtin_popcount(cands[c]);
+                if (gain > 0 && (rate > best_rate || (rate == best_rate && gain > best_gain)))
+                {
+                    best_rate = rate; best_gain = gain; best = (int)c;
+                }
+            }
+            if (best < 0) break;
+            rb |= cands[best];
+            cur += best_gain;
+        }
+        RoundPlan rp;
+        scan(rb, &rp.ops);
+        for (int i : rp.ops)
+        {
+            done[i] = 1;
+            rp.touched |= bits_of(i);
+            left--;
+        }
+        rounds.push_back(rp);
     }
-    default:
-        break;
-    }
+    return rounds;
 }
 } // namespace
 
 void encode_sweep(const Sweep& sw, EncodedSweep& out)
 {
     out.ops.clear();
+    out.rounds.clear();
     out.groups.clear();
     const int k = sw.k;
-    const int nwb = k >= kWarpBits + 2 ? kWarpBits : 0;
-    const size_t n = sw.ops.size();
+    const int nwb = k >= kWarpBits + kRegBits ? kWarpBits : 0;
+    const int R = std::min(kRegBits, k - nwb);
+    const std::vector<RoundPlan> plan = plan_rounds(sw, R);
+    const size_t nr = plan.size();
     size_t first = 0;
-    while (first < n)
+    while (first < nr)
     {
-        // grow the group while kWarpBits tile bits stay untouched
+        // ---- group: consecutive rounds that leave kWarpBits tile bits untouched ----
         unsigned used = 0;
         size_t end = first;
-        while (end < n)
+        while (end < nr)
         {
-            unsigned u = used | (1u << sw.ops[end].j0);
-            if (sw.ops[end].nb == 2) u |= 1u << sw.ops[end].j1;
+            const unsigned u = used | plan[end].touched;
             if (k - __builtin_popcount(u) < nwb) break;
             used = u;
             end++;
         }
         DevGroup g;
         memset(&g, 0, sizeof(g));
-        g.first = (int32_t)first;
-        g.count = (int32_t)(end - first);
+        g.first = (int32_t)out.rounds.size();
         g.n_warps = 1 << nwb;
         std::vector<int> wpos; // the highest untouched bits carry the warp index
         for (int p = k - 1; p >= 0 && (int)wpos.size() < nwb; p--)
@@ -122,25 +263,32 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
         std::sort(wpos.begin(), wpos.end());
         unsigned wmask = 0;
         for (int p : wpos) wmask |= 1u << p;
-        for (int w = 0; w < 8; w++) g.wtab[w] = (uint16_t)swz_host(deposit((unsigned)w, wpos));
-        out.groups.push_back(g);
+        for (int w = 0; w < (1 << kWarpBits); w++) g.wtab[w] = (uint16_t)swz_host(deposit((unsigned)w, wpos));
 
-        for (size_t i = first; i < end; i++)
+        for (size_t ri = first; ri < end; ri++)
         {
-            const TileOp& t = sw.ops[i];
-            DevOp d;
-            memset(&d, 0, sizeof(d));
-            d.cls = t.cls;
-            encode_payload(t, d);
-            unsigned opmask = 1u << t.j0;
-            if (t.nb == 2) opmask |= 1u << t.j1;
+            const RoundPlan& rp = plan[ri];
+            std::vector<int> rb;
+            for (int p = 0; p < k; p++)
+                if ((rp.touched >> p) & 1u) rb.push_back(p);
+            // pad the register bits with free tile bits (lowest first)
+            for (int p = 0; p < k && (int)rb.size() < R; p++)
+                if (!((wmask >> p) & 1u) && std::find(rb.begin(), rb.end(), p) == rb.end()) rb.push_back(p);
+            std::sort(rb.begin(), rb.end());
+            unsigned rmask = 0;
+            for (int p : rb) rmask |= 1u << p;
+
+            DevRound rd;
+            memset(&rd, 0, sizeof(rd));
+            rd.first = (int32_t)out.ops.size();
+            const int rd_first = rd.first;
+            for (int c = 0; c < 8; c++) rd.roff[c] = (uint16_t)swz_host(deposit((unsigned)c & ((1u << R) - 1u), rb));
             std::vector<int> freep;
             for (int p = 0; p < k; p++)
-                if (!(((wmask | opmask) >> p) & 1u)) freep.push_back(p);
-            const int nfree = (int)freep.size();
-            const int nl = std::min(5, nfree);
+                if (!(((wmask | rmask) >> p) & 1u)) freep.push_back(p);
+            const int nl = std::min(5, (int)freep.size());
             // lane bits 0..2 vary inside one LDS.128 phase: give them positions from three different swizzle
-            // classes ({0,3},{1,4},{2,5}) whenever the op leaves one free, so the phase is conflict-free
+            // classes ({0,3},{1,4},{2,5}) whenever one is free, so that the phase is bank-conflict free
             std::vector<int> lanep;
             std::vector<char> taken(k, 0);
             for (int cls = 0; cls < 3 && (int)lanep.size() < nl; cls++)
@@ -156,21 +304,64 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
             std::vector<int> iterp;
             for (int p : freep)
                 if (!taken[p]) iterp.push_back(p);
-            d.n_iter = 1 << (int)iterp.size();
-            d.n_active = 1 << nl;
-            for (int l = 0; l < 32; l++) d.lane_tab[l] = (uint16_t)swz_host(deposit((unsigned)l & ((1u << nl) - 1u), lanep));
+            rd.n_iter = 1 << (int)iterp.size();
+            rd.n_active = 1 << nl;
+            for (int l = 0; l < 32; l++) rd.lane_tab[l] = (uint16_t)swz_host(deposit((unsigned)l & ((1u << nl) - 1u), lanep));
             for (int it = 0; it < 8; it++)
-                d.iter_tab[it] = (uint16_t)swz_host(deposit((unsigned)it & ((unsigned)d.n_iter - 1u), iterp));
-            if (t.nb == 2)
+                rd.iter_tab[it] = (uint16_t)swz_host(deposit((unsigned)it & ((unsigned)rd.n_iter - 1u), iterp));
+            out.rounds.push_back(rd);
+
+            for (int o : rp.ops)
             {
-                d.off[1] = (uint16_t)swz_host(1u << t.j1);
-                d.off[2] = (uint16_t)swz_host(1u << t.j0);
-                d.off[3] = d.off[1] ^ d.off[2];
+                const TileOp& t = sw.ops[o];
+                const int p0 = (int)(std::find(rb.begin(), rb.end(), t.j0) - rb.begin());
+                const int p1 = t.nb == 2 ? (int)(std::find(rb.begin(), rb.end(), t.j1) - rb.begin()) : 0;
+                DevOp d = make_reg_op(t, p0, p1);
+                if (d.code == RC_DIAG1 || d.code == RC_DIAG2)
+                {
+                    // every diagonal op becomes an 8-entry diagonal over the round's register bits, and consecutive
+                    // ones are multiplied together on the host: one device op, no position dispatch
+                    cplx e[8];
+                    for (int c = 0; c < 8; c++)
+                    {
+                        int idx;
+                        if (d.code == RC_DIAG1) idx = (c >> d.pos) & 1;
+                        else
+                        {
+                            static const int hi[3] = {1, 2, 2}, lo[3] = {0, 0, 1};
+                            idx = 2 * ((c >> hi[d.pos]) & 1) + ((c >> lo[d.pos]) & 1);
+                        }
+                        e[c] = cplx(d.m[2 * idx], d.m[2 * idx + 1]);
+                    }
+                    const bool merge = (int)out.ops.size() > rd_first && out.ops.back().code == RC_DIAG3;
+                    DevOp nd;
+                    if (merge) nd = out.ops.back();
+                    else
+                    {
+                        memset(&nd, 0, sizeof(nd));
+                        nd.code = RC_DIAG3;
+                        for (int c = 0; c < 8; c++) put(nd, c, cplx(1.0, 0.0));
+                    }
+                    int skip = 0;
+                    for (int c = 0; c < 8; c++)
+                    {
+                        cplx v = cplx(nd.m[2 * c], nd.m[2 * c + 1]) * e[c];
+                        // entries within 1e-15 of 1 (e.g. u1(a)*u1(-a) inside a fused controlled phase) are exactly 1
+                        if (std::abs(v.real() - 1.0) < 1e-15 && std::abs(v.imag()) < 1e-15) v = cplx(1.0, 0.0);
+                        put(nd, c, v);
+                        if (v == cplx(1.0, 0.0)) skip |= 1 << c;
+                    }
+                    nd.aux = skip;
+                    if (merge) out.ops.back() = nd;
+                    else out.ops.push_back(nd);
+                    continue;
+                }
+                out.ops.push_back(d);
             }
-            else
-                d.off[1] = (uint16_t)swz_host(1u << t.j0);
-            out.ops.push_back(d);
+            out.rounds.back().count = (int32_t)out.ops.size() - rd_first;
         }
+        g.count = (int32_t)out.rounds.size() - g.first;
+        out.groups.push_back(g);
         first = end;
     }
 }
@@ -186,7 +377,7 @@ void fill_sweep_tables(const Sweep& sw, int M, SweepArgs& a)
     std::vector<int> ord(k);
     for (int i = 0; i < k; i++) ord[i] = i;
     std::sort(ord.begin(), ord.end(), [&](int x, int y) { return sw.out_pos[x] < sw.out_pos[y]; });
-    for (int i = 0; i < k && i < 8; i++)
+    for (int i = 0; i < k && i < kThreadBits; i++)
     {
         a.gin[i] = (unsigned char)sw.in_pos[i];
         a.gout[i] = (unsigned char)sw.out_pos[ord[i]];
@@ -196,9 +387,9 @@ void fill_sweep_tables(const Sweep& sw, int M, SweepArgs& a)
     {
         unsigned long long hi = 0, ho = 0;
         unsigned hs = 0;
-        for (int i = 8; i < k; i++)
+        for (int i = kThreadBits; i < k; i++)
         {
-            const unsigned long long bit = (it >> (i - 8)) & 1;
+            const unsigned long long bit = (it >> (i - kThreadBits)) & 1;
             hi |= bit << sw.in_pos[i];
             ho |= bit << sw.out_pos[ord[i]];
             hs |= (unsigned)bit << ord[i];
@@ -229,9 +420,9 @@ std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a)
     arr("hin", a.hin, 16); o << ",";
     arr("hout", a.hout, 16); o << ",";
     arr("hs", a.hs, 16); o << ",";
-    arr("gin", a.gin, 8); o << ",";
-    arr("gout", a.gout, 8); o << ",";
-    arr("sout", a.sout, 8); o << ",";
+    arr("gin", a.gin, 12); o << ",";
+    arr("gout", a.gout, 12); o << ",";
+    arr("sout", a.sout, 12); o << ",";
     arr("cin", a.cin, a.n_comp); o << ",";
     arr("cout", a.cout, a.n_comp);
     o << ",\"groups\":[";
@@ -239,7 +430,18 @@ std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a)
     {
         const DevGroup& G = e.groups[g];
         o << (g ? "," : "") << "{\"first\":" << G.first << ",\"count\":" << G.count << ",\"n_warps\":" << G.n_warps << ",";
-        arr("wtab", G.wtab, 8);
+        arr("wtab", G.wtab, 16);
+        o << "}";
+    }
+    o << "],\"rounds\":[";
+    for (size_t r = 0; r < e.rounds.size(); r++)
+    {
+        const DevRound& D = e.rounds[r];
+        o << (r ? "," : "") << "{\"first\":" << D.first << ",\"count\":" << D.count << ",\"n_iter\":" << D.n_iter
+          << ",\"n_active\":" << D.n_active << ",";
+        arr("lane_tab", D.lane_tab, 32); o << ",";
+        arr("iter_tab", D.iter_tab, 8); o << ",";
+        arr("roff", D.roff, 8);
         o << "}";
     }
     o << "],\"ops\":[";
@@ -247,12 +449,7 @@ std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a)
     for (size_t i = 0; i < e.ops.size(); i++)
     {
         const DevOp& d = e.ops[i];
-        o << (i ? "," : "") << "{\"cls\":" << d.cls << ",\"aux\":" << d.aux << ",\"n_iter\":" << d.n_iter
-          << ",\"n_active\":" << d.n_active << ",";
-        arr("lane_tab", d.lane_tab, 32); o << ",";
-        arr("iter_tab", d.iter_tab, 8); o << ",";
-        arr("off", d.off, 4);
-        o << ",\"m\":[";
+        o << (i ? "," : "") << "{\"code\":" << d.code << ",\"aux\":" << d.aux << ",\"pos\":" << d.pos << ",\"m\":[";
         for (int j = 0; j < 32; j++)
         {
             snprintf(buf, sizeof(buf), "%.17g", d.m[j]);

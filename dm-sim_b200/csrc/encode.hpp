@@ -11,6 +11,7 @@ namespace dmb
 struct EncodedSweep
 {
     std::vector<DevOp> ops;
+    std::vector<DevRound> rounds;
     std::vector<DevGroup> groups;
 };
 void encode_sweep(const Sweep& sw, EncodedSweep& out);

@@ -348,6 +348,12 @@ void fuse_blocks(int n, const std::vector<Block>& prims, std::vector<Block>& blo
         if (p.nq == 1)
         {
             const int q = p.q[0];
+            // structure-preserving: a dense 1-qubit gate (H, U3, ...) is NOT folded into a diagonal / monomial 2-qubit
+            // block (CX, controlled phases): the block would become a dense 4x4 (4x the FP64 work) and diagonal blocks
+            // would lose their freedom to commute in the schedulers
+            if (open[q] >= 0 && classify(1, p.m, nullptr) == CLS_DENSE1 &&
+                classify(2, work[open[q]].m, nullptr) != CLS_DENSE2)
+                close_block(open[q]);
             if (open[q] >= 0)
             {
                 Block& b = work[open[q]];
@@ -383,10 +389,16 @@ void fuse_blocks(int n, const std::vector<Block>& prims, std::vector<Block>& blo
         close_block(open[a]);
         close_block(open[b_]);
         Block nb = p;
+        const bool nb_dense = classify(2, p.m, nullptr) == CLS_DENSE2;
         for (int side = 0; side < 2; side++)
         {
             const int q = side == 0 ? a : b_;
             if (!pend[q].have) continue;
+            if (!nb_dense && classify(1, pend[q].u, nullptr) == CLS_DENSE1)
+            {
+                flush_pending(q); // keep the dense 1-qubit product as its own block (see above)
+                continue;
+            }
             if (!is_identity2(pend[q].u))
             {
                 cplx e[16];
@@ -452,6 +464,7 @@ struct FlatOp
     bool srn;
     int weight;
     int side; // 0 = L (row bits), 1 = R (column bits)
+    bool diag = false; // diagonal matrix: commutes with every other diagonal op
     bool done = false;
 };
 
@@ -502,6 +515,11 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
             const int cnt = b.nq == 1 ? 4 : 16;
             // on a conjugated store (conj_state) E acts as conj(E): conj(E conj(x)) = conj(E) x
             for (int e = 0; e < cnt; e++) f.m[e] = ((side == 1) != conj_state) ? std::conj(b.m[e]) : b.m[e];
+            if (!b.srn)
+            {
+                const int cls = classify(b.nq, f.m, nullptr);
+                f.diag = !plan.has_srn && (cls == CLS_DIAG1 || cls == CLS_DIAG2);
+            }
             ops.push_back(f);
         }
     }
@@ -528,12 +546,14 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
         std::vector<char> in_tile(N, 0), blocked(N, 0);
         for (int l = 0; l < N; l++)
         {
-            if (phys[l] >= M) blocked[l] = 1; // rank bits: not addressable inside a shard
+            if (phys[l] >= M) blocked[l] = 2; // rank bits: not addressable inside a shard
             if (phys[l] < lowb) { in_tile[l] = 1; c.tile_logical.push_back(l); }
         }
         int tile_cnt = (int)c.tile_logical.size();
         int n_free_bits = 0;
-        for (int l = 0; l < N; l++) n_free_bits += !blocked[l];
+        for (int l = 0; l < N; l++) n_free_bits += blocked[l] != 2;
+        // blocked[bit]: 0 free, 1 only DIAGONAL ops were skipped on this bit (a later diagonal op commutes with all of
+        // them and may still run in this sweep), 2 closed
         auto visit = [&](size_t i) {
             FlatOp& f = ops[i];
             if (f.done) return;
@@ -541,7 +561,8 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
             int need = 0;
             for (int b = 0; b < f.nb; b++)
             {
-                if (blocked[f.bit[b]]) blk = true;
+                const int lvl = blocked[f.bit[b]];
+                if (lvl == 2 || (lvl == 1 && !f.diag)) blk = true;
                 else if (!in_tile[f.bit[b]]) need++;
             }
             if (!blk && tile_cnt + need <= kmax && (int)c.picked.size() < opt.max_ops)
@@ -553,7 +574,14 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
             }
             else
                 for (int b = 0; b < f.nb; b++)
-                    if (!blocked[f.bit[b]]) { blocked[f.bit[b]] = 1; n_free_bits--; }
+                {
+                    const char lvl = f.diag ? 1 : 2;
+                    if (blocked[f.bit[b]] < lvl)
+                    {
+                        if (lvl == 2) n_free_bits--;
+                        blocked[f.bit[b]] = lvl;
+                    }
+                }
         };
         // strategy 0: program order (L and R interleaved); 1: all L parts first; 2: all R parts first
         if (plan.has_srn)
@@ -637,10 +665,101 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
         while (first_pending < ops.size() && ops[first_pending].done) first_pending++;
     };
 
+    // ---- gain-driven tile selection --------------------------------------------------------------------------
+    // scan_fixed: with the tile bit set FIXED, which pending ops can run (program order per bit, diagonal ops may hop
+    // over skipped diagonal ops)?  Returns the total weight; fills picked when asked.
+    auto scan_fixed = [&](const std::vector<char>& in_tile, std::vector<int>* picked) -> long {
+        std::vector<char> blocked(N, 0);
+        int n_open = 0;
+        for (int l = 0; l < N; l++) n_open += in_tile[l] ? 1 : 0;
+        long score = 0;
+        int n_picked = 0;
+        for (size_t i = first_pending; i < ops.size() && n_open > 0; i++)
+        {
+            const FlatOp& f = ops[i];
+            if (f.done) continue;
+            bool ok = n_picked < opt.max_ops;
+            for (int b = 0; b < f.nb; b++)
+            {
+                const int lvl = blocked[f.bit[b]];
+                if (!in_tile[f.bit[b]] || lvl == 2 || (lvl == 1 && !f.diag)) ok = false;
+            }
+            if (ok)
+            {
+                score += f.weight;
+                n_picked++;
+                if (picked) picked->push_back((int)i);
+                continue;
+            }
+            const char lvl = f.diag ? 1 : 2;
+            for (int b = 0; b < f.nb; b++)
+                if (blocked[f.bit[b]] < lvl)
+                {
+                    if (lvl == 2 && in_tile[f.bit[b]]) n_open--;
+                    blocked[f.bit[b]] = lvl;
+                }
+        }
+        return score;
+    };
+    auto build_by_gain = [&]() {
+        Candidate c;
+        std::vector<char> in_tile(N, 0);
+        for (int l = 0; l < N; l++)
+            if (phys[l] < lowb) { in_tile[l] = 1; c.tile_logical.push_back(l); }
+        long cur = scan_fixed(in_tile, nullptr);
+        while ((int)c.tile_logical.size() < kmax)
+        {
+            const int room = kmax - (int)c.tile_logical.size();
+            // candidate additions: the missing bits of the pending ops near the front (deduplicated)
+            std::vector<std::vector<int>> cands;
+            int looked = 0;
+            for (size_t i = first_pending; i < ops.size() && looked < 512; i++)
+            {
+                const FlatOp& f = ops[i];
+                if (f.done) continue;
+                looked++;
+                std::vector<int> miss;
+                bool local = true;
+                for (int b = 0; b < f.nb; b++)
+                {
+                    if (phys[f.bit[b]] >= M) local = false;
+                    if (!in_tile[f.bit[b]] && std::find(miss.begin(), miss.end(), f.bit[b]) == miss.end()) miss.push_back(f.bit[b]);
+                }
+                if (!local || miss.empty() || (int)miss.size() > room) continue;
+                std::sort(miss.begin(), miss.end());
+                if (std::find(cands.begin(), cands.end(), miss) == cands.end()) cands.push_back(miss);
+            }
+            long best_gain = 0;
+            double best_rate = 0;
+            int best_i = -1;
+            for (size_t ci = 0; ci < cands.size(); ci++)
+            {
+                for (int b : cands[ci]) in_tile[b] = 1;
+                const long gain = scan_fixed(in_tile, nullptr) - cur;
+                for (int b : cands[ci]) in_tile[b] = 0;
+                const double rate = (double)gain / (double)cands[ci].size();
+                if (gain > 0 && (rate > best_rate || (rate == best_rate && gain > best_gain)))
+                {
+                    best_rate = rate; best_gain = gain; best_i = (int)ci;
+                }
+            }
+            if (best_i < 0) break;
+            for (int b : cands[best_i]) { in_tile[b] = 1; c.tile_logical.push_back(b); }
+            cur += best_gain;
+        }
+        c.score = scan_fixed(in_tile, &c.picked);
+        return c;
+    };
+
     while (n_pending > 0)
     {
         Candidate best;
         bool have = false;
+        if (!plan.has_srn)
+        {
+            best = build_by_gain();
+            have = true;
+        }
         for (int s = 0; s < (plan.has_srn ? 1 : 3); s++)
         {
             Candidate c = build_candidate(s);

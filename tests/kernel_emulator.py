@@ -12,6 +12,7 @@ import numpy as np
 
 CLS_DENSE1, CLS_DIAG1, CLS_MONO1, CLS_SRN1, CLS_DENSE2, CLS_DIAG2, CLS_MONO2 = range(7)
 NT = 256
+TB = 8  # log2(NT)
 
 
 def swz(e):
@@ -32,8 +33,8 @@ def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = No
     assert shard_in.size == tile_elems * n_tiles
     out = shard_in.copy() if shard_out is None else shard_out
     t = np.arange(NT, dtype=np.int64)
-    klo = min(k, 8)
-    n_it = 1 if k <= 8 else 1 << (k - 8)
+    klo = min(k, TB)
+    n_it = 1 if k <= TB else 1 << (k - TB)
     act = t < tile_elems
     g_in_lo = _dep(t, dev["gin"][:klo])
     g_out_lo = _dep(t, dev["gout"][:klo])
@@ -46,14 +47,14 @@ def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = No
     tiles = np.full((n_tiles, tile_elems), np.nan + 0j, dtype=np.complex128)
     for it in range(n_it):
         src = (base_in[:, None] | g_in_lo[None, act]) + int(dev["hin"][it])
-        tiles[:, (it << 8) | s_in[act]] = shard_in[src]
+        tiles[:, (it << TB) | s_in[act]] = shard_in[src]
     assert not np.isnan(tiles.real).any(), "load did not fill the tile"
 
     for grp in dev["groups"]:
         for w in range(grp["n_warps"]):
             wpart = grp["wtab"][w]
-            for o in range(grp["first"], grp["first"] + grp["count"]):
-                _apply_op(dev["ops"][o], tiles, wpart)
+            for ri in range(grp["first"], grp["first"] + grp["count"]):
+                _run_round(dev, dev["rounds"][ri], tiles, wpart)
 
     seen = np.zeros(shard_in.size, dtype=bool)
     for it in range(n_it):
@@ -65,60 +66,99 @@ def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = No
     return out
 
 
-def _apply_op(op, tiles, wpart):
-    cls, aux, n_iter, n_active = op["cls"], op["aux"], op["n_iter"], op["n_active"]
+RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE2, RC_DIAG2, RC_PERM2 = range(7)
+_POS2 = {0: (1, 0), 1: (2, 0), 2: (2, 1)}
+_PERMS = {0: [0, 1, 3, 2], 1: [0, 3, 2, 1], 2: [0, 2, 1, 3]}
+
+
+def _round_items(rd, wpart):
+    lane = np.array(rd["lane_tab"][:rd["n_active"]], dtype=np.int64)
+    itab = np.array(rd["iter_tab"][:rd["n_iter"]], dtype=np.int64)
+    return ((lane[:, None] ^ wpart) ^ itab[None, :]).reshape(-1)
+
+
+def _run_round(dev, rd, tiles, wpart):
+    """One register round of one warp: load 8 elements per work item, apply the round's ops, store back."""
+    base = _round_items(rd, wpart)
+    roff = [int(x) for x in rd["roff"]]
+    idx = [base ^ roff[c] for c in range(8)]
+    v = [tiles[:, i].copy() for i in idx]  # v[c]: (n_tiles, n_items)
+    for o in range(rd["first"], rd["first"] + rd["count"]):
+        _apply_reg_op(dev["ops"][o], v)
+    for c in range(8):  # duplicates (tiny tiles) carry identical values
+        tiles[:, idx[c]] = v[c]
+
+
+def _apply_reg_op(op, v):
+    code, aux, pos = op["code"], op["aux"], op["pos"]
     m = np.array(op["m"], dtype=np.float64)
     m = m[0::2] + 1j * m[1::2]
-    lane = np.array(op["lane_tab"][:n_active], dtype=np.int64)
-    itab = np.array(op["iter_tab"][:n_iter], dtype=np.int64)
-    x = ((lane[:, None] ^ wpart) ^ itab[None, :]).reshape(-1)  # member-0 index of every work item
-    off = [int(v) for v in op["off"]]
-    nmem = 4 if cls >= CLS_DENSE2 else 2
-    idx = [x ^ off[c] for c in range(nmem)]
-    allidx = np.concatenate(idx)
-    assert len(np.unique(allidx)) == allidx.size, "work items of one warp overlap"
-    v = [tiles[:, i].copy() for i in idx]
-    skip = (aux >> 8) & 15
-    unit = (aux >> 12) & 1
-    if cls == CLS_DENSE2:
-        for r in range(4):
-            tiles[:, idx[r]] = sum(m[4 * r + c] * v[c] for c in range(4))
-    elif cls == CLS_DENSE1:
-        tiles[:, idx[0]] = m[0] * v[0] + m[1] * v[1]
-        tiles[:, idx[1]] = m[2] * v[0] + m[3] * v[1]
-    elif cls in (CLS_DIAG2, CLS_DIAG1):
-        for r in range(nmem):
-            if not (skip >> r) & 1:
-                tiles[:, idx[r]] = m[r] * v[r]
-    elif cls == CLS_MONO2:
-        for r in range(4):
-            if not (skip >> r) & 1:
-                s = (aux >> (2 * r)) & 3
-                tiles[:, idx[r]] = v[s] if unit else m[r] * v[s]
-    elif cls == CLS_MONO1:
-        tiles[:, idx[0]] = v[1] if unit else m[0] * v[1]
-        tiles[:, idx[1]] = v[0] if unit else m[1] * v[0]
-    elif cls == CLS_SRN1:
-        re = 0.5 * (v[0].real + v[1].real)
-        tiles[:, idx[0]] = re + 1j * 0.5 * (v[0].imag - v[1].imag)
-        tiles[:, idx[1]] = re + 1j * 0.5 * (-v[0].imag + v[1].imag)
-    else:
-        raise ValueError(cls)
+    skip, unit = (aux >> 8) & 15, (aux >> 12) & 1
+    if code == 7:  # RC_DIAG3
+        for c in range(8):
+            if not (aux >> c) & 1:
+                v[c] = m[c] * v[c]
+        return
+    if code in (RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1):
+        b = 1 << pos
+        for q in range(8):
+            if q & b:
+                continue
+            a0, a1 = v[q].copy(), v[q | b].copy()
+            if code == RC_DENSE1:
+                v[q], v[q | b] = m[0] * a0 + m[1] * a1, m[2] * a0 + m[3] * a1
+            elif code == RC_DIAG1:
+                if not skip & 1:
+                    v[q] = m[0] * a0
+                if not skip & 2:
+                    v[q | b] = m[1] * a1
+            elif code == RC_MONO1:
+                v[q], v[q | b] = (a1, a0) if unit else (m[0] * a1, m[1] * a0)
+            else:
+                re = 0.5 * (a0.real + a1.real)
+                v[q] = re + 1j * 0.5 * (a0.imag - a1.imag)
+                v[q | b] = re + 1j * 0.5 * (-a0.imag + a1.imag)
+        return
+    ph_, pl_ = _POS2[pos]
+    bh, bl = 1 << ph_, 1 << pl_
+    for q in range(8):
+        if q & (bh | bl):
+            continue
+        ids = [q, q | bl, q | bh, q | bh | bl]
+        a = [v[i].copy() for i in ids]
+        if code == RC_DENSE2:
+            for r in range(4):
+                v[ids[r]] = sum(m[4 * r + c] * a[c] for c in range(4))
+        elif code == RC_DIAG2:
+            for r in range(4):
+                if not (skip >> r) & 1:
+                    v[ids[r]] = m[r] * a[r]
+        elif code == RC_PERM2:
+            src = _PERMS[aux & 3]
+            for r in range(4):
+                v[ids[r]] = a[src[r]] if unit else m[r] * a[src[r]]
+        else:
+            raise ValueError(code)
 
 
 def check_group_partition(dev: dict):
-    """Every group's warps x lanes x iterations x members must tile the 2^k elements exactly once per op."""
+    """Every round's warps x lanes x iterations x 8 registers must cover the 2^k tile elements exactly once
+    (for tiles with fewer than 2^kRegBits register bits, duplicates of the same element are allowed)."""
     k = dev["k"]
     for grp in dev["groups"]:
-        for o in range(grp["first"], grp["first"] + grp["count"]):
-            op = dev["ops"][o]
-            nmem = 4 if op["cls"] >= CLS_DENSE2 else 2
-            lane = np.array(op["lane_tab"][:op["n_active"]], dtype=np.int64)
-            itab = np.array(op["iter_tab"][:op["n_iter"]], dtype=np.int64)
-            wt = np.array(grp["wtab"][:grp["n_warps"]], dtype=np.int64)
-            x = (wt[:, None, None] ^ lane[None, :, None] ^ itab[None, None, :]).reshape(-1)
-            allidx = np.concatenate([x ^ int(op["off"][c]) for c in range(nmem)])
-            assert allidx.size == 1 << k and len(np.unique(allidx)) == 1 << k, (grp, op["cls"])
+        for ri in range(grp["first"], grp["first"] + grp["count"]):
+            rd = dev["rounds"][ri]
+            wt = [int(x) for x in grp["wtab"][:grp["n_warps"]]]
+            allidx = []
+            for w in wt:
+                base = _round_items(rd, w)
+                for c in range(8):
+                    allidx.append(base ^ int(rd["roff"][c]))
+            allidx = np.concatenate(allidx)
+            uniq = np.unique(allidx)
+            assert len(uniq) == 1 << k, (k, grp, rd)
+            if k - (3 if grp["n_warps"] == 8 else 0) >= 3:
+                assert allidx.size == 1 << k
 
 
 def run_plan_dev(plan: dict, vec_logical: np.ndarray) -> np.ndarray:
