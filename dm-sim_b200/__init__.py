@@ -149,13 +149,13 @@ def pack_gates(gates):
     return rec, mats
 
 
-def plan_json(n_qubits, world_size, gates, start_layout=None, conj_state=False) -> dict:
+def plan_json(n_qubits, world_size, gates, start_layout=None, conj_state=False, non_hermitian=False) -> dict:
     """The schedule the engine would run (host-only planner; works without a GPU)."""
     rec, mats = gates if isinstance(gates, tuple) else pack_gates(gates)
     L = lib()
     lay = None if start_layout is None else np.ascontiguousarray(start_layout, dtype=np.int32)
     args = (n_qubits, world_size, rec.ctypes.data, len(rec), mats.ctypes.data if mats.size else None, mats.size // 32,
-            lay.ctypes.data if lay is not None else None, int(bool(conj_state)))
+            lay.ctypes.data if lay is not None else None, int(bool(conj_state)) | (int(bool(non_hermitian)) << 1))
     need = L.dmb_plan_json(*args, None, 0)
     if need < 0:
         _check(int(need))

@@ -118,6 +118,7 @@ struct dmb_sim
     int cur = 0;
     std::vector<int> layout; // physical bit of logical bit
     bool conj_flag = false;  // stored array = conj(state), see Plan::conj_start
+    bool non_hermitian = false; // an SRN run or dmb_set_dm may have left a non-Hermitian state (see plan.cpp)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_comm; // pairs around exchanges
@@ -128,7 +129,7 @@ struct dmb_sim
     bool have_circuit = false;
     Plan plan;
     std::vector<int> plan_layout; // layout the plan was made for
-    bool plan_conj = false;
+    bool plan_conj = false, plan_nonherm = false;
     DevOp* d_ops = nullptr;
     size_t d_ops_cap = 0;
     std::vector<size_t> op_offset;    // per step: first DevOp
@@ -262,6 +263,7 @@ int dmb_reset_dm(dmb_handle s)
     CU(cudaSetDevice(s->device));
     for (int l = 0; l < s->N; l++) s->layout[l] = l;
     s->conj_flag = false;
+    s->non_hermitian = false;
     s->cur = 0;
     launch_init_state(s->buf[0], s->shard_elems, s->rank == 0, s->stream);
     CU(cudaGetLastError());
@@ -276,6 +278,7 @@ int dmb_set_dm(dmb_handle s, const double* real, const double* imag)
     CU(cudaSetDevice(s->device));
     for (int l = 0; l < s->N; l++) s->layout[l] = l;
     s->conj_flag = false;
+    s->non_hermitian = true; // arbitrary input: keep the reference's exact frame semantics from here on
     const unsigned long long total = 1ull << s->N;
     const unsigned long long chunk = std::min<unsigned long long>(total, 1ull << 24);
     int rc = ensure_scratch(s, chunk * 2 * sizeof(double));
@@ -300,7 +303,7 @@ static int build_plan(dmb_sim* s)
     try
     {
         s->plan = make_plan(s->n, s->world, s->gates.data(), s->gates.size(), s->mats.data(), s->mats.size() / 32,
-                            s->layout, g_opt, s->conj_flag);
+                            s->layout, g_opt, s->conj_flag, s->non_hermitian);
     }
     catch (const std::invalid_argument& e)
     {
@@ -312,6 +315,7 @@ static int build_plan(dmb_sim* s)
     }
     s->plan_layout = s->layout;
     s->plan_conj = s->conj_flag;
+    s->plan_nonherm = s->non_hermitian;
     drop_graph(s);
     // device op / group tables: one contiguous upload each (the reference does 3 CUDA calls per gate per GPU, :112-163)
     std::vector<DevOp> host_ops;
@@ -486,7 +490,7 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
     if (!s) return fail(DMB_EINVAL, "null handle");
     if (!s->have_circuit) return fail(DMB_ESTATE, "dmb_run before dmb_set_circuit");
     CU(cudaSetDevice(s->device));
-    if (s->plan_layout != s->layout || s->plan_conj != s->conj_flag)
+    if (s->plan_layout != s->layout || s->plan_conj != s->conj_flag || s->plan_nonherm != s->non_hermitian)
     {
         int rc = build_plan(s); // state layout changed since planning (reset / previous run): re-plan
         if (rc) return rc;
@@ -537,6 +541,7 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
     s->cur = cur;
     s->layout = s->plan.end_layout;
     s->conj_flag = s->plan.conj_end;
+    if (s->plan.has_srn) s->non_hermitian = true;
     if (stats)
     {
         memset(stats, 0, sizeof(*stats));
@@ -705,7 +710,8 @@ int64_t dmb_plan_json(int n_qubits, int world_size, const dmb_gate* gates, size_
     {
         std::vector<int> start;
         if (start_layout) start.assign(start_layout, start_layout + 2 * n_qubits);
-        Plan p = make_plan(n_qubits, world_size, gates, n_gates, mats, n_mats, start, g_opt, conj_state != 0);
+        Plan p = make_plan(n_qubits, world_size, gates, n_gates, mats, n_mats, start, g_opt, (conj_state & 1) != 0,
+                           (conj_state & 2) != 0);
         std::vector<std::string> extra(p.steps.size());
         for (size_t i = 0; i < p.steps.size(); i++)
         {

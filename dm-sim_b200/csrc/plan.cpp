@@ -477,7 +477,7 @@ struct Candidate
 } // namespace
 
 Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, const double* mats, size_t n_mats,
-               const std::vector<int>& start_layout, const PlanOptions& opt, bool conj_state)
+               const std::vector<int>& start_layout, const PlanOptions& opt, bool conj_state, bool non_hermitian)
 {
     if (n < 1 || n > 20) throw std::invalid_argument("n_qubits must be in [1, 20]");
     int g = 0;
@@ -841,8 +841,14 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
             else if (phys[l] >= M - g) phys[l] += g;
         }
     }
+    // Every sim() of the reference ends in its transposed frame: the result it reports is S' = conj(X'^T) where X' is
+    // what this plan computes (all L parts and all R parts applied without transposing).  For a Hermitian state the
+    // two coincide; for the non-Hermitian states SRN (or an arbitrary dmb_set_dm input) produces they do not.  The
+    // transpose costs nothing here: swap the row/column halves of the layout and flip the conjugation flag.
+    // (When the state is known to be Hermitian and the circuit has no SRN the frame change is the identity and is
+    // skipped, so that repeated runs of one circuit keep one plan / one CUDA graph.)
     plan.conj_start = plan.conj_end = conj_state;
-    if (plan.has_srn)
+    if (plan.has_srn || non_hermitian)
     {
         for (int l = 0; l < n; l++) std::swap(phys[l], phys[l + n]);
         plan.conj_end = !conj_state;

@@ -88,8 +88,9 @@ struct Plan
     uint64_t n_gates = 0, n_primitives = 0, n_blocks = 0, n_sweeps = 0, n_exchanges = 0;
     bool has_srn = false;
     // The stored array X relates to the state S the reference would hold by S = conj^f(X) (f = conj flag).
-    // A run containing SRN (real-linear, :1253-1266) ends in the reference's transposed frame: S' = conj(X'^T);
-    // instead of a transpose sweep the plan relabels row<->column bits in end_layout and flips the flag.
+    // Every reference sim() ends in its transposed frame, S' = conj(X'^T) (identical to X' only for Hermitian
+    // states; SRN, reference :1253-1266, breaks Hermiticity): instead of a transpose sweep the plan swaps the
+    // row / column halves of end_layout and flips the flag.
     bool conj_start = false, conj_end = false;
 };
 
@@ -98,7 +99,8 @@ void expand_gates(int n_qubits, const dmb_gate* gates, size_t n_gates, const dou
                   std::vector<Block>& prims);
 void fuse_blocks(int n_qubits, const std::vector<Block>& prims, std::vector<Block>& blocks);
 Plan make_plan(int n_qubits, int world_size, const dmb_gate* gates, size_t n_gates, const double* mats,
-               size_t n_mats, const std::vector<int>& start_layout, const PlanOptions& opt, bool conj_state = false);
+               size_t n_mats, const std::vector<int>& start_layout, const PlanOptions& opt, bool conj_state = false,
+               bool non_hermitian = false);
 // extra (optional): one JSON object text per step, spliced into sweep steps as "dev": {...}
 std::string plan_to_json(const Plan& p, const std::vector<std::string>* extra = nullptr);
 

@@ -127,7 +127,8 @@ int dmb_get_shard(dmb_handle h, double* interleaved, int32_t* phys_of_logical);
 /* ---- planner introspection (host only, needs no GPU): used by the CPU test-suite ----
  * Plans a circuit exactly as dmb_set_circuit would for (n_qubits, world_size) and writes a JSON
  * description of the sweeps / exchanges (tile bit positions, fused op matrices, final bit layout).
- * Returns the number of bytes needed (including NUL); writes at most cap bytes. */
+ * conj_state: bit 0 = the stored array is the conjugate of the state, bit 1 = the state may be non-Hermitian
+ * (both 0 after dmb_reset_dm).  Returns the number of bytes needed (including NUL); writes at most cap bytes. */
 int64_t dmb_plan_json(int n_qubits, int world_size, const dmb_gate* gates, size_t n_gates, const double* mats,
                       size_t n_mats, const int32_t* start_layout /* NULL = identity */, int conj_state, char* out,
                       size_t cap);

@@ -199,3 +199,104 @@ def test_large_n13_properties_and_parity(dm, oracle_mod):
     ore, oim = oracle_mod.Oracle(n).sim(gates).dm()
     assert max(np.abs(re - ore).max(), np.abs(im - oim).max()) < TOL
     assert np.abs(re - re.T).max() < TOL and np.abs(im + im.T).max() < TOL  # Hermitian
+
+
+import os as _os
+
+_GOLD = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["all_ops_n5", "random_mix_n6", "random_c1c2_n6", "srn_n4"])
+def test_reference_golden_full_matrix(dm, name):
+    """Outputs of the reference itself (tests/golden, produced by make_golden.py from oracle/_ref)."""
+    z = np.load(_os.path.join(_GOLD, name + ".npz"))
+    n = int(z["n"])
+    sim = dm.Simulation(n, 1)
+    rec, mats = z["gates"], np.ascontiguousarray(z["mats"])
+    dm._check(dm.lib().dmb_set_circuit(sim._h, rec.ctypes.data, len(rec), mats.ctypes.data if mats.size else None,
+                                       mats.size // 32))
+    sim._uploaded = True
+    sim.run()
+    re, im = sim.get_dm()
+    assert np.abs(re - z["real"]).max() < TOL and np.abs(im - z["imag"]).max() < TOL
+
+
+@pytest.mark.parametrize("name", ["adder_n10", "qft_n10", "vqe_uccsd_n8"])
+def test_reference_golden_diagonal(dm, name):
+    z = np.load(_os.path.join(_GOLD, name + ".npz"))
+    n = int(z["n"])
+    sim = dm.Simulation(n, 1)
+    rec, mats = z["gates"], np.ascontiguousarray(z["mats"])
+    dm._check(dm.lib().dmb_set_circuit(sim._h, rec.ctypes.data, len(rec), mats.ctypes.data if mats.size else None,
+                                       mats.size // 32))
+    sim._uploaded = True
+    sim.run()
+    assert np.abs(sim.diag() - z["diag"]).max() < TOL
+    assert abs(sim.trace() - z["diag"].sum()) < TOL
+
+
+def test_srn_continuation_two_runs(dm, oracle_mod):
+    """After an SRN run the state is not Hermitian: the next run must follow the reference's frame exactly."""
+    n = 5
+    rng = np.random.default_rng(17)
+    a = random_gates(n, 15, rng) + [("SRN", [2], 0, 0, 0)] + random_gates(n, 5, rng)
+    b = random_gates(n, 20, rng)
+    c = [("SRN", [0], 0, 0, 0)] + random_gates(n, 10, rng)
+    sim = dm.Simulation(n, 1)
+    o = oracle_mod.Oracle(n)
+    for part in (a, b, c):
+        rec, mats = dm.pack_gates(part)
+        dm._check(dm.lib().dmb_set_circuit(sim._h, rec.ctypes.data, len(rec), mats.ctypes.data if mats.size else None,
+                                           mats.size // 32))
+        sim._uploaded = True
+        sim.run()
+        o.sim(part)
+        re, im = sim.get_dm()
+        ore, oim = o.dm()
+        assert max(np.abs(re - ore).max(), np.abs(im - oim).max()) < TOL
+        assert np.abs(sim.diag() - o.diag()).max() < TOL
+
+
+def test_repeated_runs_of_one_circuit(dm, oracle_mod):
+    """bench.py's loop: the same uploaded circuit run again and again on the evolving state."""
+    n = 7
+    rng = np.random.default_rng(23)
+    gates = random_gates(n, 40, rng)
+    sim = run_gpu(dm, n, gates)
+    sim.run()
+    sim.run()
+    o = oracle_mod.Oracle(n).sim(gates).sim(gates).sim(gates)
+    re, im = sim.get_dm()
+    ore, oim = o.dm()
+    assert max(np.abs(re - ore).max(), np.abs(im - oim).max()) < TOL
+
+
+def test_cxx_dropin_example_runs(dm, tmp_path):
+    """examples/adder_n10.cpp (the reference's example driver on include/dmsim_b200.hpp) prints 1000000010 x5."""
+    import subprocess
+    root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    lib = _os.path.join(root, "dm-sim_b200", "lib")
+    exe = tmp_path / "adder"
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-I", _os.path.join(root, "include"),
+                    _os.path.join(root, "examples", "adder_n10.cpp"), "-o", str(exe), "-L", lib, "-ldmsim_b200",
+                    "-Wl,-rpath," + lib], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("1000000010") == 5 and "nqubits:10, ngates:30" in r.stdout
+
+
+def test_pybind_module_runs_a_generated_script(dm, tmp_path):
+    """tool/dmsim_qasm.py output executed with the drop-in pybind11 module, as the reference's workflow does."""
+    import subprocess
+    import sys
+    root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    q = tmp_path / "c.qasm"
+    q.write_text('OPENQASM 2.0;\ninclude "qelib1.inc";\nqreg q[4];\nx q[0];\ncx q[0],q[3];\nccx q[0],q[3],q[2];\n')
+    out = tmp_path / "c.py"
+    subprocess.run([sys.executable, _os.path.join(root, "tool", "dmsim_qasm.py"), "-i", str(q), "-o", str(out)], check=True)
+    script = out.read_text().replace("sim.measure(10)", "print('RESULT', sim.measure(10))")
+    out.write_text(script)
+    env = dict(_os.environ, PYTHONPATH=root)
+    r = subprocess.run([sys.executable, str(out), "4", "1"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "RESULT [13, 13, 13, 13, 13, 13, 13, 13, 13, 13]" in r.stdout  # |1101> : q0, q2, q3 set

@@ -1,0 +1,137 @@
+"""CPU: the C++ host pipeline (expand -> fuse -> schedule -> encode) checked against the oracle and the reference's
+golden vectors WITHOUT a GPU, through two numpy interpreters of what the planner emits:
+  plan_emulator   : executes the schedule with the full op matrices (scheduling / fusion / remap bookkeeping),
+  kernel_emulator : walks the device tables exactly as sweep_kernel indexes them (encoder + addressing scheme)."""
+import os
+
+import numpy as np
+import pytest
+
+import kernel_emulator as ke
+import plan_emulator as pe
+from helpers import each_op_once, random_gates, to_complex
+from test_oracle import FULL, load_golden
+
+TOL = 1e-12
+
+
+def zero_state(n):
+    v = np.zeros(4 ** n, dtype=np.complex128)
+    v[0] = 1.0
+    return v
+
+
+@pytest.fixture
+def opts(dm):
+    def set_(**kw):
+        for k, v in kw.items():
+            dm.set_option(k, v)
+    yield set_
+    dm.set_option("tile_bits", 12); dm.set_option("low_bits", 3); dm.set_option("min_tiles_log2", 10)
+
+
+@pytest.mark.parametrize("name", FULL)
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_schedule_reproduces_reference_golden(dm, name, world):
+    z, packed = load_golden(name)
+    n = int(z["n"])
+    plan = dm.plan_json(n, world, packed)
+    ref = to_complex(z["real"], z["imag"])
+    assert np.abs(pe.run_plan(plan, zero_state(n)) - ref).max() < TOL
+    assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - ref).max() < TOL
+
+
+@pytest.mark.parametrize("n,world,o", [
+    (1, 1, {}), (2, 1, {}), (3, 1, {}), (4, 1, {}), (6, 1, {}), (7, 1, {}),
+    (7, 1, dict(tile_bits=9, low_bits=2, min_tiles_log2=2)),
+    (6, 1, dict(tile_bits=6, low_bits=0, min_tiles_log2=2)),
+    (4, 1, dict(tile_bits=4, low_bits=1, min_tiles_log2=2)),
+    (6, 2, {}), (6, 4, {}), (7, 8, dict(tile_bits=7, low_bits=1)), (7, 4, dict(tile_bits=8)), (5, 8, {}), (3, 8, {}),
+])
+def test_random_circuits_every_geometry(dm, oracle_mod, opts, n, world, o):
+    opts(**o)
+    rng = np.random.default_rng(1000 + 10 * n + world)
+    gates = random_gates(n, 40, rng, exclude=())  # includes SRN (full-barrier path) and raw C1/C2
+    re, im = oracle_mod.Oracle(n).sim(gates).dm()
+    ref = to_complex(re, im)
+    plan = dm.plan_json(n, world, gates)
+    assert np.abs(pe.run_plan(plan, zero_state(n)) - ref).max() < TOL
+    assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - ref).max() < TOL
+    if world > 1:
+        assert plan["n_exchanges"] >= 1
+
+
+def test_each_op_alone(dm, oracle_mod):
+    rng = np.random.default_rng(3)
+    n = 5
+    prefix = random_gates(n, 8, rng, names=["U3", "CX", "H"], with_raw=False)
+    for g in each_op_once(n, rng) + [("SRN", [2], 0, 0, 0), ("ID", [1], 0, 0, 0)]:
+        gates = prefix + [g]
+        re, im = oracle_mod.Oracle(n).sim(gates).dm()
+        out = ke.run_plan_dev(dm.plan_json(n, 1, gates), zero_state(n))
+        assert np.abs(out - to_complex(re, im)).max() < TOL, g[0]
+
+
+def test_continuation_from_permuted_layout(dm, oracle_mod):
+    """A second circuit planned from the layout (and conjugation flag) the first one left behind."""
+    rng = np.random.default_rng(8)
+    n, world = 6, 4
+    a = random_gates(n, 30, rng) + [("SRN", [1], 0, 0, 0)]
+    b = random_gates(n, 30, rng)
+    p1 = dm.plan_json(n, world, a)
+    v1 = ke.run_plan_dev(p1, zero_state(n))
+    assert p1["end_layout"] != list(range(2 * n)) and p1["conj_end"]
+    p2 = dm.plan_json(n, world, b, start_layout=p1["end_layout"], conj_state=p1["conj_end"], non_hermitian=True)
+    v2 = ke.run_plan_dev(p2, v1)
+    re, im = oracle_mod.Oracle(n).sim(a).sim(b).dm()
+    assert np.abs(v2 - to_complex(re, im)).max() < TOL
+
+
+def test_one_exchange_per_run_like_the_reference(dm):
+    """The reference needs exactly one all-to-all per sim(); so does the planner from reset."""
+    rng = np.random.default_rng(9)
+    for n, world in [(8, 2), (8, 4), (9, 8)]:
+        gates = random_gates(n, 60, rng)
+        assert dm.plan_json(n, world, gates)["n_exchanges"] == 1
+
+
+def test_fusion_and_sweep_counts_of_named_workloads(dm):
+    import importlib
+    C = importlib.import_module("dm-sim_b200.circuits")
+    p = dm.plan_json(10, 1, C.adder_n10())
+    assert (p["n_gates"], p["n_primitives"]) == (30, 142)  # example/adder_n10: 30 Gate objects = 142 primitives
+    p = dm.plan_json(15, 1, C.qft(15))
+    assert p["n_primitives"] == 540 and p["n_sweeps"] <= 10  # the reference needs 2 x 540 HBM sweeps
+    p = dm.plan_json(15, 1, C.bv(15))
+    assert p["n_primitives"] == 44 and p["n_sweeps"] <= 4
+    for st in p["steps"]:
+        assert st["in_pos"][:3] == [0, 1, 2], "every tile keeps the 3 lowest physical bits: >= 128 B HBM runs"
+
+
+def test_invalid_arguments_are_rejected(dm):
+    with pytest.raises(dm.DMSimError, match="out of range"):
+        dm.plan_json(3, 1, [("H", [3], 0, 0, 0)])
+    with pytest.raises(dm.DMSimError, match="out of range"):
+        dm.plan_json(3, 1, [("H", [0, 7], 0, 0, 0)])  # append() asserts every qb < n_qubits, used or not
+    with pytest.raises(dm.DMSimError, match="repeated"):
+        dm.plan_json(3, 1, [("CX", [1, 1], 0, 0, 0)])
+    with pytest.raises(dm.DMSimError, match="power of two"):
+        dm.plan_json(3, 3, [("H", [0], 0, 0, 0)])
+    with pytest.raises(dm.DMSimError, match="divide"):
+        dm.plan_json(2, 8, [("H", [0], 0, 0, 0)])
+    with pytest.raises(dm.DMSimError, match="unknown op"):
+        rec, mats = dm.pack_gates([("H", [0], 0, 0, 0)])
+        rec[0]["op"] = 77
+        dm.plan_json(3, 1, (rec, mats))
+    assert dm.plan_json(3, 1, [])["n_sweeps"] == 0  # empty circuit
+
+
+def test_large_op_counts_split_into_sweeps(dm, oracle_mod):
+    """More ops than the kernel's shared-memory op table holds: the planner must split the sweep."""
+    rng = np.random.default_rng(4)
+    n = 4
+    gates = random_gates(n, 400, rng)
+    plan = dm.plan_json(n, 1, gates)
+    assert all(len(st["ops"]) <= 112 for st in plan["steps"]) and plan["n_sweeps"] > 1
+    re, im = oracle_mod.Oracle(n).sim(gates).dm()
+    assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - to_complex(re, im)).max() < TOL

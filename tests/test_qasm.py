@@ -1,0 +1,131 @@
+"""CPU: the OpenQASM front-end (dm-sim_b200/qasm.py, tool/dmsim_qasm.py) -- against the reference's own translator
+(executed under a Python-3 shim when its tree is present), the golden gate list, and the oracle."""
+import glob
+import importlib
+import io
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+qasm = importlib.import_module("dm-sim_b200.qasm")
+
+SMALL = """OPENQASM 2.0;
+include "qelib1.inc";
+// a comment line
+qreg a[2];
+qreg b[3];
+creg c[5];
+gate foo(theta, phi) x, y { u3(theta, phi, pi/2) x; cx x, y; rz(-theta/2) y; }
+h a;            // broadcast over the register
+cx a, b[1];
+foo(pi/3, 0.25) a[1], b[2];
+cu1(pi/4) b[0], b[2]; barrier a; measure a[0] -> c[0];
+ccx a[0], a[1], b[0];
+"""
+
+
+def test_load_semantics():
+    n, g = qasm.load(SMALL)
+    assert n == 5
+    names = [x[0] for x in g]
+    assert names == ["H", "H", "CX", "CX", "U3", "CX", "RZ", "CU1", "CCX"]
+    assert g[2][1] == [0, 3] and g[3][1] == [1, 3]          # b[1] is global qubit 3
+    assert g[4][1] == [1] and abs(g[4][2] - np.pi / 3) < 1e-15 and g[4][3] == 0.25 and abs(g[4][4] - np.pi / 2) < 1e-15
+    assert g[6][0] == "RZ" and abs(g[6][3] + np.pi / 6) < 1e-15 and g[6][2] == 0.0   # RZ stores its angle in phi
+    assert g[7][0] == "CU1" and abs(g[7][4] - np.pi / 4) < 1e-15                     # CU1 stores it in lambda
+    with pytest.raises(qasm.QasmError):
+        qasm.load("qreg q[2]; frobnicate q[0];")
+    with pytest.raises(qasm.QasmError):
+        qasm.load("qreg q[2]; h q[5];")
+
+
+def test_translated_script_shape_and_stats():
+    script, stats = qasm.translate(SMALL)
+    assert script.startswith("import sys\nimport dmsim_py_omp_wrapper as dmsim\n")
+    assert "sim = dmsim.Simulation(int(sys.argv[1]), int(sys.argv[2]))" in script
+    assert "sim.append(sim.H(0))\nsim.append(sim.H(1))\n" in script
+    assert "def foo(sim, theta, phi, x, y):" in script
+    assert script.endswith("\nsim.upload()\nsim.run()\nsim.measure(10)\n")
+    assert stats == {"n_qubits": 5, "basic_gates": 2 + 2 + 3 + 5 + 15, "cnot_gates": 2 + 1 + 2 + 6}
+    compile(script, "circuit.py", "exec")  # valid Python 3
+
+
+def test_golden_vqe_gate_list_matches_parser():
+    if not os.path.exists(REF):
+        pytest.skip("reference tree not present")
+    z = np.load(os.path.join(ROOT, "tests", "golden", "vqe_uccsd_n8.npz"))
+    dm = importlib.import_module("dm-sim_b200")
+    n, g = qasm.load_file(os.path.join(REF, "benchmark", "vqe_uccsd_n8.qasm"))
+    rec, _ = dm.pack_gates(g)
+    assert n == 8 and len(g) == 10808 and rec.tobytes() == z["gates"].tobytes()
+
+
+def _run_reference_translator(path, out):
+    """Executes the reference's Python-2 tool under Python 3 with its two dict-concatenation lines patched in memory."""
+    with open(os.path.join(REF, "tool", "dmsim_qasm.py")) as f:
+        src = f.read()
+    src = src.replace("dict(STANDARD_GATE_TABLE.items() + COMPOSITION_GATE_TABLE.items())",
+                      "dict(list(STANDARD_GATE_TABLE.items()) + list(COMPOSITION_GATE_TABLE.items()))")
+    src = src.replace("dict(STANDARD_CX_TABLE.items() + COMPOSITION_CX_TABLE.items())",
+                      "dict(list(STANDARD_CX_TABLE.items()) + list(COMPOSITION_CX_TABLE.items()))")
+    argv, stdout = sys.argv, sys.stdout
+    sys.argv, sys.stdout = ["dmsim_qasm.py", "-i", path, "-o", out], io.StringIO()
+    try:
+        exec(compile(src, "ref_dmsim_qasm.py", "exec"), {"__name__": "__main__"})
+        printed = sys.stdout.getvalue()
+    finally:
+        sys.argv, sys.stdout = argv, stdout
+    with open(out) as f:
+        return f.read(), printed
+
+
+@pytest.mark.parametrize("name", ["bv_n15", "qft_n15", "adder_n9", "cc_n15", "vqe_uccsd_n8", "qec_n5", "w_state_n3",
+                                  "grover_n3", "sat_n10", "deutsch_n5"])
+def test_same_output_as_the_reference_translator(tmp_path, name):
+    if not os.path.exists(REF):
+        pytest.skip("reference tree not present")
+    path = os.path.join(REF, "benchmark", name + ".qasm")
+    ref_script, ref_printed = _run_reference_translator(path, str(tmp_path / "ref.py"))
+    with open(path) as f:
+        mine, stats = qasm.translate(f.read())
+
+    def body(s):  # the gate-appending lines, whitespace-normalised
+        return [ln.strip() for ln in s.splitlines() if "sim.append" in ln or ln.strip().endswith(")") and "(sim" in ln]
+    assert body(mine) == body(ref_script)
+    assert f"Number of qubits: {stats['n_qubits']}" in ref_printed
+    assert f"Number of basic gates: {stats['basic_gates']}" in ref_printed
+    assert f"Number of cnot gates: {stats['cnot_gates']}" in ref_printed
+
+
+def test_cli(tmp_path):
+    src = tmp_path / "c.qasm"
+    src.write_text(SMALL)
+    out = tmp_path / "c.py"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tool", "dmsim_qasm.py"), "-i", str(src), "-o", str(out)],
+                       capture_output=True, text=True, check=True)
+    assert "Number of qubits: 5" in r.stdout and "Number of basic gates: 27" in r.stdout
+    assert "sim.append(sim.CCX(0, 1, 2))" in out.read_text()
+
+
+def test_generators_match_the_benchmark_files():
+    if not os.path.exists(REF):
+        pytest.skip("reference tree not present")
+    C = importlib.import_module("dm-sim_b200.circuits")
+    assert qasm.load_file(os.path.join(REF, "benchmark", "qft_n15.qasm")) == (15, C.qft(15))
+    assert qasm.load_file(os.path.join(REF, "benchmark", "bv_n15.qasm")) == (15, C.bv(15))
+    n, g = qasm.load_file(os.path.join(REF, "benchmark", "adder_n9.qasm"))
+    assert n == 10 and len(g) == 30 and sorted(x[0] for x in g) == sorted(x[0] for x in C.adder_n10())
+
+
+def test_qasm_circuit_against_oracle(dm, oracle_mod):
+    import kernel_emulator as ke
+    n, g = qasm.load(SMALL)
+    re, im = oracle_mod.Oracle(n).sim(g).dm()
+    v0 = np.zeros(4 ** n, dtype=np.complex128); v0[0] = 1
+    out = ke.run_plan_dev(dm.plan_json(n, 1, g), v0)
+    assert np.abs(out - (re + 1j * im).reshape(-1)).max() < 1e-12
