@@ -135,6 +135,7 @@ struct dmb_sim
     std::vector<size_t> op_offset;    // per step: first DevOp
     std::vector<size_t> round_offset, group_offset; // per step: first DevRound / DevGroup
     std::vector<int> n_dev_ops, n_dev_rounds, n_dev_groups;
+    std::vector<unsigned> op_masks;   // per step: register-op codes present (kernel instantiation)
     DevRound* d_rounds = nullptr;
     DevGroup* d_groups = nullptr;
     size_t d_rounds_cap = 0, d_groups_cap = 0;
@@ -328,6 +329,7 @@ static int build_plan(dmb_sim* s)
     s->n_dev_ops.assign(nsteps, 0);
     s->n_dev_rounds.assign(nsteps, 0);
     s->n_dev_groups.assign(nsteps, 0);
+    s->op_masks.assign(nsteps, 0u);
     EncodedSweep enc;
     for (size_t i = 0; i < nsteps; i++)
     {
@@ -339,6 +341,7 @@ static int build_plan(dmb_sim* s)
         s->n_dev_ops[i] = (int)enc.ops.size();
         s->n_dev_rounds[i] = (int)enc.rounds.size();
         s->n_dev_groups[i] = (int)enc.groups.size();
+        for (const DevOp& d : enc.ops) s->op_masks[i] |= 1u << d.code;
         host_ops.insert(host_ops.end(), enc.ops.begin(), enc.ops.end());
         host_rounds.insert(host_rounds.end(), enc.rounds.begin(), enc.rounds.end());
         host_groups.insert(host_groups.end(), enc.groups.begin(), enc.groups.end());
@@ -418,6 +421,7 @@ static void fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, do
     a.n_ops = s->n_dev_ops[step];
     a.n_rounds = s->n_dev_rounds[step];
     a.n_groups = s->n_dev_groups[step];
+    a.op_mask = s->op_masks[step];
 }
 
 // enqueue every step of the plan on s->stream; cur is updated as buffers flip

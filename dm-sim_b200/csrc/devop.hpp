@@ -6,31 +6,40 @@
 namespace dmb
 {
 constexpr int kMaxTileBits = 12;  // 2^12 complex FP64 = 64 KiB of shared memory per CTA
-constexpr int kTileThreads = 256; // 8 warps; 2-3 CTAs per SM overlap each other's load / compute / store phases
-constexpr int kThreadBits = 8;    // log2(kTileThreads)
-constexpr int kWarpBits = 3;      // log2(warps per CTA)
-constexpr int kRegBits = 3;       // a lane keeps 2^3 tile elements (32 registers) resident per round
+constexpr int kTileThreads = 128; // 4 warps; 3 CTAs per SM overlap each other's load / compute / store phases and
+                                  // leave 170 registers per thread for the 16 resident elements of a round
+constexpr int kThreadBits = 7;    // log2(kTileThreads)
+constexpr int kWarpBits = 2;      // log2(warps per CTA)
+constexpr int kRegBits = 4;       // a lane keeps 2^4 tile elements (64 registers) resident per round
+constexpr int kRegElems = 1 << kRegBits;
+constexpr int kMaxIter = 1 << (kMaxTileBits - kThreadBits); // load / store iterations per thread
 constexpr int kMaxOpsPerSweep = 112;
 
-// XOR swizzle of the shared-memory tile (element = 16 B): low 3 element bits ^= bits 3..5, so that the 8 lanes of
-// an LDS.128 phase hit 8 different 16-byte bank groups for unit-stride as well as stride-2/4/8 element patterns.
-// GF(2)-linear: swz(a ^ b) == swz(a) ^ swz(b) -- the encoder pre-swizzles every index contribution.
-inline unsigned swz_host(unsigned e) { return e ^ ((e >> 3) & 7u); }
+// XOR swizzle of the shared-memory tile (element = 16 B): the low 3 element bits (the 16-byte bank group) are
+// XORed with bits 3..5, 6..8 and 9..11, so that tile bit p moves the bank group by the unit vector e_(p mod 3):
+// any three tile bits with different residues mod 3 enumerate 8 different bank groups.  The encoder gives lane bits
+// 0..2 (the 8 lanes of one LDS.128 / STS.128 phase) such positions.  Linear (thread-order) access is conflict free
+// for any swizzle of this form.  GF(2)-linear: swz(a ^ b) == swz(a) ^ swz(b) -- the encoder pre-swizzles every
+// index contribution.
+inline unsigned swz_host(unsigned e) { return e ^ ((e >> 3) & 7u) ^ ((e >> 6) & 7u) ^ ((e >> 9) & 7u); }
 
 // Register-level op codes (what the device switches on).  Two-bit ops are canonicalised by the encoder so that
 // the matrix MSB sits on the HIGHER register bit; `pos` then selects one of the pairs (1,0) (2,0) (2,1).
 enum RegOpCode : int32_t
 {
     RC_DENSE1 = 0, // m[0..3]
-    RC_DIAG1 = 1,  // m[0..1], skip mask in aux bits 8..9
+    RC_DIAG1 = 1,  // host-side only: folded into RC_DIAGR by the encoder
     RC_MONO1 = 2,  // out0 = m0*v1, out1 = m1*v0 (aux bit 12: unit phases)
     RC_SRN1 = 3,   // reference SRN_GATE (:1253-1266)
     RC_DENSE2 = 4, // m[0..15]
-    RC_DIAG2 = 5,  // m[0..3], skip mask in aux bits 8..11
+    RC_DIAG2 = 5,  // host-side only: folded into RC_DIAGR by the encoder
     RC_PERM2 = 6,  // monomial with a row permutation from {CX(msb ctrl), CX(lsb ctrl), SWAP}: aux bits 0..1 = which,
                    // m[0..3] = row phases, aux bit 12: unit phases
-    RC_DIAG3 = 7   // product of consecutive diagonal ops of a round: v[c] *= m[c] for the 8 registers, skip mask in
-                   // aux bits 0..7 (entries equal to 1)
+    RC_DIAGR = 7,  // product of consecutive diagonal ops of a round: v[c] *= m[c] for the 16 registers, skip mask in
+                   // aux bits 0..15 (entries equal to 1)
+    RC_DENSE1_RR = 8, // 2x2 with four REAL entries [[d0,d1],[d2,d3]] (H, RY, ...), |d0| not small, in the pivoted in-place
+                      // form m[0..3] = {d0, d1, d2/d0, det/d0}: half the FP64 work of RC_DENSE1 and no register copies
+    RC_DENSE1_RI = 9  // [[d0, i d1], [i d2, d3]] with real d (RX, W, ...), same form with det = d0 d3 + d1 d2
 };
 
 // One op of a round (272 bytes), applied to the lane's 2^kRegBits resident elements.
@@ -38,8 +47,8 @@ struct alignas(16) DevOp
 {
     int32_t code; // RegOpCode
     int32_t aux;
-    int32_t pos;  // 1-bit ops: register bit 0..2; 2-bit ops: 0 -> (1,0), 1 -> (2,0), 2 -> (2,1)  (msb, lsb)
-    int32_t pad;
+    int32_t pos;  // 1-bit ops: register bit 0..3; 2-bit ops: (msb, lsb) = (1,0) (2,0) (2,1) (3,0) (3,1) (3,2) -> 0..5
+    int32_t vid;  // code * 8 + pos: the kernel's jump-table index
     double m[32]; // up to 16 complex entries (re, im)
 };
 static_assert(sizeof(DevOp) == 272, "DevOp layout");
@@ -54,9 +63,9 @@ struct alignas(16) DevRound
     int32_t n_active; // active lanes (32 unless the sub-tile has fewer work items)
     uint16_t lane_tab[32];
     uint16_t iter_tab[8];
-    uint16_t roff[8];
+    uint16_t roff[16];
 };
-static_assert(sizeof(DevRound) == 112, "DevRound layout");
+static_assert(sizeof(DevRound) == 128, "DevRound layout");
 
 // A run of consecutive rounds that leave kWarpBits tile bits untouched: warp w owns the sub-tile where those bits
 // equal w and runs the whole group with __syncwarp() only; CTA barriers happen between groups.
@@ -79,12 +88,13 @@ struct SweepArgs
     const DevRound* rounds;
     const DevGroup* groups;
     int n_ops, n_rounds, n_groups;
+    unsigned op_mask;           // bit c set <=> some op of the sweep has RegOpCode c (selects the kernel instantiation)
     int k;                      // tile bits
     int n_comp;                 // M - k
     unsigned long long n_tiles; // 2^(M-k)
-    unsigned long long hin[16];  // element offset contributed by iteration `it` when loading
-    unsigned long long hout[16]; // ... when storing
-    unsigned short hs[16];       // swizzled smem index contributed by iteration `it` when storing
+    unsigned long long hin[kMaxIter];  // element offset contributed by iteration `it` when loading
+    unsigned long long hout[kMaxIter]; // ... when storing
+    unsigned short hs[kMaxIter];       // swizzled smem index contributed by iteration `it` when storing
     unsigned char gin[12];       // physical bit of loop bit i (< kThreadBits) when loading
     unsigned char gout[12];      // ... when storing
     unsigned char sout[12];      // tile-local bit of loop bit i (< kThreadBits) when storing

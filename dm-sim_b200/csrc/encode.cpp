@@ -71,15 +71,34 @@ DevOp make_reg_op(const TileOp& t, int p0, int p1)
         }
         else
         {
-            d.code = RC_DENSE1;
-            for (int i = 0; i < 4; i++) put(d, i, t.m[i]);
+            const bool rr = t.m[0].imag() == 0 && t.m[1].imag() == 0 && t.m[2].imag() == 0 && t.m[3].imag() == 0;
+            const bool ri = t.m[0].imag() == 0 && t.m[1].real() == 0 && t.m[2].real() == 0 && t.m[3].imag() == 0;
+            // pivoted in-place forms (see sweep_kernel.cu): only when the pivot d0 is comfortably away from zero
+            const bool pivot_ok = std::abs(t.m[0].real()) >= 0.25;
+            if (rr && pivot_ok)
+            {
+                d.code = RC_DENSE1_RR;
+                const double d0 = t.m[0].real(), d1 = t.m[1].real(), d2 = t.m[2].real(), d3 = t.m[3].real();
+                d.m[0] = d0; d.m[1] = d1; d.m[2] = d2 / d0; d.m[3] = (d0 * d3 - d1 * d2) / d0;
+            }
+            else if (ri && pivot_ok)
+            {
+                d.code = RC_DENSE1_RI;
+                const double d0 = t.m[0].real(), d1 = t.m[1].imag(), d2 = t.m[2].imag(), d3 = t.m[3].real();
+                d.m[0] = d0; d.m[1] = d1; d.m[2] = d2 / d0; d.m[3] = (d0 * d3 + d1 * d2) / d0;
+            }
+            else
+            {
+                d.code = RC_DENSE1;
+                for (int i = 0; i < 4; i++) put(d, i, t.m[i]);
+            }
         }
         return d;
     }
     cplx m[16];
     if (p0 > p1) memcpy(m, t.m, sizeof(m));
     else { swap_roles(t.m, m); std::swap(p0, p1); }
-    d.pos = (p0 == 1) ? 0 : (p1 == 0 ? 1 : 2); // (1,0) (2,0) (2,1)
+    d.pos = p0 * (p0 - 1) / 2 + p1; // (1,0) (2,0) (2,1) (3,0) (3,1) (3,2) -> 0..5
     int src[4];
     const int cls = classify(2, m, src);
     if (cls == CLS_DIAG2)
@@ -282,18 +301,18 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
             memset(&rd, 0, sizeof(rd));
             rd.first = (int32_t)out.ops.size();
             const int rd_first = rd.first;
-            for (int c = 0; c < 8; c++) rd.roff[c] = (uint16_t)swz_host(deposit((unsigned)c & ((1u << R) - 1u), rb));
+            for (int c = 0; c < kRegElems; c++) rd.roff[c] = (uint16_t)swz_host(deposit((unsigned)c & ((1u << R) - 1u), rb));
             std::vector<int> freep;
             for (int p = 0; p < k; p++)
                 if (!(((wmask | rmask) >> p) & 1u)) freep.push_back(p);
             const int nl = std::min(5, (int)freep.size());
             // lane bits 0..2 vary inside one LDS.128 phase: give them positions from three different swizzle
-            // classes ({0,3},{1,4},{2,5}) whenever one is free, so that the phase is bank-conflict free
+            // classes (p mod 3, see swz_host) whenever one is free, so that the phase is bank-conflict free
             std::vector<int> lanep;
             std::vector<char> taken(k, 0);
             for (int cls = 0; cls < 3 && (int)lanep.size() < nl; cls++)
-                for (int p : {cls, cls + 3})
-                    if (p < k && !taken[p] && std::find(freep.begin(), freep.end(), p) != freep.end())
+                for (int p : freep)
+                    if (p % 3 == cls && !taken[p])
                     {
                         lanep.push_back(p);
                         taken[p] = 1;
@@ -319,31 +338,31 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                 DevOp d = make_reg_op(t, p0, p1);
                 if (d.code == RC_DIAG1 || d.code == RC_DIAG2)
                 {
-                    // every diagonal op becomes an 8-entry diagonal over the round's register bits, and consecutive
+                    // every diagonal op becomes a 16-entry diagonal over the round's register bits, and consecutive
                     // ones are multiplied together on the host: one device op, no position dispatch
-                    cplx e[8];
-                    for (int c = 0; c < 8; c++)
+                    cplx e[kRegElems];
+                    for (int c = 0; c < kRegElems; c++)
                     {
                         int idx;
                         if (d.code == RC_DIAG1) idx = (c >> d.pos) & 1;
                         else
                         {
-                            static const int hi[3] = {1, 2, 2}, lo[3] = {0, 0, 1};
+                            static const int hi[6] = {1, 2, 2, 3, 3, 3}, lo[6] = {0, 0, 1, 0, 1, 2};
                             idx = 2 * ((c >> hi[d.pos]) & 1) + ((c >> lo[d.pos]) & 1);
                         }
                         e[c] = cplx(d.m[2 * idx], d.m[2 * idx + 1]);
                     }
-                    const bool merge = (int)out.ops.size() > rd_first && out.ops.back().code == RC_DIAG3;
+                    const bool merge = (int)out.ops.size() > rd_first && out.ops.back().code == RC_DIAGR;
                     DevOp nd;
                     if (merge) nd = out.ops.back();
                     else
                     {
                         memset(&nd, 0, sizeof(nd));
-                        nd.code = RC_DIAG3;
-                        for (int c = 0; c < 8; c++) put(nd, c, cplx(1.0, 0.0));
+                        nd.code = RC_DIAGR;
+                        for (int c = 0; c < kRegElems; c++) put(nd, c, cplx(1.0, 0.0));
                     }
                     int skip = 0;
-                    for (int c = 0; c < 8; c++)
+                    for (int c = 0; c < kRegElems; c++)
                     {
                         cplx v = cplx(nd.m[2 * c], nd.m[2 * c + 1]) * e[c];
                         // entries within 1e-15 of 1 (e.g. u1(a)*u1(-a) inside a fused controlled phase) are exactly 1
@@ -359,6 +378,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                 out.ops.push_back(d);
             }
             out.rounds.back().count = (int32_t)out.ops.size() - rd_first;
+            for (size_t o = (size_t)rd_first; o < out.ops.size(); o++) out.ops[o].vid = out.ops[o].code * 8 + out.ops[o].pos;
         }
         g.count = (int32_t)out.rounds.size() - g.first;
         out.groups.push_back(g);
@@ -383,7 +403,7 @@ void fill_sweep_tables(const Sweep& sw, int M, SweepArgs& a)
         a.gout[i] = (unsigned char)sw.out_pos[ord[i]];
         a.sout[i] = (unsigned char)ord[i];
     }
-    for (int it = 0; it < 16; it++)
+    for (int it = 0; it < kMaxIter; it++)
     {
         unsigned long long hi = 0, ho = 0;
         unsigned hs = 0;
@@ -417,9 +437,9 @@ std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a)
         o << "]";
     };
     o << "{\"k\":" << a.k << ",\"n_comp\":" << a.n_comp << ",";
-    arr("hin", a.hin, 16); o << ",";
-    arr("hout", a.hout, 16); o << ",";
-    arr("hs", a.hs, 16); o << ",";
+    arr("hin", a.hin, kMaxIter); o << ",";
+    arr("hout", a.hout, kMaxIter); o << ",";
+    arr("hs", a.hs, kMaxIter); o << ",";
     arr("gin", a.gin, 12); o << ",";
     arr("gout", a.gout, 12); o << ",";
     arr("sout", a.sout, 12); o << ",";
@@ -441,7 +461,7 @@ std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a)
           << ",\"n_active\":" << D.n_active << ",";
         arr("lane_tab", D.lane_tab, 32); o << ",";
         arr("iter_tab", D.iter_tab, 8); o << ",";
-        arr("roff", D.roff, 8);
+        arr("roff", D.roff, kRegElems);
         o << "}";
     }
     o << "],\"ops\":[";

@@ -19,7 +19,7 @@
 
 namespace dmb
 {
-__device__ __forceinline__ unsigned swz(unsigned e) { return e ^ ((e >> 3) & 7u); }
+__device__ __forceinline__ unsigned swz(unsigned e) { return e ^ ((e >> 3) & 7u) ^ ((e >> 6) & 7u) ^ ((e >> 9) & 7u); }
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b)
 {
@@ -45,17 +45,18 @@ __device__ __forceinline__ void st_stream(double2* p, double2 v)
 }
 
 // ------------------------------------------------------------------------------------------------
-// register-level op bodies.  A lane holds the 8 tile elements of its work item in v[0..7] (register index bit r
+// register-level op bodies.  A lane holds the 16 tile elements of its work item in v[0..15] (register index bit r
 // <-> round register bit r).  P / (PH, PL) are compile-time register bits, so every v[] index is static.
 // ------------------------------------------------------------------------------------------------
+constexpr int E = kRegElems;
 __device__ __forceinline__ const double2* op_m(const DevOp* op) { return reinterpret_cast<const double2*>(op->m); }
 
 template <int P>
-__device__ __forceinline__ void r_dense1(double2 (&v)[8], const DevOp* op)
+__device__ __forceinline__ void r_dense1(double2 (&v)[E], const DevOp* op)
 {
     const double2 m0 = op_m(op)[0], m1 = op_m(op)[1], m2 = op_m(op)[2], m3 = op_m(op)[3];
 #pragma unroll
-    for (int q = 0; q < 8; q++)
+    for (int q = 0; q < E; q++)
         if (!(q & (1 << P)))
         {
             const double2 a = v[q], b = v[q | (1 << P)];
@@ -63,45 +64,75 @@ __device__ __forceinline__ void r_dense1(double2 (&v)[8], const DevOp* op)
             v[q | (1 << P)] = cfma(m3, b, cmul(m2, a));
         }
 }
+// four real entries [[d0, d1], [d2, d3]] in pivoted IN-PLACE form (no temporaries to copy back, half the FP64
+// instructions of the generic 2x2): a' = d0 a + d1 b;  b' = (d2/d0) a' + (det/d0) b.  The encoder stores
+// e = {d0, d1, d2/d0, det/d0} and only emits this code when |d0| is not small.
 template <int P>
-__device__ __forceinline__ void r_diag1(double2 (&v)[8], const DevOp* op)
+__device__ __forceinline__ void r_dense1_rr(double2 (&v)[E], const DevOp* op)
 {
-    const int skip = (op->aux >> 8) & 3;
-    if (!(skip & 1))
-    {
-        const double2 d = op_m(op)[0];
+    const double e0 = op->m[0], e1 = op->m[1], e2 = op->m[2], e3 = op->m[3];
 #pragma unroll
-        for (int q = 0; q < 8; q++)
-            if (!(q & (1 << P))) v[q] = cmul(d, v[q]);
-    }
-    if (!(skip & 2))
-    {
-        const double2 d = op_m(op)[1];
+    for (int q = 0; q < E; q++)
+        if (!(q & (1 << P)))
+        {
+            double2& a = v[q];
+            double2& b = v[q | (1 << P)];
+            a.x = fma(e0, a.x, e1 * b.x);
+            a.y = fma(e0, a.y, e1 * b.y);
+            b.x = fma(e2, a.x, e3 * b.x);
+            b.y = fma(e2, a.y, e3 * b.y);
+        }
+}
+// [[d0, i d1], [i d2, d3]] with real d, same in-place form: a' = d0 a + i d1 b;  b' = i (d2/d0) a' + (det/d0) b with
+// det = d0 d3 + d1 d2.  e = {d0, d1, d2/d0, det/d0}
+template <int P>
+__device__ __forceinline__ void r_dense1_ri(double2 (&v)[E], const DevOp* op)
+{
+    const double e0 = op->m[0], e1 = op->m[1], e2 = op->m[2], e3 = op->m[3];
 #pragma unroll
-        for (int q = 0; q < 8; q++)
-            if (q & (1 << P)) v[q] = cmul(d, v[q]);
-    }
+    for (int q = 0; q < E; q++)
+        if (!(q & (1 << P)))
+        {
+            double2& a = v[q];
+            double2& b = v[q | (1 << P)];
+            a.x = fma(e0, a.x, -e1 * b.y);
+            a.y = fma(e0, a.y, e1 * b.x);
+            const double bx = fma(-e2, a.y, e3 * b.x);
+            b.y = fma(e2, a.x, e3 * b.y);
+            b.x = bx;
+        }
 }
 template <int P>
-__device__ __forceinline__ void r_mono1(double2 (&v)[8], const DevOp* op)
+__device__ __forceinline__ void r_mono1(double2 (&v)[E], const DevOp* op)
 {
-    const bool unit = (op->aux >> 12) & 1;
+    if ((op->aux >> 12) & 1) // unit phases (X): a register renaming
+    {
+#pragma unroll
+        for (int q = 0; q < E; q++)
+            if (!(q & (1 << P)))
+            {
+                const double2 a = v[q];
+                v[q] = v[q | (1 << P)];
+                v[q | (1 << P)] = a;
+            }
+        return;
+    }
     const double2 m0 = op_m(op)[0], m1 = op_m(op)[1];
 #pragma unroll
-    for (int q = 0; q < 8; q++)
+    for (int q = 0; q < E; q++)
         if (!(q & (1 << P)))
         {
             const double2 a = v[q], b = v[q | (1 << P)];
-            v[q] = unit ? b : cmul(m0, b);
-            v[q | (1 << P)] = unit ? a : cmul(m1, a);
+            v[q] = cmul(m0, b);
+            v[q | (1 << P)] = cmul(m1, a);
         }
 }
 // reference SRN_GATE (:1253-1266): re0'=re1'=(re0+re1)/2, im0'=(im0-im1)/2, im1'=(-im0+im1)/2
 template <int P>
-__device__ __forceinline__ void r_srn1(double2 (&v)[8])
+__device__ __forceinline__ void r_srn1(double2 (&v)[E])
 {
 #pragma unroll
-    for (int q = 0; q < 8; q++)
+    for (int q = 0; q < E; q++)
         if (!(q & (1 << P)))
         {
             const double2 a = v[q], b = v[q | (1 << P)];
@@ -110,98 +141,109 @@ __device__ __forceinline__ void r_srn1(double2 (&v)[8])
             v[q | (1 << P)] = make_double2(re, 0.5 * (-a.y + b.y));
         }
 }
-// register-light: the 4x4 matrix is streamed row by row from shared memory (broadcast LDS) instead of being held in
-// 64 registers, so that the kernel fits 3 CTAs per SM
+// 4x4 dense: two quads at a time, the matrix streamed row by row from shared memory (broadcast LDS.128): 32 matrix
+// loads per 256 DFMA, 32 temporaries -- the whole 4x4 in registers would not leave room for the 16 resident elements
 template <int PH, int PL>
-__device__ __forceinline__ void r_dense2(double2 (&v)[8], const DevOp* op)
+__device__ __forceinline__ void r_dense2(double2 (&v)[E], const DevOp* op)
 {
     constexpr int bh = 1 << PH, bl = 1 << PL;
+    constexpr int rest = (E - 1) & ~(bh | bl);   // the two register bits the op does not touch
+    constexpr int r0 = rest & -rest, r1 = rest & ~r0;
 #pragma unroll
-    for (int q = 0; q < 8; q++)
-        if (!(q & (bh | bl)))
-        {
-            const double2 v0 = v[q], v1 = v[q | bl], v2 = v[q | bh], v3 = v[q | bh | bl];
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-            {
-                const double2 m0 = op_m(op)[4 * r], m1 = op_m(op)[4 * r + 1], m2 = op_m(op)[4 * r + 2], m3 = op_m(op)[4 * r + 3];
-                v[q | ((r & 2) ? bh : 0) | ((r & 1) ? bl : 0)] = cfma(m3, v3, cfma(m2, v2, cfma(m1, v1, cmul(m0, v0))));
-            }
-        }
-}
-template <int PH, int PL>
-__device__ __forceinline__ void r_diag2(double2 (&v)[8], const DevOp* op)
-{
-    const int skip = (op->aux >> 8) & 15;
-    constexpr int bh = 1 << PH, bl = 1 << PL;
-#pragma unroll
-    for (int r = 0; r < 4; r++)
+    for (int half = 0; half < 2; half++)
     {
-        if ((skip >> r) & 1) continue;
-        const double2 d = op_m(op)[r];
+        const int qa = half ? r1 : 0, qb = qa | r0;
+        const double2 a0 = v[qa], a1 = v[qa | bl], a2 = v[qa | bh], a3 = v[qa | bh | bl];
+        const double2 b0 = v[qb], b1 = v[qb | bl], b2 = v[qb | bh], b3 = v[qb | bh | bl];
 #pragma unroll
-        for (int q = 0; q < 8; q++)
-            if ((q & (bh | bl)) == (((r & 2) ? bh : 0) | ((r & 1) ? bl : 0))) v[q] = cmul(d, v[q]);
+        for (int r = 0; r < 4; r++)
+        {
+            const double2 m0 = op_m(op)[4 * r], m1 = op_m(op)[4 * r + 1], m2 = op_m(op)[4 * r + 2], m3 = op_m(op)[4 * r + 3];
+            const int o = ((r & 2) ? bh : 0) | ((r & 1) ? bl : 0);
+            v[qa | o] = cfma(m3, a3, cfma(m2, a2, cfma(m1, a1, cmul(m0, a0))));
+            v[qb | o] = cfma(m3, b3, cfma(m2, b2, cfma(m1, b1, cmul(m0, b0))));
+        }
     }
 }
-// monomial ops with one of three row permutations: 0 = CX (MSB control): rows 2<->3; 1 = CX (LSB control): rows 1<->3;
-// 2 = SWAP: rows 1<->2.  out[r] = ph[r] * in[src[r]].
-template <int PH, int PL>
-__device__ __forceinline__ void r_perm2(double2 (&v)[8], const DevOp* op)
+// monomial ops with one of three row permutations: W = 0: CX (MSB control): rows 2<->3; 1: CX (LSB control): rows
+// 1<->3; 2: SWAP: rows 1<->2.  out[r] = ph[r] * in[src[r]].  With unit phases the op is a pure register renaming.
+template <int PH, int PL, int W>
+__device__ __forceinline__ void r_perm2w(double2 (&v)[E], const DevOp* op)
 {
-    const int which = op->aux & 3;
-    const bool unit = (op->aux >> 12) & 1;
     constexpr int bh = 1 << PH, bl = 1 << PL;
-    const double2 p0 = op_m(op)[0], p1 = op_m(op)[1], p2 = op_m(op)[2], p3 = op_m(op)[3];
+    constexpr int x = W == 0 ? bh : (W == 1 ? bl : bl), y = W == 0 ? (bh | bl) : (W == 1 ? (bh | bl) : bh);
 #pragma unroll
-    for (int q = 0; q < 8; q++)
+    for (int q = 0; q < E; q++)
         if (!(q & (bh | bl)))
         {
-            double2 a0 = v[q], a1 = v[q | bl], a2 = v[q | bh], a3 = v[q | bh | bl];
-            double2 t;
-            if (which == 0) { t = a2; a2 = a3; a3 = t; }
-            else if (which == 1) { t = a1; a1 = a3; a3 = t; }
-            else { t = a1; a1 = a2; a2 = t; }
-            if (!unit) { a0 = cmul(p0, a0); a1 = cmul(p1, a1); a2 = cmul(p2, a2); a3 = cmul(p3, a3); }
-            v[q] = a0; v[q | bl] = a1; v[q | bh] = a2; v[q | bh | bl] = a3;
+            const double2 t = v[q | x];
+            v[q | x] = v[q | y];
+            v[q | y] = t;
         }
+    if (!((op->aux >> 12) & 1))
+    {
+        const double2 p0 = op_m(op)[0], p1 = op_m(op)[1], p2 = op_m(op)[2], p3 = op_m(op)[3];
+#pragma unroll
+        for (int q = 0; q < E; q++)
+            if (!(q & (bh | bl)))
+            {
+                v[q] = cmul(p0, v[q]);
+                v[q | bl] = cmul(p1, v[q | bl]);
+                v[q | bh] = cmul(p2, v[q | bh]);
+                v[q | bh | bl] = cmul(p3, v[q | bh | bl]);
+            }
+    }
+}
+template <int PH, int PL>
+__device__ __forceinline__ void r_perm2(double2 (&v)[E], const DevOp* op)
+{
+    switch (op->aux & 3)
+    {
+    case 0: r_perm2w<PH, PL, 0>(v, op); break;
+    case 1: r_perm2w<PH, PL, 1>(v, op); break;
+    default: r_perm2w<PH, PL, 2>(v, op); break;
+    }
 }
 
-__device__ __forceinline__ void r_diag3(double2 (&v)[8], const DevOp* op)
+__device__ __forceinline__ void r_diagr(double2 (&v)[E], const DevOp* op)
 {
-    const int skip = op->aux & 255;
+    const int skip = op->aux & 0xffff;
 #pragma unroll
-    for (int c = 0; c < 8; c++)
+    for (int c = 0; c < E; c++)
         if (!((skip >> c) & 1)) v[c] = cmul(op_m(op)[c], v[c]);
 }
 
-#define DMB_DISPATCH1(FN, ...)                      \
-    switch (op->pos)                                \
-    {                                               \
-    case 0: FN<0>(__VA_ARGS__); break;              \
-    case 1: FN<1>(__VA_ARGS__); break;              \
-    default: FN<2>(__VA_ARGS__); break;             \
-    }
-#define DMB_DISPATCH2(FN, ...)                      \
-    switch (op->pos)                                \
-    {                                               \
-    case 0: FN<1, 0>(__VA_ARGS__); break;           \
-    case 1: FN<2, 0>(__VA_ARGS__); break;           \
-    default: FN<2, 1>(__VA_ARGS__); break;          \
-    }
+// MASK = the register-op codes compiled into this instantiation of the kernel (bit c <-> RegOpCode c).  ptxas keeps
+// the 16 resident elements in ONE register assignment across the dispatch only when few bodies meet there; with all
+// bodies in one kernel it copies all 64 registers before and after every op (measured: 135 moves per op).
+// vid = code * 8 + pos (DevOp::vid, set by the encoder): one jump table for op kind and register position.
+#define DMB_HAS(c) ((MASK >> (c)) & 1u)
+#define DMB_CASE1(c, FN, ...)                                                \
+    case (c) * 8 + 0: if (DMB_HAS(c)) FN<0>(__VA_ARGS__); break;             \
+    case (c) * 8 + 1: if (DMB_HAS(c)) FN<1>(__VA_ARGS__); break;             \
+    case (c) * 8 + 2: if (DMB_HAS(c)) FN<2>(__VA_ARGS__); break;             \
+    case (c) * 8 + 3: if (DMB_HAS(c)) FN<3>(__VA_ARGS__); break;
+#define DMB_CASE2(c, FN, ...)                                                \
+    case (c) * 8 + 0: if (DMB_HAS(c)) FN<1, 0>(__VA_ARGS__); break;          \
+    case (c) * 8 + 1: if (DMB_HAS(c)) FN<2, 0>(__VA_ARGS__); break;          \
+    case (c) * 8 + 2: if (DMB_HAS(c)) FN<2, 1>(__VA_ARGS__); break;          \
+    case (c) * 8 + 3: if (DMB_HAS(c)) FN<3, 0>(__VA_ARGS__); break;          \
+    case (c) * 8 + 4: if (DMB_HAS(c)) FN<3, 1>(__VA_ARGS__); break;          \
+    case (c) * 8 + 5: if (DMB_HAS(c)) FN<3, 2>(__VA_ARGS__); break;
 
-__device__ __forceinline__ void apply_reg_op(double2 (&v)[8], const DevOp* op)
+template <unsigned MASK>
+__device__ __forceinline__ void apply_reg_op(double2 (&v)[E], const DevOp* op, int vid)
 {
-    switch (op->code)
+    switch (vid)
     {
-    case RC_DIAG3: r_diag3(v, op); break;
-    case RC_DENSE2: DMB_DISPATCH2(r_dense2, v, op); break;
-    case RC_DIAG2: DMB_DISPATCH2(r_diag2, v, op); break;
-    case RC_PERM2: DMB_DISPATCH2(r_perm2, v, op); break;
-    case RC_DENSE1: DMB_DISPATCH1(r_dense1, v, op); break;
-    case RC_DIAG1: DMB_DISPATCH1(r_diag1, v, op); break;
-    case RC_MONO1: DMB_DISPATCH1(r_mono1, v, op); break;
-    case RC_SRN1: DMB_DISPATCH1(r_srn1, v); break;
+        DMB_CASE2(RC_DENSE2, r_dense2, v, op)
+        DMB_CASE2(RC_PERM2, r_perm2, v, op)
+        DMB_CASE1(RC_DENSE1, r_dense1, v, op)
+        DMB_CASE1(RC_DENSE1_RR, r_dense1_rr, v, op)
+        DMB_CASE1(RC_DENSE1_RI, r_dense1_ri, v, op)
+        DMB_CASE1(RC_MONO1, r_mono1, v, op)
+        DMB_CASE1(RC_SRN1, r_srn1, v)
+    case RC_DIAGR * 8: if (DMB_HAS(RC_DIAGR)) r_diagr(v, op); break;
     default: break;
     }
 }
@@ -209,6 +251,7 @@ __device__ __forceinline__ void apply_reg_op(double2 (&v)[8], const DevOp* op)
 // ------------------------------------------------------------------------------------------------
 // the sweep kernel.  Shared memory = [tile | ops | rounds | groups]
 // ------------------------------------------------------------------------------------------------
+template <unsigned MASK>
 __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_constant__ SweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -267,8 +310,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
         {
             const double2* src = gin + (base_in | g_in_lo);
 #pragma unroll
-            for (int it = 0; it < 16; it++)
-                if (it < n_it) cp_async16(&tile[(it << kThreadBits) | s_in], src + a.hin[it]);
+            for (int it = 0; it < kMaxIter; it++)
+                if (it < n_it) cp_async16(&tile[swz((unsigned)(it << kThreadBits)) ^ s_in], src + a.hin[it]);
         }
         cp_async_commit();
         cp_async_wait<0>();
@@ -292,18 +335,30 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                         const int n_iter = rd->n_iter;
                         const DevOp* ops = s_ops + rd->first;
                         const int n_ops = rd->count;
-                        unsigned roff[8];
-#pragma unroll
-                        for (int c = 0; c < 8; c++) roff[c] = rd->roff[c];
+                        // the 16 register offsets, packed two per word (kept in 8 registers: re-reading them from
+                        // shared memory at store time would serialise every STS behind an LDS)
+                        unsigned rw[E / 2];
+                        {
+                            const uint4 r0 = *reinterpret_cast<const uint4*>(rd->roff);
+                            const uint4 r1 = *(reinterpret_cast<const uint4*>(rd->roff) + 1);
+                            rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w;
+                            rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
+                        }
                         for (int it = 0; it < n_iter; it++)
                         {
                             const unsigned base = lbase ^ rd->iter_tab[it];
-                            double2 v[8];
+                            double2 v[E];
 #pragma unroll
-                            for (int c = 0; c < 8; c++) v[c] = tile[base ^ roff[c]];
-                            for (int o = 0; o < n_ops; o++) apply_reg_op(v, ops + o);
+                            for (int c = 0; c < E; c++) v[c] = tile[base ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)];
+                            int vid = n_ops > 0 ? ops[0].vid : 0;
+                            for (int o = 0; o < n_ops; o++)
+                            {
+                                const int next = o + 1 < n_ops ? ops[o + 1].vid : 0; // fetched while this op runs
+                                apply_reg_op<MASK>(v, ops + o, vid);
+                                vid = next;
+                            }
 #pragma unroll
-                            for (int c = 0; c < 8; c++) tile[base ^ roff[c]] = v[c];
+                            for (int c = 0; c < E; c++) tile[base ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)] = v[c];
                         }
                     }
                     __syncwarp();
@@ -317,7 +372,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
         {
             double2* dst = gout + (base_out | g_out_lo);
 #pragma unroll
-            for (int it = 0; it < 16; it++)
+            for (int it = 0; it < kMaxIter; it++)
                 if (it < n_it) st_stream(dst + a.hout[it], tile[s_out_lo ^ a.hs[it]]);
         }
         __syncthreads(); // every thread is done with the tile before the next load overwrites it
@@ -326,14 +381,54 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
 
 static int g_num_sms = 0;
 
+// instantiations, smallest first: a sweep runs on the first one that covers its op codes
+#define BIT(c) (1u << (c))
+constexpr unsigned kVariantMasks[] = {
+    0u,                                                                              // pure data movement (remap pack)
+    BIT(RC_DENSE2),                                                                  // random C2 blocks
+    BIT(RC_DIAGR) | BIT(RC_DENSE1_RR),                                               // QFT-like
+    BIT(RC_DENSE1_RR) | BIT(RC_PERM2),                                               // H / CX
+    BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_DENSE1_RI),         // dense 1- and 2-qubit blocks
+    BIT(RC_DIAGR) | BIT(RC_DENSE1_RR) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1),               // Clifford+T style
+    BIT(RC_DIAGR) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1), // no dense 4x4
+    BIT(RC_DIAGR) | BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) |
+        BIT(RC_SRN1),                                                                // everything
+};
+constexpr int kNumVariants = sizeof(kVariantMasks) / sizeof(kVariantMasks[0]);
+typedef void (*SweepFn)(const SweepArgs);
+template <int I>
+struct VariantTable
+{
+    static void fill(SweepFn* t)
+    {
+        t[I] = sweep_kernel<kVariantMasks[I]>;
+        VariantTable<I - 1>::fill(t);
+    }
+};
+template <>
+struct VariantTable<-1>
+{
+    static void fill(SweepFn*) {}
+};
+static SweepFn g_variants[kNumVariants];
+
+static int pick_variant(unsigned mask)
+{
+    for (int i = 0; i < kNumVariants; i++)
+        if (!(mask & ~kVariantMasks[i])) return i;
+    return kNumVariants - 1;
+}
+
 void sweep_setup()
 {
     if (g_num_sms) return;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    VariantTable<kNumVariants - 1>::fill(g_variants);
     const int max_smem = (16 << kMaxTileBits) + kMaxOpsPerSweep * (int)(sizeof(DevOp) + sizeof(DevRound) + sizeof(DevGroup));
-    cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    for (int i = 0; i < kNumVariants; i++)
+        cudaFuncSetAttribute(g_variants[i], cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
 }
 
 size_t sweep_smem_bytes(const SweepArgs& a)
@@ -346,13 +441,15 @@ int sweep_max_grid(const SweepArgs& a)
 {
     sweep_setup();
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel, kTileThreads, sweep_smem_bytes(a));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, g_variants[pick_variant(a.op_mask)], kTileThreads, sweep_smem_bytes(a));
     if (occ < 1) occ = 1;
     return g_num_sms * occ;
 }
 
 void launch_sweep(const SweepArgs& a, int grid, cudaStream_t s)
 {
-    sweep_kernel<<<grid, kTileThreads, sweep_smem_bytes(a), s>>>(a);
+    sweep_setup();
+    void* params[] = {const_cast<SweepArgs*>(&a)};
+    cudaLaunchKernel((const void*)g_variants[pick_variant(a.op_mask)], dim3(grid), dim3(kTileThreads), params, sweep_smem_bytes(a), s);
 }
 } // namespace dmb

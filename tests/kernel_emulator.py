@@ -11,12 +11,14 @@ from __future__ import annotations
 import numpy as np
 
 CLS_DENSE1, CLS_DIAG1, CLS_MONO1, CLS_SRN1, CLS_DENSE2, CLS_DIAG2, CLS_MONO2 = range(7)
-NT = 256
-TB = 8  # log2(NT)
+NT = 128
+TB = 7  # log2(NT)
+E = 16  # elements a lane keeps in registers per round (2^kRegBits)
+WB = 2  # log2(warps per CTA)
 
 
 def swz(e):
-    return e ^ ((e >> 3) & 7)
+    return e ^ ((e >> 3) & 7) ^ ((e >> 6) & 7) ^ ((e >> 9) & 7)
 
 
 def _dep(v, pos):
@@ -47,7 +49,7 @@ def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = No
     tiles = np.full((n_tiles, tile_elems), np.nan + 0j, dtype=np.complex128)
     for it in range(n_it):
         src = (base_in[:, None] | g_in_lo[None, act]) + int(dev["hin"][it])
-        tiles[:, (it << TB) | s_in[act]] = shard_in[src]
+        tiles[:, swz(it << TB) ^ s_in[act]] = shard_in[src]
     assert not np.isnan(tiles.real).any(), "load did not fill the tile"
 
     for grp in dev["groups"]:
@@ -66,8 +68,8 @@ def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = No
     return out
 
 
-RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE2, RC_DIAG2, RC_PERM2 = range(7)
-_POS2 = {0: (1, 0), 1: (2, 0), 2: (2, 1)}
+RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE2, RC_DIAG2, RC_PERM2, RC_DIAGR, RC_DENSE1_RR, RC_DENSE1_RI = range(10)
+_POS2 = {0: (1, 0), 1: (2, 0), 2: (2, 1), 3: (3, 0), 4: (3, 1), 5: (3, 2)}
 _PERMS = {0: [0, 1, 3, 2], 1: [0, 3, 2, 1], 2: [0, 2, 1, 3]}
 
 
@@ -78,14 +80,14 @@ def _round_items(rd, wpart):
 
 
 def _run_round(dev, rd, tiles, wpart):
-    """One register round of one warp: load 8 elements per work item, apply the round's ops, store back."""
+    """One register round of one warp: load 16 elements per work item, apply the round's ops, store back."""
     base = _round_items(rd, wpart)
     roff = [int(x) for x in rd["roff"]]
-    idx = [base ^ roff[c] for c in range(8)]
+    idx = [base ^ roff[c] for c in range(E)]
     v = [tiles[:, i].copy() for i in idx]  # v[c]: (n_tiles, n_items)
     for o in range(rd["first"], rd["first"] + rd["count"]):
         _apply_reg_op(dev["ops"][o], v)
-    for c in range(8):  # duplicates (tiny tiles) carry identical values
+    for c in range(E):  # duplicates (tiny tiles) carry identical values
         tiles[:, idx[c]] = v[c]
 
 
@@ -94,19 +96,26 @@ def _apply_reg_op(op, v):
     m = np.array(op["m"], dtype=np.float64)
     m = m[0::2] + 1j * m[1::2]
     skip, unit = (aux >> 8) & 15, (aux >> 12) & 1
-    if code == 7:  # RC_DIAG3
-        for c in range(8):
+    if code == RC_DIAGR:
+        for c in range(E):
             if not (aux >> c) & 1:
                 v[c] = m[c] * v[c]
         return
-    if code in (RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1):
+    if code in (RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE1_RR, RC_DENSE1_RI):
         b = 1 << pos
-        for q in range(8):
+        d = op["m"]
+        for q in range(E):
             if q & b:
                 continue
             a0, a1 = v[q].copy(), v[q | b].copy()
             if code == RC_DENSE1:
                 v[q], v[q | b] = m[0] * a0 + m[1] * a1, m[2] * a0 + m[3] * a1
+            elif code == RC_DENSE1_RR:  # pivoted in-place form {d0, d1, d2/d0, det/d0}
+                v[q] = d[0] * a0 + d[1] * a1
+                v[q | b] = d[2] * v[q] + d[3] * a1
+            elif code == RC_DENSE1_RI:
+                v[q] = d[0] * a0 + 1j * d[1] * a1
+                v[q | b] = 1j * d[2] * v[q] + d[3] * a1
             elif code == RC_DIAG1:
                 if not skip & 1:
                     v[q] = m[0] * a0
@@ -121,7 +130,7 @@ def _apply_reg_op(op, v):
         return
     ph_, pl_ = _POS2[pos]
     bh, bl = 1 << ph_, 1 << pl_
-    for q in range(8):
+    for q in range(E):
         if q & (bh | bl):
             continue
         ids = [q, q | bl, q | bh, q | bh | bl]
@@ -142,7 +151,7 @@ def _apply_reg_op(op, v):
 
 
 def check_group_partition(dev: dict):
-    """Every round's warps x lanes x iterations x 8 registers must cover the 2^k tile elements exactly once
+    """Every round's warps x lanes x iterations x 16 registers must cover the 2^k tile elements exactly once
     (for tiles with fewer than 2^kRegBits register bits, duplicates of the same element are allowed)."""
     k = dev["k"]
     for grp in dev["groups"]:
@@ -152,12 +161,12 @@ def check_group_partition(dev: dict):
             allidx = []
             for w in wt:
                 base = _round_items(rd, w)
-                for c in range(8):
+                for c in range(E):
                     allidx.append(base ^ int(rd["roff"][c]))
             allidx = np.concatenate(allidx)
             uniq = np.unique(allidx)
             assert len(uniq) == 1 << k, (k, grp, rd)
-            if k - (3 if grp["n_warps"] == 8 else 0) >= 3:
+            if k - (WB if grp["n_warps"] == (1 << WB) else 0) >= 4:
                 assert allidx.size == 1 << k
 
 
