@@ -51,6 +51,7 @@ static void init_options()
     if (const char* e = getenv("DMB_LOW_BITS")) g_opt.low_bits = atoi(e);
     if (const char* e = getenv("DMB_MIN_TILES_LOG2")) g_opt.min_tiles_log2 = atoi(e);
     if (const char* e = getenv("DMB_GRAPH")) g_use_graph = atoi(e);
+    if (const char* e = getenv("DMB_CPHASE")) g_opt.cphase = atoi(e) != 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -130,9 +131,13 @@ struct dmb_sim
     Plan plan;
     std::vector<int> plan_layout; // layout the plan was made for
     bool plan_conj = false, plan_nonherm = false;
-    DevOp* d_ops = nullptr;
+    unsigned char* d_ops = nullptr;   // op streams of all sweeps, back to back
     size_t d_ops_cap = 0;
-    std::vector<size_t> op_offset;    // per step: first DevOp
+    DevStar* d_stars = nullptr;
+    size_t d_stars_cap = 0;
+    std::vector<size_t> op_offset;    // per step: byte offset of its op stream
+    std::vector<size_t> star_offset;  // per step: first DevStar
+    std::vector<int> n_dev_stars;
     std::vector<size_t> round_offset, group_offset; // per step: first DevRound / DevGroup
     std::vector<int> n_dev_ops, n_dev_rounds, n_dev_groups;
     std::vector<unsigned> op_masks;   // per step: register-op codes present (kernel instantiation)
@@ -196,6 +201,7 @@ int dmb_set_option(const char* name, int64_t value)
     else if (!strcmp(name, "low_bits")) g_opt.low_bits = (int)value;
     else if (!strcmp(name, "min_tiles_log2")) g_opt.min_tiles_log2 = (int)value;
     else if (!strcmp(name, "graph")) g_use_graph = (int)value;
+    else if (!strcmp(name, "cphase")) g_opt.cphase = value != 0;
     else return fail(DMB_EINVAL, std::string("unknown option ") + name);
     return DMB_OK;
 }
@@ -251,6 +257,7 @@ int dmb_destroy(dmb_handle s)
     if (s->buf[0]) cudaFree(s->buf[0]);
     if (s->buf[1]) cudaFree(s->buf[1]);
     if (s->d_ops) cudaFree(s->d_ops);
+    if (s->d_stars) cudaFree(s->d_stars);
     if (s->d_rounds) cudaFree(s->d_rounds);
     if (s->d_groups) cudaFree(s->d_groups);
     if (s->d_scratch) cudaFree(s->d_scratch);
@@ -319,7 +326,8 @@ static int build_plan(dmb_sim* s)
     s->plan_nonherm = s->non_hermitian;
     drop_graph(s);
     // device op / group tables: one contiguous upload each (the reference does 3 CUDA calls per gate per GPU, :112-163)
-    std::vector<DevOp> host_ops;
+    std::vector<unsigned char> host_ops;
+    std::vector<DevStar> host_stars;
     std::vector<DevRound> host_rounds;
     std::vector<DevGroup> host_groups;
     const size_t nsteps = s->plan.steps.size();
@@ -330,19 +338,31 @@ static int build_plan(dmb_sim* s)
     s->n_dev_rounds.assign(nsteps, 0);
     s->n_dev_groups.assign(nsteps, 0);
     s->op_masks.assign(nsteps, 0u);
+    s->star_offset.assign(nsteps, 0);
+    s->n_dev_stars.assign(nsteps, 0);
     EncodedSweep enc;
     for (size_t i = 0; i < nsteps; i++)
     {
         s->op_offset[i] = host_ops.size();
         s->round_offset[i] = host_rounds.size();
         s->group_offset[i] = host_groups.size();
+        s->star_offset[i] = host_stars.size();
         if (s->plan.steps[i].kind != 0) continue;
-        encode_sweep(s->plan.steps[i].sweep, enc);
-        s->n_dev_ops[i] = (int)enc.ops.size();
+        try
+        {
+            encode_sweep(s->plan.steps[i].sweep, enc);
+        }
+        catch (const std::exception& e)
+        {
+            return fail(DMB_ESTATE, e.what());
+        }
+        s->n_dev_ops[i] = (int)enc.stream.size(); // bytes
+        s->n_dev_stars[i] = (int)enc.stars.size();
+        s->op_masks[i] = enc.op_mask;
+        host_stars.insert(host_stars.end(), enc.stars.begin(), enc.stars.end());
         s->n_dev_rounds[i] = (int)enc.rounds.size();
         s->n_dev_groups[i] = (int)enc.groups.size();
-        for (const DevOp& d : enc.ops) s->op_masks[i] |= 1u << d.code;
-        host_ops.insert(host_ops.end(), enc.ops.begin(), enc.ops.end());
+        host_ops.insert(host_ops.end(), enc.stream.begin(), enc.stream.end());
         host_rounds.insert(host_rounds.end(), enc.rounds.begin(), enc.rounds.end());
         host_groups.insert(host_groups.end(), enc.groups.begin(), enc.groups.end());
     }
@@ -352,8 +372,16 @@ static int build_plan(dmb_sim* s)
         if (s->d_ops) cudaFree(s->d_ops);
         s->d_ops = nullptr;
         s->d_ops_cap = 0;
-        CU(cudaMalloc(&s->d_ops, host_ops.size() * sizeof(DevOp)));
+        CU(cudaMalloc(&s->d_ops, host_ops.size()));
         s->d_ops_cap = host_ops.size();
+    }
+    if (host_stars.size() > s->d_stars_cap)
+    {
+        if (s->d_stars) cudaFree(s->d_stars);
+        s->d_stars = nullptr;
+        s->d_stars_cap = 0;
+        CU(cudaMalloc(&s->d_stars, host_stars.size() * sizeof(DevStar)));
+        s->d_stars_cap = host_stars.size();
     }
     if (host_rounds.size() > s->d_rounds_cap)
     {
@@ -371,10 +399,14 @@ static int build_plan(dmb_sim* s)
         CU(cudaMalloc(&s->d_groups, host_groups.size() * sizeof(DevGroup)));
         s->d_groups_cap = host_groups.size();
     }
-    s->h2d_bytes = host_ops.size() * sizeof(DevOp) + host_rounds.size() * sizeof(DevRound) + host_groups.size() * sizeof(DevGroup);
+    s->h2d_bytes = host_ops.size() + host_stars.size() * sizeof(DevStar) + host_rounds.size() * sizeof(DevRound) +
+                   host_groups.size() * sizeof(DevGroup);
     if (!host_ops.empty())
     {
-        CU(cudaMemcpyAsync(s->d_ops, host_ops.data(), host_ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->d_ops, host_ops.data(), host_ops.size(), cudaMemcpyHostToDevice, s->stream));
+        if (!host_stars.empty())
+            CU(cudaMemcpyAsync(s->d_stars, host_stars.data(), host_stars.size() * sizeof(DevStar), cudaMemcpyHostToDevice,
+                               s->stream));
         CU(cudaMemcpyAsync(s->d_rounds, host_rounds.data(), host_rounds.size() * sizeof(DevRound), cudaMemcpyHostToDevice,
                            s->stream));
         CU(cudaMemcpyAsync(s->d_groups, host_groups.data(), host_groups.size() * sizeof(DevGroup), cudaMemcpyHostToDevice,
@@ -418,7 +450,10 @@ static void fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, do
     a.ops = s->d_ops + s->op_offset[step];
     a.rounds = s->d_rounds + s->round_offset[step];
     a.groups = s->d_groups + s->group_offset[step];
-    a.n_ops = s->n_dev_ops[step];
+    a.ops_bytes = s->n_dev_ops[step];
+    a.stars = s->d_stars + s->star_offset[step];
+    a.n_stars = s->n_dev_stars[step];
+    a.rank_bits = (unsigned long long)s->rank << s->M;
     a.n_rounds = s->n_dev_rounds[step];
     a.n_groups = s->n_dev_groups[step];
     a.op_mask = s->op_masks[step];

@@ -39,16 +39,60 @@ enum RegOpCode : int32_t
                    // aux bits 0..15 (entries equal to 1)
     RC_DENSE1_RR = 8, // 2x2 with four REAL entries [[d0,d1],[d2,d3]] (H, RY, ...), |d0| not small, in the pivoted in-place
                       // form m[0..3] = {d0, d1, d2/d0, det/d0}: half the FP64 work of RC_DENSE1 and no register copies
-    RC_DENSE1_RI = 9  // [[d0, i d1], [i d2, d3]] with real d (RX, W, ...), same form with det = d0 d3 + d1 d2
+    RC_DENSE1_RI = 9, // [[d0, i d1], [i d2, d3]] with real d (RX, W, ...), same form with det = d0 d3 + d1 d2
+    RC_STAR = 10      // controlled-phase star: for every register bit p in aux bits 0..3, the elements with that bit set
+                      // are multiplied by  L_p[lane] * WO_p[warp, iteration]  (DevStar slot star[p]): the product of the
+                      // phases of all controlled-phase ops between register bit p and the partner bits that are set in
+                      // this lane's / warp's / tile's index
 };
 
-// One op of a round (272 bytes), applied to the lane's 2^kRegBits resident elements.
+// One (star op, register bit) pair.  l[] and w[] are host-computed partial products over the partner bits that are
+// lane bits resp. iteration / warp bits of the round; the partners outside the tile (any physical bit, rank bits
+// included) are multiplied in once per tile by the kernel's prologue (WO = w * prod phi[j] over set bits).
+constexpr int kMaxStarOut = 28;
+struct alignas(16) DevStar
+{
+    double w[16];  // 8 complex: index = (warp << iteration bits) | iteration
+    double l[64];  // 32 complex: index = lane
+    int32_t n_out;
+    int32_t pad[3];
+    int32_t bit[kMaxStarOut];    // physical bit of the full index (>= M: rank bits)
+    double phi[2 * kMaxStarOut]; // (re, im)
+};
+static_assert(sizeof(DevStar) == 1216, "DevStar layout");
+constexpr int kMaxStarsPerSweep = 160; // 128 bytes of shared memory each
+
+// Device op stream: 16-byte header + payload (the used part of DevOp::m), 16-byte granularity; a zero header ends it.
+struct alignas(16) DevOpHdr
+{
+    int32_t vid;    // code * 8 + pos
+    int32_t aux;
+    int32_t size16; // header + payload in 16-byte units
+    int32_t star[1]; // RC_STAR: star[0] = first DevStar slot of this op (one per set aux bit, ascending)
+};
+inline int dev_op_payload_bytes(int code)
+{
+    switch (code)
+    {
+    case RC_DENSE1: return 64;
+    case RC_MONO1: return 32;
+    case RC_DENSE2: return 256;
+    case RC_PERM2: return 64;
+    case RC_DIAGR: return 256;
+    case RC_DENSE1_RR: return 32;
+    case RC_DENSE1_RI: return 32;
+    default: return 0;
+    }
+}
+
+// One op of a round, applied to the lane's 2^kRegBits resident elements (host-side description; the device reads the
+// compact stream of DevOpHdr + payload built from it).
 struct alignas(16) DevOp
 {
     int32_t code; // RegOpCode
     int32_t aux;
     int32_t pos;  // 1-bit ops: register bit 0..3; 2-bit ops: (msb, lsb) = (1,0) (2,0) (2,1) (3,0) (3,1) (3,2) -> 0..5
-    int32_t vid;  // code * 8 + pos: the kernel's jump-table index
+    int32_t vid;  // code * 8 + pos: the kernel's jump-table index; RC_STAR: first DevStar slot (host side)
     double m[32]; // up to 16 complex entries (re, im)
 };
 static_assert(sizeof(DevOp) == 272, "DevOp layout");
@@ -58,7 +102,7 @@ static_assert(sizeof(DevOp) == 272, "DevOp layout");
 // ONE shared-memory round trip for `count` ops.
 struct alignas(16) DevRound
 {
-    int32_t first, count;
+    int32_t first, count; // first: offset of the round's first op in the op stream, in 16-byte units
     int32_t n_iter;   // iterations per lane
     int32_t n_active; // active lanes (32 unless the sub-tile has fewer work items)
     uint16_t lane_tab[32];
@@ -84,10 +128,12 @@ struct SweepArgs
 {
     const void* in;   // double2*
     void* out;        // double2*
-    const DevOp* ops; // device copies
+    const void* ops;  // device copies: op stream (DevOpHdr + payload ...)
     const DevRound* rounds;
     const DevGroup* groups;
-    int n_ops, n_rounds, n_groups;
+    const DevStar* stars;
+    int ops_bytes, n_rounds, n_groups, n_stars;
+    unsigned long long rank_bits; // rank << M: the index bits above the shard
     unsigned op_mask;           // bit c set <=> some op of the sweep has RegOpCode c (selects the kernel instantiation)
     int k;                      // tile bits
     int n_comp;                 // M - k

@@ -141,12 +141,15 @@ namespace
 struct RoundPlan
 {
     std::vector<int> ops;   // indices into sw.ops, execution order
-    unsigned touched = 0;   // tile bits its ops act on
+    unsigned touched = 0;   // tile bits its ops need in registers
 };
+
+inline bool is_cp(const TileOp& t) { return t.cls == CLS_CPHASE; }
 
 // Splits the sweep's op list into register rounds.  Like the tile scheduler one level up: pick <= R register bits by
 // gain (how much of the remaining list becomes executable: per-bit program order, diagonal ops hop over skipped
-// diagonal ops), run everything that fits, repeat.  Sweeps containing SRN (a full barrier) keep strict list order.
+// diagonal ops), run everything that fits, repeat.  A controlled phase (CLS_CPHASE) runs as soon as ONE of its bits is
+// a register bit.  Sweeps containing SRN (a full barrier) keep strict list order.
 std::vector<RoundPlan> plan_rounds(const Sweep& sw, int R)
 {
     const int n = (int)sw.ops.size();
@@ -156,15 +159,16 @@ std::vector<RoundPlan> plan_rounds(const Sweep& sw, int R)
     {
         const TileOp& t = sw.ops[i];
         if (t.cls == CLS_SRN1) has_srn = true;
+        else if (is_cp(t)) diag[i] = 1;
         else
         {
             const int c = classify(t.nb, t.m, nullptr);
             diag[i] = (c == CLS_DIAG1 || c == CLS_DIAG2);
         }
     }
-    auto bits_of = [&](int i) {
+    auto bits_of = [&](int i) { // the op's bits INSIDE the tile
         unsigned m = 1u << sw.ops[i].j0;
-        if (sw.ops[i].nb == 2) m |= 1u << sw.ops[i].j1;
+        if (sw.ops[i].nb == 2 && sw.ops[i].j1 >= 0) m |= 1u << sw.ops[i].j1;
         return m;
     };
     std::vector<RoundPlan> rounds;
@@ -191,10 +195,11 @@ std::vector<RoundPlan> plan_rounds(const Sweep& sw, int R)
         {
             if (done[i]) continue;
             const unsigned m = bits_of(i);
-            const bool ok = (m & ~rb) == 0 && !(m & hard) && (diag[i] || !(m & soft));
+            const bool fits = is_cp(sw.ops[i]) ? (m & rb) != 0 : (m & ~rb) == 0;
+            const bool ok = fits && !(m & hard) && (diag[i] || !(m & soft));
             if (ok)
             {
-                score += sw.ops[i].weight > 0 ? 1 : 1;
+                score += 1;
                 if (picked) picked->push_back(i);
             }
             else if (diag[i]) soft |= m;
@@ -212,13 +217,22 @@ std::vector<RoundPlan> plan_rounds(const Sweep& sw, int R)
             const int room = R - __builtin_popcount(rb);
             std::vector<unsigned> cands;
             int looked = 0;
+            auto add_cand = [&](unsigned miss) {
+                if (!miss || __builtin_popcount(miss) > room) return;
+                if (std::find(cands.begin(), cands.end(), miss) == cands.end()) cands.push_back(miss);
+            };
             for (int i = first; i < n && looked < 96; i++)
             {
                 if (done[i]) continue;
                 looked++;
-                const unsigned miss = bits_of(i) & ~rb;
-                if (!miss || __builtin_popcount(miss) > room) continue;
-                if (std::find(cands.begin(), cands.end(), miss) == cands.end()) cands.push_back(miss);
+                const unsigned m = bits_of(i);
+                if (is_cp(sw.ops[i]))
+                {
+                    if (m & rb) continue;
+                    for (int p = 0; p < 16; p++)
+                        if ((m >> p) & 1u) add_cand(1u << p);
+                }
+                else add_cand(m & ~rb);
             }
             int best_gain = 0, best = -1;
             double best_rate = 0;
@@ -240,20 +254,47 @@ std::vector<RoundPlan> plan_rounds(const Sweep& sw, int R)
         for (int i : rp.ops)
         {
             done[i] = 1;
-            rp.touched |= bits_of(i);
+            rp.touched |= is_cp(sw.ops[i]) ? (bits_of(i) & rb) : bits_of(i);
             left--;
         }
+        if (rp.ops.empty()) break; // cannot happen: the first pending op always fits a fresh round
         rounds.push_back(rp);
     }
     return rounds;
 }
+
+// a run of consecutive diagonal-type ops of a round (they all commute): one 16-entry diagonal over the register bits
+// plus, per register bit, the controlled phases whose other bit is NOT a register bit of this round
+struct StarPartner
+{
+    bool tile;  // partner is a tile-local bit (lane / iteration / warp bit), else a physical bit outside the tile
+    int bit;
+    cplx phi;
+};
+struct DiagRun
+{
+    bool have_diag = false;
+    cplx e[kRegElems];
+    std::vector<StarPartner> star[kRegBits];
+    bool any_star = false;
+    void reset()
+    {
+        have_diag = false;
+        any_star = false;
+        for (auto& v : star) v.clear();
+        for (auto& x : e) x = cplx(1.0, 0.0);
+    }
+};
 } // namespace
 
 void encode_sweep(const Sweep& sw, EncodedSweep& out)
 {
     out.ops.clear();
+    out.stream.clear();
     out.rounds.clear();
     out.groups.clear();
+    out.stars.clear();
+    out.op_mask = 0;
     const int k = sw.k;
     const int nwb = k >= kWarpBits + kRegBits ? kWarpBits : 0;
     const int R = std::min(kRegBits, k - nwb);
@@ -299,7 +340,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
 
             DevRound rd;
             memset(&rd, 0, sizeof(rd));
-            rd.first = (int32_t)out.ops.size();
+            rd.first = (int32_t)out.ops.size(); // op INDEX for now; rewritten to the stream offset below
             const int rd_first = rd.first;
             for (int c = 0; c < kRegElems; c++) rd.roff[c] = (uint16_t)swz_host(deposit((unsigned)c & ((1u << R) - 1u), rb));
             std::vector<int> freep;
@@ -330,17 +371,111 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                 rd.iter_tab[it] = (uint16_t)swz_host(deposit((unsigned)it & ((unsigned)rd.n_iter - 1u), iterp));
             out.rounds.push_back(rd);
 
+            auto reg_pos = [&](int j) { // position of tile bit j among the round's register bits, -1 if none
+                const auto it = std::find(rb.begin(), rb.end(), j);
+                return it == rb.end() ? -1 : (int)(it - rb.begin());
+            };
+            DiagRun run;
+            run.reset();
+            auto flush_run = [&]() {
+                if (run.have_diag)
+                {
+                    DevOp nd;
+                    memset(&nd, 0, sizeof(nd));
+                    nd.code = RC_DIAGR;
+                    int skip = 0;
+                    for (int c = 0; c < kRegElems; c++)
+                    {
+                        cplx v = run.e[c];
+                        // entries within 1e-15 of 1 (e.g. u1(a)*u1(-a) inside a fused controlled phase) are exactly 1
+                        if (std::abs(v.real() - 1.0) < 1e-15 && std::abs(v.imag()) < 1e-15) v = cplx(1.0, 0.0);
+                        put(nd, c, v);
+                        if (v == cplx(1.0, 0.0)) skip |= 1 << c;
+                    }
+                    nd.aux = skip;
+                    if (skip != (1 << kRegElems) - 1) out.ops.push_back(nd);
+                }
+                if (run.any_star)
+                {
+                    DevOp sd;
+                    memset(&sd, 0, sizeof(sd));
+                    sd.code = RC_STAR;
+                    sd.vid = (int32_t)out.stars.size(); // first slot (host-side meaning of vid for RC_STAR)
+                    const int nib = (int)iterp.size();
+                    for (int p = 0; p < kRegBits; p++)
+                    {
+                        if (run.star[p].empty()) continue;
+                        sd.aux |= 1 << p;
+                        DevStar st;
+                        memset(&st, 0, sizeof(st));
+                        for (int iw = 0; iw < 8; iw++)
+                        {
+                            const unsigned itv = (unsigned)iw & ((1u << nib) - 1u), wv = (unsigned)iw >> nib;
+                            const unsigned idx = deposit(itv, iterp) | deposit(wv, wpos);
+                            cplx acc(1.0, 0.0);
+                            for (const StarPartner& sp : run.star[p])
+                                if (sp.tile && ((idx >> sp.bit) & 1u)) acc *= sp.phi;
+                            st.w[2 * iw] = acc.real();
+                            st.w[2 * iw + 1] = acc.imag();
+                        }
+                        for (int l = 0; l < 32; l++)
+                        {
+                            const unsigned idx = deposit((unsigned)l & ((1u << nl) - 1u), lanep);
+                            cplx acc(1.0, 0.0);
+                            for (const StarPartner& sp : run.star[p])
+                                if (sp.tile && ((idx >> sp.bit) & 1u)) acc *= sp.phi;
+                            st.l[2 * l] = acc.real();
+                            st.l[2 * l + 1] = acc.imag();
+                        }
+                        for (const StarPartner& sp : run.star[p])
+                            if (!sp.tile)
+                            {
+                                if (st.n_out >= kMaxStarOut) throw std::logic_error("too many outside partners in a star");
+                                st.bit[st.n_out] = sp.bit;
+                                st.phi[2 * st.n_out] = sp.phi.real();
+                                st.phi[2 * st.n_out + 1] = sp.phi.imag();
+                                st.n_out++;
+                            }
+                        out.stars.push_back(st);
+                    }
+                    out.ops.push_back(sd);
+                }
+                run.reset();
+            };
+
             for (int o : rp.ops)
             {
                 const TileOp& t = sw.ops[o];
-                const int p0 = (int)(std::find(rb.begin(), rb.end(), t.j0) - rb.begin());
-                const int p1 = t.nb == 2 ? (int)(std::find(rb.begin(), rb.end(), t.j1) - rb.begin()) : 0;
+                if (is_cp(t))
+                {
+                    const cplx phi = t.m[15];
+                    const int p0 = reg_pos(t.j0), p1 = t.j1 >= 0 ? reg_pos(t.j1) : -1;
+                    if (p0 >= 0 && p1 >= 0)
+                    {
+                        for (int c = 0; c < kRegElems; c++)
+                            if (((c >> p0) & 1) && ((c >> p1) & 1)) run.e[c] *= phi;
+                        run.have_diag = true;
+                    }
+                    else if (p0 >= 0 || p1 >= 0)
+                    {
+                        StarPartner sp;
+                        sp.phi = phi;
+                        if (p0 >= 0) { sp.tile = t.j1 >= 0; sp.bit = t.j1 >= 0 ? t.j1 : t.p1; }
+                        else { sp.tile = true; sp.bit = t.j0; }
+                        run.star[p0 >= 0 ? p0 : p1].push_back(sp);
+                        run.any_star = true;
+                    }
+                    else
+                        throw std::logic_error("controlled phase without a register bit in its round");
+                    continue;
+                }
+                const int p0 = reg_pos(t.j0);
+                const int p1 = t.nb == 2 ? reg_pos(t.j1) : 0;
                 DevOp d = make_reg_op(t, p0, p1);
                 if (d.code == RC_DIAG1 || d.code == RC_DIAG2)
                 {
-                    // every diagonal op becomes a 16-entry diagonal over the round's register bits, and consecutive
-                    // ones are multiplied together on the host: one device op, no position dispatch
-                    cplx e[kRegElems];
+                    // every diagonal op becomes a 16-entry diagonal over the round's register bits, and the ones of
+                    // a run are multiplied together on the host: one device op, no position dispatch
                     for (int c = 0; c < kRegElems; c++)
                     {
                         int idx;
@@ -350,40 +485,45 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                             static const int hi[6] = {1, 2, 2, 3, 3, 3}, lo[6] = {0, 0, 1, 0, 1, 2};
                             idx = 2 * ((c >> hi[d.pos]) & 1) + ((c >> lo[d.pos]) & 1);
                         }
-                        e[c] = cplx(d.m[2 * idx], d.m[2 * idx + 1]);
+                        run.e[c] *= cplx(d.m[2 * idx], d.m[2 * idx + 1]);
                     }
-                    const bool merge = (int)out.ops.size() > rd_first && out.ops.back().code == RC_DIAGR;
-                    DevOp nd;
-                    if (merge) nd = out.ops.back();
-                    else
-                    {
-                        memset(&nd, 0, sizeof(nd));
-                        nd.code = RC_DIAGR;
-                        for (int c = 0; c < kRegElems; c++) put(nd, c, cplx(1.0, 0.0));
-                    }
-                    int skip = 0;
-                    for (int c = 0; c < kRegElems; c++)
-                    {
-                        cplx v = cplx(nd.m[2 * c], nd.m[2 * c + 1]) * e[c];
-                        // entries within 1e-15 of 1 (e.g. u1(a)*u1(-a) inside a fused controlled phase) are exactly 1
-                        if (std::abs(v.real() - 1.0) < 1e-15 && std::abs(v.imag()) < 1e-15) v = cplx(1.0, 0.0);
-                        put(nd, c, v);
-                        if (v == cplx(1.0, 0.0)) skip |= 1 << c;
-                    }
-                    nd.aux = skip;
-                    if (merge) out.ops.back() = nd;
-                    else out.ops.push_back(nd);
+                    run.have_diag = true;
                     continue;
                 }
+                flush_run();
                 out.ops.push_back(d);
             }
+            flush_run();
             out.rounds.back().count = (int32_t)out.ops.size() - rd_first;
-            for (size_t o = (size_t)rd_first; o < out.ops.size(); o++) out.ops[o].vid = out.ops[o].code * 8 + out.ops[o].pos;
         }
         g.count = (int32_t)out.rounds.size() - g.first;
         out.groups.push_back(g);
         first = end;
     }
+    if ((int)out.stars.size() > kMaxStarsPerSweep) throw std::logic_error("too many controlled-phase stars in one sweep");
+
+    // ---- the device op stream: 16-byte header + the used part of the payload per op, a zero header at the end ----
+    std::vector<int> offset16(out.ops.size() + 1, 0);
+    for (size_t i = 0; i < out.ops.size(); i++)
+    {
+        DevOp& d = out.ops[i];
+        const int star0 = d.code == RC_STAR ? d.vid : 0;
+        DevOpHdr h;
+        h.vid = d.code * 8 + (d.code == RC_STAR || d.code == RC_DIAGR ? 0 : d.pos);
+        h.aux = d.aux;
+        const int payload = dev_op_payload_bytes(d.code);
+        h.size16 = 1 + payload / 16;
+        h.star[0] = star0;
+        offset16[i] = (int)(out.stream.size() / 16);
+        const unsigned char* hb = reinterpret_cast<const unsigned char*>(&h);
+        out.stream.insert(out.stream.end(), hb, hb + sizeof(h));
+        const unsigned char* pb = reinterpret_cast<const unsigned char*>(d.m);
+        out.stream.insert(out.stream.end(), pb, pb + payload);
+        out.op_mask |= 1u << d.code;
+    }
+    offset16[out.ops.size()] = (int)(out.stream.size() / 16);
+    out.stream.insert(out.stream.end(), 16, (unsigned char)0);
+    for (DevRound& rd : out.rounds) rd.first = offset16[rd.first];
 }
 
 void fill_sweep_tables(const Sweep& sw, int M, SweepArgs& a)
@@ -466,15 +606,36 @@ std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a)
     }
     o << "],\"ops\":[";
     char buf[40];
+    auto dbl = [&](const double* v, int n) {
+        for (int j = 0; j < n; j++)
+        {
+            snprintf(buf, sizeof(buf), "%.17g", v[j]);
+            o << (j ? "," : "") << buf;
+        }
+    };
+    int off16 = 0;
     for (size_t i = 0; i < e.ops.size(); i++)
     {
         const DevOp& d = e.ops[i];
-        o << (i ? "," : "") << "{\"code\":" << d.code << ",\"aux\":" << d.aux << ",\"pos\":" << d.pos << ",\"m\":[";
-        for (int j = 0; j < 32; j++)
-        {
-            snprintf(buf, sizeof(buf), "%.17g", d.m[j]);
-            o << (j ? "," : "") << buf;
-        }
+        // "off": where the op sits in the device stream (DevRound::first refers to it); RC_STAR: "star" = first slot
+        o << (i ? "," : "") << "{\"code\":" << d.code << ",\"aux\":" << d.aux << ",\"pos\":" << d.pos << ",\"off\":" << off16
+          << ",\"star\":" << (d.code == RC_STAR ? d.vid : -1) << ",\"m\":[";
+        dbl(d.m, 32);
+        o << "]}";
+        off16 += 1 + dev_op_payload_bytes(d.code) / 16;
+    }
+    o << "],\"stars\":[";
+    for (size_t i = 0; i < e.stars.size(); i++)
+    {
+        const DevStar& st = e.stars[i];
+        o << (i ? "," : "") << "{\"w\":[";
+        dbl(st.w, 16);
+        o << "],\"l\":[";
+        dbl(st.l, 64);
+        o << "],\"bit\":[";
+        for (int j = 0; j < st.n_out; j++) o << (j ? "," : "") << st.bit[j];
+        o << "],\"phi\":[";
+        dbl(st.phi, 2 * st.n_out);
         o << "]}";
     }
     o << "]}";

@@ -10,9 +10,12 @@ namespace dmb
 {
 struct EncodedSweep
 {
-    std::vector<DevOp> ops;
-    std::vector<DevRound> rounds;
+    std::vector<DevOp> ops;             // host-side description (JSON / tests); vid of RC_STAR = first star slot
+    std::vector<unsigned char> stream;  // what the device reads: DevOpHdr + payload per op, zero header at the end
+    std::vector<DevRound> rounds;       // first = offset into `stream` in 16-byte units
     std::vector<DevGroup> groups;
+    std::vector<DevStar> stars;
+    unsigned op_mask = 0;               // register-op codes present
 };
 void encode_sweep(const Sweep& sw, EncodedSweep& out);
 // fills k, n_comp, n_tiles and every address table of `a` (pointers / counts are the caller's job)

@@ -309,18 +309,53 @@ void swap_roles(const cplx* m, cplx* o)
 bool is_identity2(const cplx* u) { return u[0] == cplx(1) && u[3] == cplx(1) && u[1] == cplx(0) && u[2] == cplx(0); }
 } // namespace
 
-void fuse_blocks(int n, const std::vector<Block>& prims, std::vector<Block>& blocks)
+void fuse_blocks(int n, const std::vector<Block>& prims, std::vector<Block>& blocks, bool split_cphase)
 {
     struct Pend { bool have = false; cplx u[4]; int weight = 0; };
     std::vector<Pend> pend(n);
     std::vector<int> open(n, -1);       // index into work[] of the open 2-qubit block on this qubit
     std::vector<Block> work;
 
+    bool any_srn = false;
+    for (const Block& p : prims) any_srn |= p.srn;
     auto close_block = [&](int idx) {
         if (idx < 0) return;
-        blocks.push_back(work[idx]);
-        open[work[idx].q[0]] = -1;
-        open[work[idx].q[1]] = -1;
+        Block b = work[idx];
+        open[b.q[0]] = -1;
+        open[b.q[1]] = -1;
+        // A diagonal block diag(d0, d1, d2, d3) = d0 * diag_q0(1, d2/d0) * diag_q1(1, d1/d0) * CP(d0 d3 / (d1 d2)): emit
+        // the pure controlled phase (the schedulers only need ONE of its bits in a tile, CLS_CPHASE) and leave the
+        // 1-qubit phases pending on their qubits -- they commute with it and merge into whatever follows there.
+        if (split_cphase && !any_srn && classify(2, b.m, nullptr) == CLS_DIAG2)
+        {
+            const cplx d0 = b.m[0], d1 = b.m[5], d2 = b.m[10], d3 = b.m[15];
+            const double tiny = 1e-8;
+            if (std::abs(d0) > tiny && std::abs(d1) > tiny && std::abs(d2) > tiny)
+            {
+                const cplx u0[4] = {d0, 0, 0, d2}, u1[4] = {1, 0, 0, d1 / d0}; // d0 rides on q0's factor
+                const cplx phi = d0 * d3 / (d1 * d2);
+                for (auto& e : b.m) e = 0;
+                b.m[0] = b.m[5] = b.m[10] = 1;
+                b.m[15] = phi;
+                const bool trivial = std::abs(phi.real() - 1.0) < 1e-15 && std::abs(phi.imag()) < 1e-15;
+                if (!trivial) blocks.push_back(b);
+                const cplx* us[2] = {u0, u1};
+                for (int side = 0; side < 2; side++)
+                {
+                    const int q = b.q[side];
+                    if (is_identity2(us[side])) continue;
+                    if (pend[q].have) mat2_mul(us[side], pend[q].u, pend[q].u);
+                    else
+                    {
+                        pend[q].have = true;
+                        memcpy(pend[q].u, us[side], sizeof(cplx) * 4);
+                        pend[q].weight = 0;
+                    }
+                }
+                return;
+            }
+        }
+        blocks.push_back(b);
     };
     auto flush_pending = [&](int q) {
         if (!pend[q].have) return;
@@ -412,10 +447,8 @@ void fuse_blocks(int n, const std::vector<Block>& prims, std::vector<Block>& blo
         open[a] = open[b_] = (int)work.size() - 1;
     }
     for (int q = 0; q < n; q++)
-    {
-        if (open[q] >= 0) close_block(open[q]);
-        flush_pending(q);
-    }
+        if (open[q] >= 0) close_block(open[q]); // may leave 1-qubit phases pending on either qubit
+    for (int q = 0; q < n; q++) flush_pending(q);
 }
 
 int classify(int nb, const cplx* m, int* src_out)
@@ -465,6 +498,7 @@ struct FlatOp
     int weight;
     int side; // 0 = L (row bits), 1 = R (column bits)
     bool diag = false; // diagonal matrix: commutes with every other diagonal op
+    bool cp = false;   // diag(1, 1, 1, phi): needs only ONE of its bits inside the tile (see CLS_CPHASE)
     bool done = false;
 };
 
@@ -493,7 +527,7 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
     std::vector<Block> prims, blocks;
     expand_gates(n, gates, n_gates, mats, n_mats, prims);
     plan.n_primitives = prims.size();
-    fuse_blocks(n, prims, blocks);
+    fuse_blocks(n, prims, blocks, opt.cphase);
     plan.n_blocks = blocks.size();
 
     // mirror: L part on bit q, R part (conjugated) on bit q+n.  SRN is real-linear and self-conjugate.
@@ -519,6 +553,16 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
             {
                 const int cls = classify(b.nq, f.m, nullptr);
                 f.diag = !plan.has_srn && (cls == CLS_DIAG1 || cls == CLS_DIAG2);
+                if (f.diag && cls == CLS_DIAG2 && opt.cphase)
+                {
+                    // entries within 1e-15 of 1 (u1(a) u1(-a) inside a fused controlled phase) are exactly 1
+                    auto is_one = [](cplx v) { return std::abs(v.real() - 1.0) < 1e-15 && std::abs(v.imag()) < 1e-15; };
+                    if (is_one(f.m[0]) && is_one(f.m[5]) && is_one(f.m[10]))
+                    {
+                        f.cp = true;
+                        f.m[0] = f.m[5] = f.m[10] = cplx(1.0, 0.0);
+                    }
+                }
             }
             ops.push_back(f);
         }
@@ -543,34 +587,55 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
 
     auto build_candidate = [&](int strategy) {
         Candidate c;
-        std::vector<char> in_tile(N, 0), blocked(N, 0);
+        std::vector<char> in_tile(N, 0), blocked(N, 0), is_rank(N, 0);
         for (int l = 0; l < N; l++)
         {
-            if (phys[l] >= M) blocked[l] = 2; // rank bits: not addressable inside a shard
+            if (phys[l] >= M) is_rank[l] = 1; // rank bits: not addressable inside a shard
             if (phys[l] < lowb) { in_tile[l] = 1; c.tile_logical.push_back(l); }
         }
         int tile_cnt = (int)c.tile_logical.size();
+        long picked_cost = 0;
+        int picked_cp = 0;
         int n_free_bits = 0;
-        for (int l = 0; l < N; l++) n_free_bits += blocked[l] != 2;
+        for (int l = 0; l < N; l++) n_free_bits += !is_rank[l];
         // blocked[bit]: 0 free, 1 only DIAGONAL ops were skipped on this bit (a later diagonal op commutes with all of
         // them and may still run in this sweep), 2 closed
         auto visit = [&](size_t i) {
             FlatOp& f = ops[i];
             if (f.done) return;
             bool blk = false;
-            int need = 0;
-            for (int b = 0; b < f.nb; b++)
+            int add[2], n_add = 0;
+            if (f.cp)
             {
-                const int lvl = blocked[f.bit[b]];
-                if (lvl == 2 || (lvl == 1 && !f.diag)) blk = true;
-                else if (!in_tile[f.bit[b]]) need++;
+                // a controlled phase runs as soon as ONE of its bits is in the tile; the other one is only read
+                bool any_in = false;
+                for (int b = 0; b < 2; b++)
+                {
+                    if (blocked[f.bit[b]] == 2) blk = true;
+                    if (in_tile[f.bit[b]]) any_in = true;
+                }
+                if (!blk && !any_in)
+                {
+                    if (!is_rank[f.bit[0]]) add[n_add++] = f.bit[0];
+                    else if (!is_rank[f.bit[1]]) add[n_add++] = f.bit[1];
+                    else blk = true;
+                }
             }
-            if (!blk && tile_cnt + need <= kmax && (int)c.picked.size() < opt.max_ops)
-            {
+            else
                 for (int b = 0; b < f.nb; b++)
-                    if (!in_tile[f.bit[b]]) { in_tile[f.bit[b]] = 1; c.tile_logical.push_back(f.bit[b]); tile_cnt++; }
+                {
+                    const int lvl = blocked[f.bit[b]];
+                    if (is_rank[f.bit[b]] || lvl == 2 || (lvl == 1 && !f.diag)) blk = true;
+                    else if (!in_tile[f.bit[b]]) add[n_add++] = f.bit[b];
+                }
+            if (!blk && tile_cnt + n_add <= kmax && picked_cost + (f.cp ? 1 : 8) <= 8 * opt.max_ops &&
+                (!f.cp || picked_cp < opt.max_cphase))
+            {
+                picked_cost += f.cp ? 1 : 8; // controlled phases merge into star ops: they hardly use op-table space
+                picked_cp += f.cp ? 1 : 0;   // ... but every one of them may need its own star slot
+                for (int b = 0; b < n_add; b++) { in_tile[add[b]] = 1; c.tile_logical.push_back(add[b]); tile_cnt++; }
                 c.picked.push_back((int)i);
-                c.score += f.weight;
+                c.score += 1000L * f.weight + 1; // zero-weight ops (1-qubit phases split off a controlled phase) still count as progress
             }
             else
                 for (int b = 0; b < f.nb; b++)
@@ -578,7 +643,7 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
                     const char lvl = f.diag ? 1 : 2;
                     if (blocked[f.bit[b]] < lvl)
                     {
-                        if (lvl == 2) n_free_bits--;
+                        if (lvl == 2 && !is_rank[f.bit[b]]) n_free_bits--;
                         blocked[f.bit[b]] = lvl;
                     }
                 }
@@ -652,6 +717,13 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
             t.weight = f.weight;
             memcpy(t.m, f.m, sizeof(t.m));
             t.cls = f.srn ? (int)CLS_SRN1 : classify(f.nb, f.m, nullptr);
+            if (f.cp)
+            {
+                t.cls = CLS_CPHASE; // symmetric in its two bits: keep the in-tile one first
+                if (t.j0 < 0) { std::swap(t.j0, t.j1); t.p1 = phys[f.bit[0]]; }
+                else if (t.j1 < 0) t.p1 = phys[f.bit[1]];
+                if (t.j0 < 0) throw std::logic_error("controlled phase scheduled without a tile bit");
+            }
             sw.ops.push_back(t);
             sw.weight += f.weight;
             f.done = true;
@@ -673,21 +745,28 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
         int n_open = 0;
         for (int l = 0; l < N; l++) n_open += in_tile[l] ? 1 : 0;
         long score = 0;
-        int n_picked = 0;
+        int n_picked = 0, n_cp = 0;
         for (size_t i = first_pending; i < ops.size() && n_open > 0; i++)
         {
             const FlatOp& f = ops[i];
             if (f.done) continue;
-            bool ok = n_picked < opt.max_ops;
-            for (int b = 0; b < f.nb; b++)
+            bool ok = n_picked + (f.cp ? 1 : 8) <= 8 * opt.max_ops && (!f.cp || n_cp < opt.max_cphase);
+            if (f.cp)
             {
-                const int lvl = blocked[f.bit[b]];
-                if (!in_tile[f.bit[b]] || lvl == 2 || (lvl == 1 && !f.diag)) ok = false;
+                if (blocked[f.bit[0]] == 2 || blocked[f.bit[1]] == 2) ok = false;
+                if (!in_tile[f.bit[0]] && !in_tile[f.bit[1]]) ok = false;
             }
+            else
+                for (int b = 0; b < f.nb; b++)
+                {
+                    const int lvl = blocked[f.bit[b]];
+                    if (!in_tile[f.bit[b]] || lvl == 2 || (lvl == 1 && !f.diag)) ok = false;
+                }
             if (ok)
             {
-                score += f.weight;
-                n_picked++;
+                score += 1000L * f.weight + 1;
+                n_picked += f.cp ? 1 : 8;
+                n_cp += f.cp ? 1 : 0;
                 if (picked) picked->push_back((int)i);
                 continue;
             }
@@ -718,6 +797,18 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
                 const FlatOp& f = ops[i];
                 if (f.done) continue;
                 looked++;
+                if (f.cp)
+                {
+                    // one bit in the tile is enough: each local bit is a candidate on its own
+                    if (in_tile[f.bit[0]] || in_tile[f.bit[1]]) continue;
+                    for (int b = 0; b < 2; b++)
+                    {
+                        if (phys[f.bit[b]] >= M) continue;
+                        std::vector<int> one(1, f.bit[b]);
+                        if (std::find(cands.begin(), cands.end(), one) == cands.end()) cands.push_back(one);
+                    }
+                    continue;
+                }
                 std::vector<int> miss;
                 bool local = true;
                 for (int b = 0; b < f.nb; b++)
@@ -788,11 +879,13 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
             {
                 if (ops[i].done) continue;
                 bool frontier = true, on_rank = false;
+                int n_rank = 0;
                 for (int b = 0; b < ops[i].nb; b++)
                 {
                     if (seen[ops[i].bit[b]]) frontier = false;
-                    if (phys[ops[i].bit[b]] >= M) on_rank = true;
+                    if (phys[ops[i].bit[b]] >= M) n_rank++;
                 }
+                on_rank = ops[i].cp ? n_rank == 2 : n_rank > 0; // a controlled phase only needs one local bit
                 if (frontier && on_rank)
                     for (int b = 0; b < ops[i].nb; b++) pending_w[ops[i].bit[b]] += (long)1 << 40;
                 for (int b = 0; b < ops[i].nb; b++) seen[ops[i].bit[b]] = 1;
@@ -887,7 +980,8 @@ std::string plan_to_json(const Plan& p, const std::vector<std::string>* extra)
         {
             const TileOp& t = sw.ops[i];
             if (i) o << ",";
-            o << "{\"cls\":" << t.cls << ",\"nb\":" << t.nb << ",\"j0\":" << t.j0 << ",\"j1\":" << t.j1 << ",\"m\":[";
+            o << "{\"cls\":" << t.cls << ",\"nb\":" << t.nb << ",\"j0\":" << t.j0 << ",\"j1\":" << t.j1 << ",\"p1\":" << t.p1
+              << ",\"m\":[";
             const int cnt = t.nb == 1 ? 4 : 16;
             for (int e = 0; e < cnt; e++) o << (e ? "," : "") << num(t.m[e].real()) << "," << num(t.m[e].imag());
             o << "]}";

@@ -31,7 +31,9 @@ enum OpClass : int
     CLS_SRN1 = 3,   // reference SRN_GATE (:1253-1266), real-linear, not a matrix
     CLS_DENSE2 = 4, // 4x4 dense:        m[0..15]
     CLS_DIAG2 = 5,  // diag(m0..m3)
-    CLS_MONO2 = 6   // monomial:         out[r] = m[r] * v[src[r]]
+    CLS_MONO2 = 6,  // monomial:         out[r] = m[r] * v[src[r]]
+    CLS_CPHASE = 7  // controlled phase diag(1, 1, 1, phi): only ONE of its bits has to be inside the tile -- the other
+                    // may be any physical bit (even a rank bit), it merely selects whether the phase applies
 };
 
 // one primitive / fused block on the half circuit (logical qubits 0..n-1)
@@ -49,6 +51,7 @@ struct TileOp
 {
     int cls = 0;
     int j0 = 0, j1 = 0; // tile-local bits; j0 carries the matrix MSB for 2-bit ops
+    int p1 = -1;        // CLS_CPHASE with its second bit outside the tile: j1 = -1 and p1 = that PHYSICAL bit
     int nb = 1;
     cplx m[16];         // FULL matrix (2x2 or 4x4) as applied (already conjugated for R parts)
     int weight = 1;
@@ -76,6 +79,8 @@ struct PlanOptions
     int low_bits = 3;   // physical bits 0..low_bits-1 are always tile bits (2^3 * 16 B = 128 B runs)
     int min_tiles_log2 = 10; // prefer >= 2^10 tiles when the state is small (keeps 148 SMs busy)
     int max_ops = 112;       // ops per sweep (the kernel keeps the sweep's op table in shared memory)
+    int max_cphase = 160;    // controlled phases per sweep (<= kMaxStarsPerSweep: each may need its own star slot)
+    bool cphase = true;      // schedule controlled phases with only one bit in the tile (CLS_CPHASE)
 };
 
 struct Plan
@@ -97,7 +102,7 @@ struct Plan
 // Throws std::invalid_argument on bad gates.
 void expand_gates(int n_qubits, const dmb_gate* gates, size_t n_gates, const double* mats, size_t n_mats,
                   std::vector<Block>& prims);
-void fuse_blocks(int n_qubits, const std::vector<Block>& prims, std::vector<Block>& blocks);
+void fuse_blocks(int n_qubits, const std::vector<Block>& prims, std::vector<Block>& blocks, bool split_cphase = true);
 Plan make_plan(int n_qubits, int world_size, const dmb_gate* gates, size_t n_gates, const double* mats,
                size_t n_mats, const std::vector<int>& start_layout, const PlanOptions& opt, bool conj_state = false,
                bool non_hermitian = false);

@@ -49,10 +49,18 @@ __device__ __forceinline__ void st_stream(double2* p, double2 v)
 // <-> round register bit r).  P / (PH, PL) are compile-time register bits, so every v[] index is static.
 // ------------------------------------------------------------------------------------------------
 constexpr int E = kRegElems;
-__device__ __forceinline__ const double2* op_m(const DevOp* op) { return reinterpret_cast<const double2*>(op->m); }
+// an op in the shared-memory op stream: DevOpHdr (16 bytes) + payload
+struct Op
+{
+    const unsigned char* p;
+    __device__ __forceinline__ const DevOpHdr* hdr() const { return reinterpret_cast<const DevOpHdr*>(p); }
+    __device__ __forceinline__ const double* m() const { return reinterpret_cast<const double*>(p + 16); }
+    __device__ __forceinline__ int aux() const { return hdr()->aux; }
+};
+__device__ __forceinline__ const double2* op_m(Op op) { return reinterpret_cast<const double2*>(op.p + 16); }
 
 template <int P>
-__device__ __forceinline__ void r_dense1(double2 (&v)[E], const DevOp* op)
+__device__ __forceinline__ void r_dense1(double2 (&v)[E], Op op)
 {
     const double2 m0 = op_m(op)[0], m1 = op_m(op)[1], m2 = op_m(op)[2], m3 = op_m(op)[3];
 #pragma unroll
@@ -68,9 +76,9 @@ __device__ __forceinline__ void r_dense1(double2 (&v)[E], const DevOp* op)
 // instructions of the generic 2x2): a' = d0 a + d1 b;  b' = (d2/d0) a' + (det/d0) b.  The encoder stores
 // e = {d0, d1, d2/d0, det/d0} and only emits this code when |d0| is not small.
 template <int P>
-__device__ __forceinline__ void r_dense1_rr(double2 (&v)[E], const DevOp* op)
+__device__ __forceinline__ void r_dense1_rr(double2 (&v)[E], Op op)
 {
-    const double e0 = op->m[0], e1 = op->m[1], e2 = op->m[2], e3 = op->m[3];
+    const double e0 = op.m()[0], e1 = op.m()[1], e2 = op.m()[2], e3 = op.m()[3];
 #pragma unroll
     for (int q = 0; q < E; q++)
         if (!(q & (1 << P)))
@@ -86,9 +94,9 @@ __device__ __forceinline__ void r_dense1_rr(double2 (&v)[E], const DevOp* op)
 // [[d0, i d1], [i d2, d3]] with real d, same in-place form: a' = d0 a + i d1 b;  b' = i (d2/d0) a' + (det/d0) b with
 // det = d0 d3 + d1 d2.  e = {d0, d1, d2/d0, det/d0}
 template <int P>
-__device__ __forceinline__ void r_dense1_ri(double2 (&v)[E], const DevOp* op)
+__device__ __forceinline__ void r_dense1_ri(double2 (&v)[E], Op op)
 {
-    const double e0 = op->m[0], e1 = op->m[1], e2 = op->m[2], e3 = op->m[3];
+    const double e0 = op.m()[0], e1 = op.m()[1], e2 = op.m()[2], e3 = op.m()[3];
 #pragma unroll
     for (int q = 0; q < E; q++)
         if (!(q & (1 << P)))
@@ -103,9 +111,9 @@ __device__ __forceinline__ void r_dense1_ri(double2 (&v)[E], const DevOp* op)
         }
 }
 template <int P>
-__device__ __forceinline__ void r_mono1(double2 (&v)[E], const DevOp* op)
+__device__ __forceinline__ void r_mono1(double2 (&v)[E], Op op)
 {
-    if ((op->aux >> 12) & 1) // unit phases (X): a register renaming
+    if ((op.aux() >> 12) & 1) // unit phases (X): a register renaming
     {
 #pragma unroll
         for (int q = 0; q < E; q++)
@@ -144,7 +152,7 @@ __device__ __forceinline__ void r_srn1(double2 (&v)[E])
 // 4x4 dense: two quads at a time, the matrix streamed row by row from shared memory (broadcast LDS.128): 32 matrix
 // loads per 256 DFMA, 32 temporaries -- the whole 4x4 in registers would not leave room for the 16 resident elements
 template <int PH, int PL>
-__device__ __forceinline__ void r_dense2(double2 (&v)[E], const DevOp* op)
+__device__ __forceinline__ void r_dense2(double2 (&v)[E], Op op)
 {
     constexpr int bh = 1 << PH, bl = 1 << PL;
     constexpr int rest = (E - 1) & ~(bh | bl);   // the two register bits the op does not touch
@@ -168,7 +176,7 @@ __device__ __forceinline__ void r_dense2(double2 (&v)[E], const DevOp* op)
 // monomial ops with one of three row permutations: W = 0: CX (MSB control): rows 2<->3; 1: CX (LSB control): rows
 // 1<->3; 2: SWAP: rows 1<->2.  out[r] = ph[r] * in[src[r]].  With unit phases the op is a pure register renaming.
 template <int PH, int PL, int W>
-__device__ __forceinline__ void r_perm2w(double2 (&v)[E], const DevOp* op)
+__device__ __forceinline__ void r_perm2w(double2 (&v)[E], Op op)
 {
     constexpr int bh = 1 << PH, bl = 1 << PL;
     constexpr int x = W == 0 ? bh : (W == 1 ? bl : bl), y = W == 0 ? (bh | bl) : (W == 1 ? (bh | bl) : bh);
@@ -180,7 +188,7 @@ __device__ __forceinline__ void r_perm2w(double2 (&v)[E], const DevOp* op)
             v[q | x] = v[q | y];
             v[q | y] = t;
         }
-    if (!((op->aux >> 12) & 1))
+    if (!((op.aux() >> 12) & 1))
     {
         const double2 p0 = op_m(op)[0], p1 = op_m(op)[1], p2 = op_m(op)[2], p3 = op_m(op)[3];
 #pragma unroll
@@ -195,9 +203,9 @@ __device__ __forceinline__ void r_perm2w(double2 (&v)[E], const DevOp* op)
     }
 }
 template <int PH, int PL>
-__device__ __forceinline__ void r_perm2(double2 (&v)[E], const DevOp* op)
+__device__ __forceinline__ void r_perm2(double2 (&v)[E], Op op)
 {
-    switch (op->aux & 3)
+    switch (op.aux() & 3)
     {
     case 0: r_perm2w<PH, PL, 0>(v, op); break;
     case 1: r_perm2w<PH, PL, 1>(v, op); break;
@@ -205,12 +213,36 @@ __device__ __forceinline__ void r_perm2(double2 (&v)[E], const DevOp* op)
     }
 }
 
-__device__ __forceinline__ void r_diagr(double2 (&v)[E], const DevOp* op)
+__device__ __forceinline__ void r_diagr(double2 (&v)[E], Op op)
 {
-    const int skip = op->aux & 0xffff;
+    const int skip = op.aux() & 0xffff;
 #pragma unroll
     for (int c = 0; c < E; c++)
         if (!((skip >> c) & 1)) v[c] = cmul(op_m(op)[c], v[c]);
+}
+
+// controlled-phase star: the elements whose register bit p is set get the phase  L_p[lane] * WO_p[iw]
+struct StarCtx
+{
+    const DevStar* stars; // global
+    const double2* wo;    // shared: per tile, [slot][8]
+    int lane, iw;
+};
+__device__ __forceinline__ void r_star(double2 (&v)[E], Op op, const StarCtx& sc)
+{
+    const int mask = op.aux() & 15;
+    int slot = op.hdr()->star[0];
+#pragma unroll
+    for (int p = 0; p < kRegBits; p++)
+        if ((mask >> p) & 1)
+        {
+            const double2 l = __ldg(reinterpret_cast<const double2*>(sc.stars[slot].l) + sc.lane);
+            const double2 phi = cmul(l, sc.wo[slot * 8 + sc.iw]);
+            slot++;
+#pragma unroll
+            for (int c = 0; c < E; c++)
+                if (c & (1 << p)) v[c] = cmul(phi, v[c]);
+        }
 }
 
 // MASK = the register-op codes compiled into this instantiation of the kernel (bit c <-> RegOpCode c).  ptxas keeps
@@ -232,7 +264,7 @@ __device__ __forceinline__ void r_diagr(double2 (&v)[E], const DevOp* op)
     case (c) * 8 + 5: if (DMB_HAS(c)) FN<3, 2>(__VA_ARGS__); break;
 
 template <unsigned MASK>
-__device__ __forceinline__ void apply_reg_op(double2 (&v)[E], const DevOp* op, int vid)
+__device__ __forceinline__ void apply_reg_op(double2 (&v)[E], Op op, int vid, const StarCtx& sc)
 {
     switch (vid)
     {
@@ -244,6 +276,7 @@ __device__ __forceinline__ void apply_reg_op(double2 (&v)[E], const DevOp* op, i
         DMB_CASE1(RC_MONO1, r_mono1, v, op)
         DMB_CASE1(RC_SRN1, r_srn1, v)
     case RC_DIAGR * 8: if (DMB_HAS(RC_DIAGR)) r_diagr(v, op); break;
+    case RC_STAR * 8: if (DMB_HAS(RC_STAR)) r_star(v, op, sc); break;
     default: break;
     }
 }
@@ -258,9 +291,10 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
     const int k = a.k;
     const unsigned tile_elems = 1u << k;
     double2* tile = reinterpret_cast<double2*>(smem_raw);
-    DevOp* s_ops = reinterpret_cast<DevOp*>(smem_raw + (size_t)16 * tile_elems);
-    DevRound* s_rounds = reinterpret_cast<DevRound*>(s_ops + a.n_ops);
+    unsigned char* s_ops = smem_raw + (size_t)16 * tile_elems;
+    DevRound* s_rounds = reinterpret_cast<DevRound*>(s_ops + a.ops_bytes);
     DevGroup* s_groups = reinterpret_cast<DevGroup*>(s_rounds + a.n_rounds);
+    double2* s_wo = reinterpret_cast<double2*>(s_groups + a.n_groups); // [n_stars][8], rebuilt for every tile
     constexpr int NT = kTileThreads;
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
@@ -272,7 +306,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
             int4* dst = reinterpret_cast<int4*>(sdst);
             for (int i = t; i < bytes / 16; i += NT) dst[i] = __ldg(src + i);
         };
-        stage(a.ops, s_ops, a.n_ops * (int)sizeof(DevOp));
+        stage(a.ops, s_ops, a.ops_bytes);
         stage(a.rounds, s_rounds, a.n_rounds * (int)sizeof(DevRound));
         stage(a.groups, s_groups, a.n_groups * (int)sizeof(DevGroup));
     }
@@ -314,6 +348,21 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                 if (it < n_it) cp_async16(&tile[swz((unsigned)(it << kThreadBits)) ^ s_in], src + a.hin[it]);
         }
         cp_async_commit();
+        // controlled-phase stars: fold the partner bits OUTSIDE the tile (fixed for this tile) into the per-warp /
+        // per-iteration table while the tile is in flight
+        if (DMB_HAS(RC_STAR))
+        {
+            const unsigned long long full = base_in | a.rank_bits;
+            for (int i = t; i < a.n_stars * 8; i += NT)
+            {
+                const DevStar* st = a.stars + (i >> 3);
+                double2 acc = __ldg(reinterpret_cast<const double2*>(st->w) + (i & 7));
+                const int n_out = st->n_out;
+                for (int j = 0; j < n_out; j++)
+                    if ((full >> st->bit[j]) & 1ull) acc = cmul(acc, __ldg(reinterpret_cast<const double2*>(st->phi) + j));
+                s_wo[i] = acc;
+            }
+        }
         cp_async_wait<0>();
         __syncthreads();
 
@@ -333,8 +382,10 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                     {
                         const unsigned lbase = rd->lane_tab[lane] ^ wpart;
                         const int n_iter = rd->n_iter;
-                        const DevOp* ops = s_ops + rd->first;
+                        const unsigned char* ops = s_ops + (size_t)rd->first * 16;
                         const int n_ops = rd->count;
+                        int nib = 0;
+                        while ((1 << nib) < n_iter) nib++;
                         // the 16 register offsets, packed two per word (kept in 8 registers: re-reading them from
                         // shared memory at store time would serialise every STS behind an LDS)
                         unsigned rw[E / 2];
@@ -350,11 +401,15 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                             double2 v[E];
 #pragma unroll
                             for (int c = 0; c < E; c++) v[c] = tile[base ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)];
-                            int vid = n_ops > 0 ? ops[0].vid : 0;
+                            const StarCtx sc = {a.stars, s_wo, lane, (warp << nib) | it};
+                            Op op = {ops};
+                            int vid = op.hdr()->vid; // (a zero header follows the last op of the stream)
                             for (int o = 0; o < n_ops; o++)
                             {
-                                const int next = o + 1 < n_ops ? ops[o + 1].vid : 0; // fetched while this op runs
-                                apply_reg_op<MASK>(v, ops + o, vid);
+                                const Op nxt = {op.p + op.hdr()->size16 * 16};
+                                const int next = nxt.hdr()->vid; // fetched while this op runs
+                                apply_reg_op<MASK>(v, op, vid, sc);
+                                op = nxt;
                                 vid = next;
                             }
 #pragma unroll
@@ -386,13 +441,14 @@ static int g_num_sms = 0;
 constexpr unsigned kVariantMasks[] = {
     0u,                                                                              // pure data movement (remap pack)
     BIT(RC_DENSE2),                                                                  // random C2 blocks
-    BIT(RC_DIAGR) | BIT(RC_DENSE1_RR),                                               // QFT-like
+    BIT(RC_DIAGR) | BIT(RC_DENSE1_RR),                                               // H + diagonal
+    BIT(RC_DIAGR) | BIT(RC_DENSE1_RR) | BIT(RC_STAR),                                // QFT-like
     BIT(RC_DENSE1_RR) | BIT(RC_PERM2),                                               // H / CX
     BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_DENSE1_RI),         // dense 1- and 2-qubit blocks
     BIT(RC_DIAGR) | BIT(RC_DENSE1_RR) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1),               // Clifford+T style
-    BIT(RC_DIAGR) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1), // no dense 4x4
+    BIT(RC_DIAGR) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) | BIT(RC_STAR), // no dense 4x4
     BIT(RC_DIAGR) | BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) |
-        BIT(RC_SRN1),                                                                // everything
+        BIT(RC_SRN1) | BIT(RC_STAR),                                                 // everything
 };
 constexpr int kNumVariants = sizeof(kVariantMasks) / sizeof(kVariantMasks[0]);
 typedef void (*SweepFn)(const SweepArgs);
@@ -426,15 +482,16 @@ void sweep_setup()
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     VariantTable<kNumVariants - 1>::fill(g_variants);
-    const int max_smem = (16 << kMaxTileBits) + kMaxOpsPerSweep * (int)(sizeof(DevOp) + sizeof(DevRound) + sizeof(DevGroup));
+    const int max_smem = (16 << kMaxTileBits) + kMaxOpsPerSweep * (int)(sizeof(DevOp) + sizeof(DevRound) + sizeof(DevGroup)) +
+                         kMaxStarsPerSweep * 128;
     for (int i = 0; i < kNumVariants; i++)
         cudaFuncSetAttribute(g_variants[i], cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
 }
 
 size_t sweep_smem_bytes(const SweepArgs& a)
 {
-    return ((size_t)16 << a.k) + (size_t)a.n_ops * sizeof(DevOp) + (size_t)a.n_rounds * sizeof(DevRound) +
-           (size_t)a.n_groups * sizeof(DevGroup);
+    return ((size_t)16 << a.k) + (size_t)a.ops_bytes + (size_t)a.n_rounds * sizeof(DevRound) +
+           (size_t)a.n_groups * sizeof(DevGroup) + (size_t)a.n_stars * 128;
 }
 
 int sweep_max_grid(const SweepArgs& a)

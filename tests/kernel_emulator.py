@@ -28,7 +28,7 @@ def _dep(v, pos):
     return r
 
 
-def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = None) -> np.ndarray:
+def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = None, rank: int = 0) -> np.ndarray:
     """One sweep_kernel launch over a shard given in PHYSICAL order; returns the output shard."""
     k, n_comp = dev["k"], dev["n_comp"]
     tile_elems, n_tiles = 1 << k, 1 << n_comp
@@ -52,11 +52,12 @@ def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = No
         tiles[:, swz(it << TB) ^ s_in[act]] = shard_in[src]
     assert not np.isnan(tiles.real).any(), "load did not fill the tile"
 
+    full = base_in | (rank << (k + n_comp))  # the full physical index of the tile's first element (rank bits on top)
     for grp in dev["groups"]:
         for w in range(grp["n_warps"]):
             wpart = grp["wtab"][w]
             for ri in range(grp["first"], grp["first"] + grp["count"]):
-                _run_round(dev, dev["rounds"][ri], tiles, wpart)
+                _run_round(dev, dev["rounds"][ri], tiles, wpart, w, full)
 
     seen = np.zeros(shard_in.size, dtype=bool)
     for it in range(n_it):
@@ -68,7 +69,7 @@ def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = No
     return out
 
 
-RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE2, RC_DIAG2, RC_PERM2, RC_DIAGR, RC_DENSE1_RR, RC_DENSE1_RI = range(10)
+RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE2, RC_DIAG2, RC_PERM2, RC_DIAGR, RC_DENSE1_RR, RC_DENSE1_RI, RC_STAR = range(11)
 _POS2 = {0: (1, 0), 1: (2, 0), 2: (2, 1), 3: (3, 0), 4: (3, 1), 5: (3, 2)}
 _PERMS = {0: [0, 1, 3, 2], 1: [0, 3, 2, 1], 2: [0, 2, 1, 3]}
 
@@ -79,16 +80,49 @@ def _round_items(rd, wpart):
     return ((lane[:, None] ^ wpart) ^ itab[None, :]).reshape(-1)
 
 
-def _run_round(dev, rd, tiles, wpart):
+def _run_round(dev, rd, tiles, wpart, warp, full):
     """One register round of one warp: load 16 elements per work item, apply the round's ops, store back."""
     base = _round_items(rd, wpart)
     roff = [int(x) for x in rd["roff"]]
     idx = [base ^ roff[c] for c in range(E)]
     v = [tiles[:, i].copy() for i in idx]  # v[c]: (n_tiles, n_items)
-    for o in range(rd["first"], rd["first"] + rd["count"]):
-        _apply_reg_op(dev["ops"][o], v)
+    # work item -> (lane, iteration), as _round_items flattens them; iw = (warp << iteration bits) | iteration
+    n_iter = rd["n_iter"]
+    lane = np.repeat(np.arange(rd["n_active"]), n_iter)
+    iw = (warp << (n_iter.bit_length() - 1)) | np.tile(np.arange(n_iter), rd["n_active"])
+    first = next(i for i, op in enumerate(dev["ops"]) if op["off"] == rd["first"]) if rd["count"] else 0
+    for o in range(first, first + rd["count"]):
+        op = dev["ops"][o]
+        if op["code"] == RC_STAR:
+            _apply_star(dev, op, v, lane, iw, full)
+        else:
+            _apply_reg_op(op, v)
     for c in range(E):  # duplicates (tiny tiles) carry identical values
         tiles[:, idx[c]] = v[c]
+
+
+def _cplx(a):
+    a = np.asarray(a, dtype=np.float64)
+    return a[0::2] + 1j * a[1::2]
+
+
+def _apply_star(dev, op, v, lane, iw, full):
+    """RC_STAR: elements with register bit p set get L_p[lane] * WO_p[tile, iw]; WO folds the outside partner bits."""
+    slot = op["star"]
+    for p in range(4):
+        if not (op["aux"] >> p) & 1:
+            continue
+        st = dev["stars"][slot]
+        slot += 1
+        w, l, phi = _cplx(st["w"]), _cplx(st["l"]), _cplx(st["phi"])
+        wo = np.tile(w[None, :], (full.size, 1))  # (n_tiles, 8)
+        for j, b in enumerate(st["bit"]):
+            sel = ((full >> int(b)) & 1).astype(bool)
+            wo[sel, :] *= phi[j]
+        ph = l[lane][None, :] * wo[:, iw]  # (n_tiles, n_items)
+        for c in range(E):
+            if c & (1 << p):
+                v[c] = ph * v[c]
 
 
 def _apply_reg_op(op, v):
@@ -193,8 +227,8 @@ def run_plan_dev(plan: dict, vec_logical: np.ndarray) -> np.ndarray:
         check_group_partition(st["dev"])
         for r in range(P):
             if st["out_of_place"]:
-                shards[r] = run_sweep(st["dev"], shards[r], np.full_like(shards[r], np.nan))
+                shards[r] = run_sweep(st["dev"], shards[r], np.full_like(shards[r], np.nan), rank=r)
             else:
-                shards[r] = run_sweep(st["dev"], shards[r])
+                shards[r] = run_sweep(st["dev"], shards[r], rank=r)
     v = physical_to_logical(np.concatenate(shards), plan["end_layout"])
     return np.conj(v) if plan.get("conj_end") else v

@@ -82,7 +82,9 @@ def run_plan(plan: dict, vec_logical: np.ndarray) -> np.ndarray:
                 continue
             m = np.array(op["m"], dtype=np.float64)
             m = (m[0::2] + 1j * m[1::2]).reshape(1 << nb, 1 << nb)
-            bits = [in_pos[op["j0"]]] + ([in_pos[op["j1"]]] if nb == 2 else [])
+            bits = [in_pos[op["j0"]]]
+            if nb == 2:  # a controlled phase may have its second bit outside the tile (even on a rank bit)
+                bits.append(in_pos[op["j1"]] if op["j1"] >= 0 else op["p1"])
             v = _apply_matrix(v, N, m, bits)
         if in_pos != out_pos:
             assert st["out_of_place"]

@@ -132,6 +132,46 @@ def test_large_op_counts_split_into_sweeps(dm, oracle_mod):
     n = 4
     gates = random_gates(n, 400, rng)
     plan = dm.plan_json(n, 1, gates)
-    assert all(len(st["ops"]) <= 112 for st in plan["steps"]) and plan["n_sweeps"] > 1
+    # controlled phases (cls 7) merge into star ops and count 1/8 towards the table, at most 160 of them per sweep
+    for st in plan["steps"]:
+        n_cp = sum(1 for o in st["ops"] if o["cls"] == 7)
+        assert 8 * (len(st["ops"]) - n_cp) + n_cp <= 8 * 112 and n_cp <= 160
+    assert plan["n_sweeps"] > 1
     re, im = oracle_mod.Oracle(n).sim(gates).dm()
     assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - to_complex(re, im)).max() < TOL
+
+
+@pytest.mark.parametrize("n,world,o", [
+    (5, 1, {}), (7, 1, {}), (7, 1, dict(tile_bits=8, low_bits=2, min_tiles_log2=2)),
+    (6, 1, dict(tile_bits=5, low_bits=0, min_tiles_log2=2)), (7, 1, dict(tile_bits=12, low_bits=3, min_tiles_log2=1)),
+    (6, 2, {}), (7, 4, dict(tile_bits=8)), (7, 8, dict(tile_bits=7, low_bits=1)), (6, 8, {}),
+])
+def test_controlled_phase_stars(dm, oracle_mod, opts, n, world, o):
+    """Controlled phases run with ONE bit in the tile / in the register round (CLS_CPHASE, RC_STAR): the partner bit may be
+    a lane / warp / iteration bit, a bit outside the tile or a rank bit.  QFT plus a mix of diagonal 2-qubit gates."""
+    import importlib
+    circuits = importlib.import_module("dm-sim_b200.circuits")
+    opts(**o)
+    rng = np.random.default_rng(77 + n + world)
+    gates = circuits.qft(n)
+    for _ in range(30):
+        a, b = (int(x) for x in rng.choice(n, size=2, replace=False))
+        kind = rng.integers(6)
+        th = float(rng.uniform(-3, 3))
+        gates.append([("CU1", [a, b], 0, 0, th), ("CZ", [a, b], 0, 0, 0), ("CRZ", [a, b], 0, 0, th), ("RZZ", [a, b], th, 0, 0),
+                      ("H", [a], 0, 0, 0), ("U3", [b], th, 0.3, -0.2)][kind])
+    re, im = oracle_mod.Oracle(n).sim(gates).dm()
+    ref = to_complex(re, im)
+    plan = dm.plan_json(n, world, gates)
+    n_cp = sum(1 for st in plan["steps"] if st["kind"] == "sweep" for op in st["ops"] if op["cls"] == 7)
+    assert n_cp > 0
+    assert np.abs(pe.run_plan(plan, zero_state(n)) - ref).max() < TOL
+    assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - ref).max() < TOL
+    # the same circuit with the controlled-phase scheduling switched off gives the same state
+    dm.set_option("cphase", 0)
+    try:
+        plan0 = dm.plan_json(n, world, gates)
+        assert sum(1 for st in plan0["steps"] if st["kind"] == "sweep" for op in st["ops"] if op["cls"] == 7) == 0
+        assert np.abs(ke.run_plan_dev(plan0, zero_state(n)) - ref).max() < TOL
+    finally:
+        dm.set_option("cphase", 1)
