@@ -53,14 +53,16 @@ constexpr int kMaxStarOut = 28;
 struct alignas(16) DevStar
 {
     double w[16];  // 8 complex: index = (warp << iteration bits) | iteration
-    double l[64];  // 32 complex: index = lane
+    double la[16]; // lane part, factored so that it fits shared memory: L[lane] = la[lane & 7] * lb[lane >> 3]
+    double lb[8];
     int32_t n_out;
     int32_t pad[3];
     int32_t bit[kMaxStarOut];    // physical bit of the full index (>= M: rank bits)
     double phi[2 * kMaxStarOut]; // (re, im)
 };
-static_assert(sizeof(DevStar) == 1216, "DevStar layout");
-constexpr int kMaxStarsPerSweep = 160; // 128 bytes of shared memory each
+static_assert(sizeof(DevStar) == 896, "DevStar layout");
+constexpr int kMaxStarsPerSweep = 160; // 320 bytes of shared memory each (w + la + lb staged once, WO rebuilt per tile)
+constexpr int kStarSmemBytes = 320;
 
 // Device op stream: 16-byte header + payload (the used part of DevOp::m), 16-byte granularity; a zero header ends it.
 struct alignas(16) DevOpHdr

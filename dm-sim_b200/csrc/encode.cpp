@@ -418,14 +418,16 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                             st.w[2 * iw] = acc.real();
                             st.w[2 * iw + 1] = acc.imag();
                         }
-                        for (int l = 0; l < 32; l++)
+                        for (int l = 0; l < 12; l++) // la[0..7]: lane bits 0..2, lb[0..3]: lane bits 3..4
                         {
-                            const unsigned idx = deposit((unsigned)l & ((1u << nl) - 1u), lanep);
+                            const unsigned lane = l < 8 ? (unsigned)l : (unsigned)(l - 8) << 3;
+                            const unsigned idx = deposit(lane & ((1u << nl) - 1u), lanep);
                             cplx acc(1.0, 0.0);
                             for (const StarPartner& sp : run.star[p])
                                 if (sp.tile && ((idx >> sp.bit) & 1u)) acc *= sp.phi;
-                            st.l[2 * l] = acc.real();
-                            st.l[2 * l + 1] = acc.imag();
+                            double* dst = l < 8 ? st.la + 2 * l : st.lb + 2 * (l - 8);
+                            dst[0] = acc.real();
+                            dst[1] = acc.imag();
                         }
                         for (const StarPartner& sp : run.star[p])
                             if (!sp.tile)
@@ -630,8 +632,10 @@ std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a)
         const DevStar& st = e.stars[i];
         o << (i ? "," : "") << "{\"w\":[";
         dbl(st.w, 16);
-        o << "],\"l\":[";
-        dbl(st.l, 64);
+        o << "],\"la\":[";
+        dbl(st.la, 16);
+        o << "],\"lb\":[";
+        dbl(st.lb, 8);
         o << "],\"bit\":[";
         for (int j = 0; j < st.n_out; j++) o << (j ? "," : "") << st.bit[j];
         o << "],\"phi\":[";

@@ -224,10 +224,10 @@ __device__ __forceinline__ void r_diagr(double2 (&v)[E], Op op)
 // controlled-phase star: the elements whose register bit p is set get the phase  L_p[lane] * WO_p[iw]
 struct StarCtx
 {
-    const DevStar* stars; // global
-    const double2* wo;    // shared: per tile, [slot][8]
+    const double2* tab; // shared, per slot 20 entries: WO[8] (rebuilt per tile) | la[8] | lb[4] (staged once)
     int lane, iw;
 };
+constexpr int kStarEntries = kStarSmemBytes / 16;
 __device__ __forceinline__ void r_star(double2 (&v)[E], Op op, const StarCtx& sc)
 {
     const int mask = op.aux() & 15;
@@ -236,8 +236,8 @@ __device__ __forceinline__ void r_star(double2 (&v)[E], Op op, const StarCtx& sc
     for (int p = 0; p < kRegBits; p++)
         if ((mask >> p) & 1)
         {
-            const double2 l = __ldg(reinterpret_cast<const double2*>(sc.stars[slot].l) + sc.lane);
-            const double2 phi = cmul(l, sc.wo[slot * 8 + sc.iw]);
+            const double2* tb = sc.tab + slot * kStarEntries;
+            const double2 phi = cmul(cmul(tb[8 + (sc.lane & 7)], tb[16 + (sc.lane >> 3)]), tb[sc.iw]);
             slot++;
 #pragma unroll
             for (int c = 0; c < E; c++)
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
     unsigned char* s_ops = smem_raw + (size_t)16 * tile_elems;
     DevRound* s_rounds = reinterpret_cast<DevRound*>(s_ops + a.ops_bytes);
     DevGroup* s_groups = reinterpret_cast<DevGroup*>(s_rounds + a.n_rounds);
-    double2* s_wo = reinterpret_cast<double2*>(s_groups + a.n_groups); // [n_stars][8], rebuilt for every tile
+    double2* s_star = reinterpret_cast<double2*>(s_groups + a.n_groups); // [n_stars][WO[8] | la[8] | lb[4]]
     constexpr int NT = kTileThreads;
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
@@ -309,6 +309,9 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
         stage(a.ops, s_ops, a.ops_bytes);
         stage(a.rounds, s_rounds, a.n_rounds * (int)sizeof(DevRound));
         stage(a.groups, s_groups, a.n_groups * (int)sizeof(DevGroup));
+        if (DMB_HAS(RC_STAR))
+            for (int i = t; i < a.n_stars * 12; i += NT) // la | lb are contiguous in DevStar
+                s_star[(i / 12) * kStarEntries + 8 + i % 12] = __ldg(reinterpret_cast<const double2*>(a.stars[i / 12].la) + i % 12);
     }
 
     // per-thread part of the address maps (the low kThreadBits loop bits come from the thread index)
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                 const int n_out = st->n_out;
                 for (int j = 0; j < n_out; j++)
                     if ((full >> st->bit[j]) & 1ull) acc = cmul(acc, __ldg(reinterpret_cast<const double2*>(st->phi) + j));
-                s_wo[i] = acc;
+                s_star[(i >> 3) * kStarEntries + (i & 7)] = acc;
             }
         }
         cp_async_wait<0>();
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                             double2 v[E];
 #pragma unroll
                             for (int c = 0; c < E; c++) v[c] = tile[base ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)];
-                            const StarCtx sc = {a.stars, s_wo, lane, (warp << nib) | it};
+                            const StarCtx sc = {s_star, lane, (warp << nib) | it};
                             Op op = {ops};
                             int vid = op.hdr()->vid; // (a zero header follows the last op of the stream)
                             for (int o = 0; o < n_ops; o++)
@@ -483,7 +486,7 @@ void sweep_setup()
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     VariantTable<kNumVariants - 1>::fill(g_variants);
     const int max_smem = (16 << kMaxTileBits) + kMaxOpsPerSweep * (int)(sizeof(DevOp) + sizeof(DevRound) + sizeof(DevGroup)) +
-                         kMaxStarsPerSweep * 128;
+                         kMaxStarsPerSweep * kStarSmemBytes;
     for (int i = 0; i < kNumVariants; i++)
         cudaFuncSetAttribute(g_variants[i], cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
 }
@@ -491,7 +494,7 @@ void sweep_setup()
 size_t sweep_smem_bytes(const SweepArgs& a)
 {
     return ((size_t)16 << a.k) + (size_t)a.ops_bytes + (size_t)a.n_rounds * sizeof(DevRound) +
-           (size_t)a.n_groups * sizeof(DevGroup) + (size_t)a.n_stars * 128;
+           (size_t)a.n_groups * sizeof(DevGroup) + (size_t)a.n_stars * kStarSmemBytes;
 }
 
 int sweep_max_grid(const SweepArgs& a)

@@ -114,7 +114,8 @@ def _apply_star(dev, op, v, lane, iw, full):
             continue
         st = dev["stars"][slot]
         slot += 1
-        w, l, phi = _cplx(st["w"]), _cplx(st["l"]), _cplx(st["phi"])
+        w, phi = _cplx(st["w"]), _cplx(st["phi"])
+        l = _cplx(st["la"])[np.arange(32) & 7] * _cplx(st["lb"])[np.arange(32) >> 3]
         wo = np.tile(w[None, :], (full.size, 1))  # (n_tiles, 8)
         for j, b in enumerate(st["bit"]):
             sel = ((full >> int(b)) & 1).astype(bool)
