@@ -91,6 +91,12 @@ def workload(name):
         return n, circuits.bv(n)
     if fam == "adder":
         return 10, circuits.adder_n10()
+    if fam == "vqe_uccsd":  # benchmark/vqe_uccsd_n8.qasm (10808 gates): the gate list travels inside the golden fixture
+        import numpy as np
+        z = np.load(os.path.join(ROOT, "tests", "golden", "vqe_uccsd_n8.npz"))
+        names = importlib.import_module("dm-sim_b200").OP_NAMES
+        return int(z["n"]), [(names[int(g["op"])], [int(q) for q in g["qb"][:2]], float(g["theta"]), float(g["phi"]),
+                              float(g["lam"])) for g in z["gates"]]
     if fam == "random_c1c2":
         return n, circuits.random_c1c2(n, 256)
     if fam == "single":   # one gate = one sweep with 2 ops: the memory pipeline of the sweep kernel
@@ -135,7 +141,7 @@ def reference_arm(args, name):
     sample = (f"{fam}_n{n_s} ({len(g_s)} gates) via dmsim_cpu_omp n_cpus={n_cpus}: {ms_sample:.1f} ms/sim; scaled x4^{n - n_s}"
               f" and x{len(gates)}/{len(g_s)} gates to {name}")
     line = {"metric": "gates/sec", "value": value, "unit": "gates/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_full, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": ms_full, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": {"workload": name, "n_qubits": n, "n_gates": len(gates)},
             "cpu_baseline": {"value": value, "unit": "gates/s", "cores": n_cpus, "kind": kind, "sample": sample},
@@ -147,11 +153,11 @@ def reference_arm(args, name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=None)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--cpu-sample-qubits", type=int, default=12)
+    ap.add_argument("--cpu-sample-qubits", type=int, default=13)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -256,18 +262,22 @@ def main():
     line = {
         "metric": "gates/sec", "value": n_gates / (ms_step * 1e-3), "unit": "gates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_gate": ms_step / n_gates,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "n_qubits": n, "n_gates": n_gates, "n_primitives": st["n_primitives"],
                    "fused_blocks_per_side": st["n_blocks"], "sweeps_per_step": st["n_sweeps"],
                    "exchanges_per_step": st["n_exchanges"], "state_bytes": 16 * 4 ** n,
-                   "l2_policy": "state (>= 16 GiB per GPU) is far larger than the 126 MB L2; no flush needed",
+                   "state_bytes_per_gpu": 16 * 4 ** n // world,
+                   "scaling_note": "BASELINE.json configs: 15 q on 1 GPU, 16 q on 2/4 GPUs, 17 q on 8 GPUs (16-32 GiB per GPU)",
+                   "l2_policy": "state per GPU (>= 16 GiB at the named sizes) is far larger than the 126 MB L2; no flush needed",
                    "parallelism": f"shard on top {world.bit_length() - 1} index bits" if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "kernel": "sweep_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "frac_of_8TBs_nominal": achieved / 8000.0, "peak_source": peak_src,
-                     "avg_launch_ms": comp_ms / max(1, sweeps), "bytes_per_launch": sweep_bytes, "traffic": None},
+                     "avg_launch_ms": comp_ms / max(1, sweeps), "bytes_per_launch": sweep_bytes,
+                     "traffic": _ncu_traffic(args.workload)},
         "e2e": {"value": n_gates / (e2e * 1e-3), "unit": "gates/s", "ms_per_step": e2e,
-                "h2d_bytes_per_step": int(sim_h2d_bytes(st, len(rec), mats)), "d2h_bytes_per_step": 8 * (1 << n),
-                "what": "dmb_reset_dm + dmb_set_circuit(host gate list) + dmb_run + dmb_get_diag(host)"},
+                "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": 8 * (1 << n),
+                "what": "host gate list in, host diagonal out: dmb_reset_dm + dmb_set_circuit (plan + H2D of the device op "
+                        "tables) + dmb_run + dmb_get_diag (D2H of the 2^n probabilities), wall clock"},
         "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
         "trace_after_run": trace, "clocks": clocks,
     }
@@ -285,10 +295,14 @@ def main():
         dist.destroy_process_group()
 
 
-def sim_h2d_bytes(st, n_rec, mats):
-    # host gate list handed to the C-ABI (56 B per Gate + matrix table); the device op table derived from it is
-    # what actually crosses PCIe: 272 B per fused op
-    return n_rec * 56 + mats.size * 8
+def _ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per sweep_kernel launch from the committed `ncu --set full` capture
+    of this workload (profiles/ncu_traffic.json), or None when it has not been captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
 
 
 if __name__ == "__main__":

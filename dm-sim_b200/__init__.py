@@ -43,7 +43,7 @@ class dmb_stats(ctypes.Structure):
     _fields_ = [("sim_ms", ctypes.c_double), ("comm_ms", ctypes.c_double), ("comp_ms", ctypes.c_double),
                 ("n_gates", ctypes.c_uint64), ("n_primitives", ctypes.c_uint64), ("n_blocks", ctypes.c_uint64),
                 ("n_sweeps", ctypes.c_uint64), ("n_exchanges", ctypes.c_uint64), ("n_launches", ctypes.c_uint64),
-                ("sweep_bytes", ctypes.c_uint64), ("exchange_bytes", ctypes.c_uint64)]
+                ("sweep_bytes", ctypes.c_uint64), ("exchange_bytes", ctypes.c_uint64), ("h2d_bytes", ctypes.c_uint64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -75,6 +75,7 @@ def lib():
     L.dmb_run.argtypes = [vp, ctypes.POINTER(dmb_stats)]
     L.dmb_get_dm.argtypes = [vp, vp, vp]
     L.dmb_get_diag.argtypes = [vp, vp]
+    L.dmb_get_elements.argtypes = [vp, vp, sz, vp, vp]
     L.dmb_trace.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.dmb_purity.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.dmb_sample.argtypes = [vp, vp, sz, vp, ctypes.POINTER(ctypes.c_double)]
@@ -288,6 +289,13 @@ class Simulation:
         imag = np.ascontiguousarray(imag, dtype=np.float64)
         assert real.size == self.dim * self.dim and imag.size == self.dim * self.dim
         _check(lib().dmb_set_dm(self._h, real.ctypes.data, imag.ctypes.data))
+
+    def elements(self, flat_index):
+        """dm_real_res[f] + 1j * dm_imag_res[f] for f = col*dim + row (spot checks without the full copy-back)."""
+        idx = np.ascontiguousarray(flat_index, dtype=np.uint64)
+        re, im = np.empty(idx.size), np.empty(idx.size)
+        _check(lib().dmb_get_elements(self._h, idx.ctypes.data, idx.size, re.ctypes.data, im.ctypes.data))
+        return re + 1j * im
 
     def diag(self):
         d = np.empty(self.dim)

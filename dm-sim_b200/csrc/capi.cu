@@ -604,6 +604,7 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
         stats->n_launches = launches;
         stats->sweep_bytes = 32ull * s->shard_elems;
         stats->exchange_bytes = s->plan.n_exchanges * (uint64_t)(s->world - 1) * (s->shard_elems / s->world) * 16ull;
+        stats->h2d_bytes = s->h2d_bytes;
     }
     return DMB_OK;
 }
@@ -629,6 +630,28 @@ int dmb_get_dm(dmb_handle s, double* real, double* imag)
         CU(cudaMemcpyAsync(imag + first, d_im, chunk * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
     }
+    return DMB_OK;
+}
+
+int dmb_get_elements(dmb_handle s, const uint64_t* flat_index, size_t n, double* real, double* imag)
+{
+    if (!s || (n && (!flat_index || !real || !imag))) return fail(DMB_EINVAL, "null argument");
+    if (!n) return DMB_OK;
+    const uint64_t total = 1ull << s->N;
+    for (size_t i = 0; i < n; i++)
+        if (flat_index[i] >= total) return fail(DMB_EINVAL, "element index out of range");
+    CU(cudaSetDevice(s->device));
+    int rc = ensure_scratch(s, n * (sizeof(unsigned long long) + 2 * sizeof(double)));
+    if (rc) return rc;
+    double* d_re = s->d_scratch;
+    double* d_im = d_re + n;
+    unsigned long long* d_idx = reinterpret_cast<unsigned long long*>(d_im + n);
+    CU(cudaMemcpyAsync(d_idx, flat_index, n * sizeof(unsigned long long), cudaMemcpyHostToDevice, s->stream));
+    launch_gather_elements(s->buf[s->cur], layout_args(s), d_idx, n, d_re, d_im, s->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(real, d_re, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(imag, d_im, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
     return DMB_OK;
 }
 

@@ -190,6 +190,29 @@ void launch_gather_split(const double2* buf, const LayoutArgs& L, unsigned long 
     gather_split_kernel<<<grid, 256, 0, s>>>(buf, L, first, count, re, im);
 }
 
+// arbitrary logical flat indices (col*dim + row) -> values; elements another rank owns come back as zero
+__global__ void gather_elements_kernel(const double2* __restrict__ buf, const __grid_constant__ LayoutArgs L,
+                                       const unsigned long long* __restrict__ idx, unsigned long long count,
+                                       double* __restrict__ re, double* __restrict__ im)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long mask = (L.M >= 64) ? ~0ull : ((1ull << L.M) - 1ull);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    {
+        const unsigned long long p = to_phys(idx[i], L);
+        const bool mine = (p >> L.M) == (unsigned long long)L.rank;
+        const double2 v = mine ? buf[p & mask] : make_double2(0.0, 0.0);
+        re[i] = v.x;
+        im[i] = L.conj ? -v.y : v.y;
+    }
+}
+void launch_gather_elements(const double2* buf, const LayoutArgs& L, const unsigned long long* idx, unsigned long long count,
+                            double* re, double* im, cudaStream_t s)
+{
+    const unsigned grid = (unsigned)min((unsigned long long)148 * 16, (count + 255) / 256);
+    gather_elements_kernel<<<grid, 256, 0, s>>>(buf, L, idx, count, re, im);
+}
+
 __global__ void scatter_split_kernel(double2* __restrict__ buf, const __grid_constant__ LayoutArgs L,
                                      unsigned long long first, unsigned long long count, const double* __restrict__ re,
                                      const double* __restrict__ im)

@@ -30,6 +30,8 @@ void launch_sample(const double* scan, size_t dim, const double* r, size_t n, un
 // logical [first, first+count) of the flat col*dim+row index -> split real / imag staging
 void launch_gather_split(const double2* buf, const LayoutArgs& L, unsigned long long first, unsigned long long count,
                          double* re, double* im, cudaStream_t s);
+void launch_gather_elements(const double2* buf, const LayoutArgs& L, const unsigned long long* idx, unsigned long long count,
+                            double* re, double* im, cudaStream_t s);
 void launch_scatter_split(double2* buf, const LayoutArgs& L, unsigned long long first, unsigned long long count,
                           const double* re, const double* im, cudaStream_t s);
 } // namespace dmb

@@ -71,6 +71,7 @@ typedef struct dmb_stats
     uint64_t n_launches;   /* kernels launched by this run */
     uint64_t sweep_bytes;  /* algorithmic bytes of one sweep of the local shard = 32 * 4^n / P */
     uint64_t exchange_bytes; /* bytes sent per rank over NVLink by this run */
+    uint64_t h2d_bytes;    /* device op tables copied host -> device by the dmb_set_circuit this run executes */
 } dmb_stats;
 
 typedef struct dmb_sim* dmb_handle;
@@ -101,6 +102,9 @@ int dmb_run(dmb_handle h, dmb_stats* stats);
 /* ---- results: replaces the D2H of dm_real_res / dm_imag_res (:458-466) and measure (:521-549) ---- */
 /* Full matrix into split host arrays (4^n doubles each, [col][row], holds rho^T).  world_size == 1. */
 int dmb_get_dm(dmb_handle h, double* real, double* imag);
+/* n arbitrary elements dm_real_res[f] / dm_imag_res[f], f = col*dim + row (spot checks of states too large to copy
+ * back).  With world_size > 1 elements owned by another rank come back as zero (sum over ranks = the values). */
+int dmb_get_elements(dmb_handle h, const uint64_t* flat_index, size_t n, double* real, double* imag);
 /* Real part of the diagonal (2^n doubles), dm_real_res[i*dim+i].  With world_size > 1 a rank fills the
  * entries it owns and zeroes the others (sum over ranks = full diagonal). */
 int dmb_get_diag(dmb_handle h, double* diag);

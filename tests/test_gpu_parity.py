@@ -300,3 +300,58 @@ def test_pybind_module_runs_a_generated_script(dm, tmp_path):
     r = subprocess.run([sys.executable, str(out), "4", "1"], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "RESULT [13, 13, 13, 13, 13, 13, 13, 13, 13, 13]" in r.stdout  # |1101> : q0, q2, q3 set
+
+
+# ---- BASELINE.json's full size: 15 qubits, 16 GiB density matrix (the oracle would need 64 GiB and ~10 minutes) -------
+def _inverse(gates):
+    inv = []
+    for g in reversed(gates):
+        name = g[0]
+        if name in ("H", "X", "CX"):
+            inv.append(g)
+        elif name == "U1":
+            inv.append(("U1", g[1], 0.0, 0.0, -g[4]))
+        else:
+            raise ValueError(name)
+    return inv
+
+
+@pytest.mark.parametrize("family", ["qft", "bv"])
+def test_fullsize_n15_against_statevector(dm, family):
+    """qft_n15 / bv_n15 gate for gate (benchmark/*.qasm) on a non-trivial input: trace, purity, ALL 2^15 diagonal
+    probabilities and 2^16 random off-diagonal elements against rho^T built from a state-vector run of the same gates."""
+    import importlib
+    from helpers import statevector
+    circuits = importlib.import_module("dm-sim_b200.circuits")
+    n = 15
+    prefix = [("X", [q], 0.0, 0.0, 0.0) for q in (0, 3, 4, 9, 14)] if family == "qft" else []
+    gates = prefix + (circuits.qft(n) if family == "qft" else circuits.bv(n))
+    sim = run_gpu(dm, n, gates)
+    psi = statevector(n, gates)
+    assert abs(sim.trace() - 1.0) < TOL
+    assert abs(sim.purity() - 1.0) < 1e-11
+    assert np.abs(sim.diag() - np.abs(psi) ** 2).max() < TOL
+    rng = np.random.default_rng(15)
+    col = rng.integers(0, 1 << n, size=1 << 16, dtype=np.uint64)
+    row = rng.integers(0, 1 << n, size=1 << 16, dtype=np.uint64)
+    got = sim.elements((col << np.uint64(n)) | row)
+    want = psi[row.astype(np.int64)] * np.conj(psi[col.astype(np.int64)])  # res[col][row] = rho[row][col]
+    assert np.abs(got - want).max() < TOL
+    if family == "bv":  # hidden string all ones, ancilla left in |->: two outcomes with probability 1/2 each
+        d = sim.diag()
+        assert abs(d[(1 << 14) - 1] - 0.5) < TOL and abs(d[(1 << 15) - 1] - 0.5) < TOL
+
+
+def test_fullsize_n15_circuit_then_inverse_is_identity(dm):
+    """Round trip at full size: qft_n15 followed by its inverse returns |0..0><0..0| exactly (to 1e-12)."""
+    import importlib
+    circuits = importlib.import_module("dm-sim_b200.circuits")
+    n = 15
+    g = circuits.qft(n)
+    sim = run_gpu(dm, n, g + _inverse(g))
+    d = sim.diag()
+    assert abs(d[0] - 1.0) < TOL and np.abs(d[1:]).max() < TOL
+    assert abs(sim.purity() - 1.0) < 1e-11
+    rng = np.random.default_rng(16)
+    f = rng.integers(1, 1 << (2 * n), size=1 << 14, dtype=np.uint64)
+    assert np.abs(sim.elements(f)).max() < TOL
