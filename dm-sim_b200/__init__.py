@@ -82,6 +82,8 @@ def lib():
     L.dmb_measure.argtypes = [vp, ctypes.c_uint, sz, vp, ctypes.POINTER(ctypes.c_double)]
     L.dmb_comm_unique_id.argtypes = [vp]
     L.dmb_comm_init.argtypes = [vp, vp]
+    L.dmb_comm_export.argtypes = [vp, vp]
+    L.dmb_comm_import.argtypes = [vp, vp]
     L.dmb_get_shard.argtypes = [vp, vp, vp]
     L.dmb_plan_json.argtypes = [i32, i32, vp, sz, vp, sz, vp, i32, ctypes.c_char_p, sz]
     L.dmb_plan_json.restype = ctypes.c_int64
@@ -206,6 +208,16 @@ class Simulation:
         ident = np.frombuffer(obj[0], dtype=np.uint8).copy()
         _check(lib().dmb_comm_init(self._h, ident.ctypes.data))
         del torch
+        # peer-memory exchange (fused pack + all-to-all over NVLink); DMB_P2P=0 keeps the NCCL send/recv path
+        self.p2p = False
+        if os.environ.get("DMB_P2P", "1") != "0":
+            mine = np.zeros(128, dtype=np.uint8)
+            _check(lib().dmb_comm_export(self._h, mine.ctypes.data))
+            everyone = [None] * self.n_gpus
+            dist.all_gather_object(everyone, mine.tobytes())
+            blob = np.frombuffer(b"".join(everyone), dtype=np.uint8).copy()
+            _check(lib().dmb_comm_import(self._h, blob.ctypes.data))
+            self.p2p = True
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -71,6 +71,7 @@ struct Nccl
     int (*GroupEnd)() = nullptr;
     int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 Nccl g_nccl;
@@ -101,6 +102,7 @@ bool load_nccl(std::string& why)
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(Send, "ncclSend");
     SYM(Recv, "ncclRecv");
+    SYM(AllReduce, "ncclAllReduce");
     SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
     return true;
@@ -153,6 +155,10 @@ struct dmb_sim
     size_t d_scratch_bytes = 0;
 
     ncclComm_t comm = nullptr;
+    // peer-memory exchange: IPC-mapped shard buffers of every rank (peer[b][r] = rank r's buf[b]); see dmb_comm_import
+    bool p2p = false;
+    double2* peer[2][8] = {{nullptr}};
+    double* d_barrier = nullptr; // 2 doubles: all-reduce source / sink used as the cross-GPU barrier
 };
 
 static LayoutArgs layout_args(const dmb_sim* s)
@@ -250,6 +256,11 @@ int dmb_destroy(dmb_handle s)
     cudaSetDevice(s->device);
     drop_graph(s);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+    if (s->p2p)
+        for (int b = 0; b < 2; b++)
+            for (int r = 0; r < s->world; r++)
+                if (r != s->rank && s->peer[b][r]) cudaIpcCloseMemHandle(s->peer[b][r]);
+    if (s->d_barrier) cudaFree(s->d_barrier);
     for (auto ev : s->ev_comm) cudaEventDestroy(ev);
     if (s->ev_begin) cudaEventDestroy(s->ev_begin);
     if (s->ev_end) cudaEventDestroy(s->ev_end);
@@ -454,6 +465,7 @@ static void fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, do
     a.stars = s->d_stars + s->star_offset[step];
     a.n_stars = s->n_dev_stars[step];
     a.rank_bits = (unsigned long long)s->rank << s->M;
+    a.peer_shift = -1;
     a.n_rounds = s->n_dev_rounds[step];
     a.n_groups = s->n_dev_groups[step];
     a.op_mask = s->op_masks[step];
@@ -466,6 +478,38 @@ static int enqueue_steps(dmb_sim* s, int& cur, uint64_t& launches, bool allow_ex
     for (size_t i = 0; i < s->plan.steps.size(); i++)
     {
         const Step& st = s->plan.steps[i];
+        // qubit remap with peer memory: the permuting sweep stores straight into the destination ranks' shards (one
+        // kernel = pack + all-to-all over NVLink), followed by a one-element all-reduce as the cross-GPU barrier
+        const bool fused = st.kind == 0 && st.sweep.out_of_place && s->p2p && allow_exchange && i + 1 < s->plan.steps.size() &&
+                           s->plan.steps[i + 1].kind == 1;
+        if (fused)
+        {
+            if (s->ev_comm.size() < 2 * (comm_idx + 1))
+            {
+                cudaEvent_t a_, b_;
+                CU(cudaEventCreate(&a_));
+                CU(cudaEventCreate(&b_));
+                s->ev_comm.push_back(a_);
+                s->ev_comm.push_back(b_);
+            }
+            CU(cudaEventRecord(s->ev_comm[2 * comm_idx], s->stream));
+            SweepArgs a;
+            fill_sweep_args(s, i, s->buf[cur], s->buf[cur ^ 1], a);
+            a.peer_shift = s->M - s->g;
+            a.peer_rank = s->rank;
+            for (int r = 0; r < s->world; r++) a.peer_out[r] = (unsigned long long)s->peer[cur ^ 1][r];
+            const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)sweep_max_grid(a));
+            launch_sweep(a, grid, s->stream);
+            CU(cudaGetLastError());
+            const int nr = g_nccl.AllReduce(s->d_barrier, s->d_barrier + 1, 1, kNcclDouble, 0 /* ncclSum */, s->comm, s->stream);
+            if (nr != 0) return fail(DMB_ECOMM, std::string("NCCL barrier failed: ") + g_nccl.GetErrorString(nr));
+            CU(cudaEventRecord(s->ev_comm[2 * comm_idx + 1], s->stream));
+            comm_idx++;
+            launches += 2;
+            cur ^= 1;
+            i++; // the exchange step is done
+            continue;
+        }
         if (st.kind == 0)
         {
             const Sweep& sw = st.sweep;
@@ -760,6 +804,52 @@ int dmb_comm_init(dmb_handle s, const uint8_t id[128])
     memcpy(u.internal, id, 128);
     int rc = g_nccl.CommInitRank(&s->comm, s->world, u, s->rank);
     if (rc) return fail(DMB_ECOMM, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc));
+    return DMB_OK;
+}
+
+int dmb_comm_export(dmb_handle s, uint8_t out[128])
+{
+    if (!s || !out) return fail(DMB_EINVAL, "null argument");
+    CU(cudaSetDevice(s->device));
+    int rc = ensure_second_buffer(s);
+    if (rc) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    for (int b = 0; b < 2; b++)
+    {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, s->buf[b]));
+        memcpy(out + 64 * b, &h, 64);
+    }
+    return DMB_OK;
+}
+
+int dmb_comm_import(dmb_handle s, const uint8_t* all_handles)
+{
+    if (!s || !all_handles) return fail(DMB_EINVAL, "null argument");
+    if (s->world > 8) return fail(DMB_EINVAL, "peer-memory exchange supports up to 8 ranks (one NVSwitch node)");
+    if (!s->comm) return fail(DMB_ESTATE, "dmb_comm_import needs dmb_comm_init first (the barrier runs on the communicator)");
+    CU(cudaSetDevice(s->device));
+    for (int r = 0; r < s->world; r++)
+        for (int b = 0; b < 2; b++)
+        {
+            if (r == s->rank) { s->peer[b][r] = s->buf[b]; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all_handles + 128 * (size_t)r + 64 * b, 64);
+            void* ptr = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess)
+            {
+                cudaGetLastError();
+                return fail(DMB_ECOMM, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+            }
+            s->peer[b][r] = reinterpret_cast<double2*>(ptr);
+        }
+    if (!s->d_barrier)
+    {
+        CU(cudaMalloc(&s->d_barrier, 2 * sizeof(double)));
+        CU(cudaMemset(s->d_barrier, 0, 2 * sizeof(double)));
+    }
+    s->p2p = true;
     return DMB_OK;
 }
 

@@ -40,6 +40,9 @@ enum RegOpCode : int32_t
     RC_DENSE1_RR = 8, // 2x2 with four REAL entries [[d0,d1],[d2,d3]] (H, RY, ...), |d0| not small, in the pivoted in-place
                       // form m[0..3] = {d0, d1, d2/d0, det/d0}: half the FP64 work of RC_DENSE1 and no register copies
     RC_DENSE1_RI = 9, // [[d0, i d1], [i d2, d3]] with real d (RX, W, ...), same form with det = d0 d3 + d1 d2
+    RC_HAD = 11,      // unscaled butterfly [[1, 1], [1, -1]] (a' = a + b, b' = a' - 2 b: 2 FP64 instructions per pair and
+                      // component, in place, no payload); the 1/sqrt(2) factors of the H gates of a round are folded by
+                      // the encoder into the payload of a later op of the same round (scalars commute with everything)
     RC_STAR = 10      // controlled-phase star: for every register bit p in aux bits 0..3, the elements with that bit set
                       // are multiplied by  L_p[lane] * WO_p[warp, iteration]  (DevStar slot star[p]): the product of the
                       // phases of all controlled-phase ops between register bit p and the partner bits that are set in
@@ -136,6 +139,11 @@ struct SweepArgs
     const DevStar* stars;
     int ops_bytes, n_rounds, n_groups, n_stars;
     unsigned long long rank_bits; // rank << M: the index bits above the shard
+    // fused qubit-remap exchange (peer_shift >= 0): the store phase writes element `off` of the OUTPUT frame straight
+    // into the shard of rank p = off >> peer_shift, at (my rank << peer_shift) | (off & low mask), over NVLink
+    int peer_shift;
+    int peer_rank;
+    unsigned long long peer_out[8]; // double2* of every rank's destination buffer (IPC-mapped; own pointer for self)
     unsigned op_mask;           // bit c set <=> some op of the sweep has RegOpCode c (selects the kernel instantiation)
     int k;                      // tile bits
     int n_comp;                 // M - k

@@ -263,6 +263,44 @@ std::vector<RoundPlan> plan_rounds(const Sweep& sw, int R)
     return rounds;
 }
 
+// H gates of a round: every s*[[1,1],[1,-1]] that is followed (in the same round) by an op with a numeric payload becomes
+// the payload-free butterfly RC_HAD and its scale s multiplies that later payload (a scalar commutes with everything).
+// ops[first..] = the round's device ops; RC_DENSE1_RR payload = {d0, d1, d2/d0, det/d0}.
+void fold_hadamard_scales(std::vector<DevOp>& ops, size_t first)
+{
+    auto scalable = [](const DevOp& d) {
+        switch (d.code)
+        {
+        case RC_DENSE1: case RC_DENSE2: case RC_DIAGR: case RC_DENSE1_RR: case RC_DENSE1_RI: return true;
+        default: return false;
+        }
+    };
+    auto scale_payload = [](DevOp& d, double f) {
+        switch (d.code)
+        {
+        case RC_DENSE1: for (int i = 0; i < 8; i++) d.m[i] *= f; break;
+        case RC_DENSE2: for (int i = 0; i < 32; i++) d.m[i] *= f; break;
+        case RC_DIAGR: for (int i = 0; i < 32; i++) d.m[i] *= f; d.aux = 0; break; // no entry is exactly 1 any more
+        case RC_DENSE1_RR: case RC_DENSE1_RI: d.m[0] *= f; d.m[1] *= f; d.m[3] *= f; break; // d2/d0 is scale free
+        default: break;
+        }
+    };
+    for (size_t i = first; i < ops.size(); i++)
+    {
+        DevOp& d = ops[i];
+        if (d.code != RC_DENSE1_RR) continue;
+        // s*[[1,1],[1,-1]] in pivoted form: {s, s, 1, -2 s}
+        const double sc = d.m[0];
+        if (!(d.m[1] == sc && d.m[2] == 1.0 && d.m[3] == -2.0 * sc) || sc == 0.0) continue;
+        size_t j = i + 1;
+        while (j < ops.size() && !scalable(ops[j])) j++;
+        if (j == ops.size()) continue; // nobody to carry the scale: stays a scaled real 2x2
+        scale_payload(ops[j], sc);
+        d.code = RC_HAD;
+        memset(d.m, 0, sizeof(d.m));
+    }
+}
+
 // a run of consecutive diagonal-type ops of a round (they all commute): one 16-entry diagonal over the register bits
 // plus, per register bit, the controlled phases whose other bit is NOT a register bit of this round
 struct StarPartner
@@ -496,6 +534,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                 out.ops.push_back(d);
             }
             flush_run();
+            fold_hadamard_scales(out.ops, (size_t)rd_first);
             out.rounds.back().count = (int32_t)out.ops.size() - rd_first;
         }
         g.count = (int32_t)out.rounds.size() - g.first;

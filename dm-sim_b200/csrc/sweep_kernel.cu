@@ -91,6 +91,22 @@ __device__ __forceinline__ void r_dense1_rr(double2 (&v)[E], Op op)
             b.y = fma(e2, a.y, e3 * b.y);
         }
 }
+// unscaled Hadamard butterfly, in place (the scale lives in another op of the round, see RC_HAD)
+template <int P>
+__device__ __forceinline__ void r_had(double2 (&v)[E])
+{
+#pragma unroll
+    for (int q = 0; q < E; q++)
+        if (!(q & (1 << P)))
+        {
+            double2& a = v[q];
+            double2& b = v[q | (1 << P)];
+            a.x = a.x + b.x;
+            a.y = a.y + b.y;
+            b.x = fma(-2.0, b.x, a.x);
+            b.y = fma(-2.0, b.y, a.y);
+        }
+}
 // [[d0, i d1], [i d2, d3]] with real d, same in-place form: a' = d0 a + i d1 b;  b' = i (d2/d0) a' + (det/d0) b with
 // det = d0 d3 + d1 d2.  e = {d0, d1, d2/d0, det/d0}
 template <int P>
@@ -275,6 +291,7 @@ __device__ __forceinline__ void apply_reg_op(double2 (&v)[E], Op op, int vid, co
         DMB_CASE1(RC_DENSE1_RI, r_dense1_ri, v, op)
         DMB_CASE1(RC_MONO1, r_mono1, v, op)
         DMB_CASE1(RC_SRN1, r_srn1, v)
+        DMB_CASE1(RC_HAD, r_had, v)
     case RC_DIAGR * 8: if (DMB_HAS(RC_DIAGR)) r_diagr(v, op); break;
     case RC_STAR * 8: if (DMB_HAS(RC_STAR)) r_star(v, op, sc); break;
     default: break;
@@ -428,10 +445,26 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
         // ---- store (streaming, evict-first) ----
         if (t_active)
         {
-            double2* dst = gout + (base_out | g_out_lo);
+            if (a.peer_shift < 0)
+            {
+                double2* dst = gout + (base_out | g_out_lo);
 #pragma unroll
-            for (int it = 0; it < kMaxIter; it++)
-                if (it < n_it) st_stream(dst + a.hout[it], tile[s_out_lo ^ a.hs[it]]);
+                for (int it = 0; it < kMaxIter; it++)
+                    if (it < n_it) st_stream(dst + a.hout[it], tile[s_out_lo ^ a.hs[it]]);
+            }
+            else
+            {
+                // fused remap: every 128-byte run goes straight into its destination rank's shard (peer memory)
+                const unsigned long long o_lo = base_out | g_out_lo;
+                const unsigned long long low_mask = (1ull << a.peer_shift) - 1ull;
+                const unsigned long long mine = (unsigned long long)a.peer_rank << a.peer_shift;
+                for (int it = 0; it < n_it; it++)
+                {
+                    const unsigned long long off = o_lo | a.hout[it];
+                    double2* dst = reinterpret_cast<double2*>(a.peer_out[off >> a.peer_shift]) + (mine | (off & low_mask));
+                    st_stream(dst, tile[s_out_lo ^ a.hs[it]]);
+                }
+            }
         }
         __syncthreads(); // every thread is done with the tile before the next load overwrites it
     }
@@ -444,13 +477,13 @@ static int g_num_sms = 0;
 constexpr unsigned kVariantMasks[] = {
     0u,                                                                              // pure data movement (remap pack)
     BIT(RC_DENSE2),                                                                  // random C2 blocks
-    BIT(RC_DIAGR) | BIT(RC_DENSE1_RR),                                               // H + diagonal
-    BIT(RC_DIAGR) | BIT(RC_DENSE1_RR) | BIT(RC_STAR),                                // QFT-like
-    BIT(RC_DENSE1_RR) | BIT(RC_PERM2),                                               // H / CX
-    BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_DENSE1_RI),         // dense 1- and 2-qubit blocks
-    BIT(RC_DIAGR) | BIT(RC_DENSE1_RR) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1),               // Clifford+T style
-    BIT(RC_DIAGR) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) | BIT(RC_STAR), // no dense 4x4
-    BIT(RC_DIAGR) | BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) |
+    BIT(RC_DIAGR) | BIT(RC_DENSE1_RR) | BIT(RC_HAD),                                               // H + diagonal
+    BIT(RC_DIAGR) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_STAR),                                // QFT-like
+    BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_PERM2),                                               // H / CX
+    BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI),         // dense 1- and 2-qubit blocks
+    BIT(RC_DIAGR) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1),               // Clifford+T style
+    BIT(RC_DIAGR) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) | BIT(RC_STAR), // no dense 4x4
+    BIT(RC_DIAGR) | BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) |
         BIT(RC_SRN1) | BIT(RC_STAR),                                                 // everything
 };
 constexpr int kNumVariants = sizeof(kVariantMasks) / sizeof(kVariantMasks[0]);

@@ -124,6 +124,13 @@ int dmb_measure(dmb_handle h, unsigned seed, size_t repetition, uint64_t* out, d
  * (libnccl.so.2), so single-GPU users need no NCCL at all. */
 int dmb_comm_unique_id(uint8_t id[128]);
 int dmb_comm_init(dmb_handle h, const uint8_t id[128]);
+/* Optional, ranks of ONE node (NVLink / NVSwitch): peer-memory exchange.  Every rank exports the IPC handles of its two
+ * shard buffers (2 x 64 bytes), the host plumbing all-gathers them (world_size x 128 bytes, rank order) and every rank
+ * imports the lot after dmb_comm_init.  From then on a qubit remap is ONE kernel: the permuting sweep stores straight
+ * into the destination ranks' shards over NVLink (pack + all-to-all fused), followed by a one-element all-reduce as
+ * the cross-GPU barrier.  Without it the remap is pack sweep + ncclSend/ncclRecv. */
+int dmb_comm_export(dmb_handle h, uint8_t out[128]);
+int dmb_comm_import(dmb_handle h, const uint8_t* all_handles);
 /* Raw shard + layout, for tests and host-side gathers: copies the local shard (interleaved complex,
  * 2 * 4^n / world_size doubles, PHYSICAL order) and the logical->physical bit map (2n ints). */
 int dmb_get_shard(dmb_handle h, double* interleaved, int32_t* phys_of_logical);

@@ -69,7 +69,8 @@ def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = No
     return out
 
 
-RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE2, RC_DIAG2, RC_PERM2, RC_DIAGR, RC_DENSE1_RR, RC_DENSE1_RI, RC_STAR = range(11)
+(RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE2, RC_DIAG2, RC_PERM2, RC_DIAGR, RC_DENSE1_RR, RC_DENSE1_RI, RC_STAR,
+ RC_HAD) = range(12)
 _POS2 = {0: (1, 0), 1: (2, 0), 2: (2, 1), 3: (3, 0), 4: (3, 1), 5: (3, 2)}
 _PERMS = {0: [0, 1, 3, 2], 1: [0, 3, 2, 1], 2: [0, 2, 1, 3]}
 
@@ -136,7 +137,7 @@ def _apply_reg_op(op, v):
             if not (aux >> c) & 1:
                 v[c] = m[c] * v[c]
         return
-    if code in (RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE1_RR, RC_DENSE1_RI):
+    if code in (RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE1_RR, RC_DENSE1_RI, RC_HAD):
         b = 1 << pos
         d = op["m"]
         for q in range(E):
@@ -145,6 +146,9 @@ def _apply_reg_op(op, v):
             a0, a1 = v[q].copy(), v[q | b].copy()
             if code == RC_DENSE1:
                 v[q], v[q | b] = m[0] * a0 + m[1] * a1, m[2] * a0 + m[3] * a1
+            elif code == RC_HAD:  # unscaled butterfly; the scale sits in a later op of the round
+                v[q] = a0 + a1
+                v[q | b] = v[q] - 2.0 * a1
             elif code == RC_DENSE1_RR:  # pivoted in-place form {d0, d1, d2/d0, det/d0}
                 v[q] = d[0] * a0 + d[1] * a1
                 v[q | b] = d[2] * v[q] + d[3] * a1
