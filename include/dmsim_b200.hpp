@@ -34,8 +34,11 @@
 
 #include "dmsim_b200.h"
 
-#ifndef PRINT_MEA_PER_CIRCUIT
-#define PRINT_MEA_PER_CIRCUIT // reference src/config.hpp:25: print the per-sim() summary line
+// reference src/config.hpp:25: print the per-sim() summary line.  Define DMSIM_NO_PRINT_MEA before including this
+// header to silence it (what the XACC runners do with `#undef PRINT_MEA_PER_CIRCUIT`,
+// xacc/cpu_omp/dm_sim_omp_runner.cpp:2-4).
+#if !defined(PRINT_MEA_PER_CIRCUIT) && !defined(DMSIM_NO_PRINT_MEA)
+#define PRINT_MEA_PER_CIRCUIT
 #endif
 
 namespace DMSim

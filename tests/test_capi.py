@@ -50,6 +50,25 @@ def test_cxx_dropin_header_builds_against_the_library(tmp_path):
     assert os.path.exists(exe)
 
 
+def test_xacc_plugin_abi_builds_against_the_library(tmp_path):
+    """include/DmSimApi.hpp (the reference's xacc/DmSimApi.hpp plugin ABI: DmSimBackend + getGpuDmSim) compiles and
+    links; the enum mirrors DMSim::OP value for value (xacc/DmSimApi.hpp:6-45)."""
+    src = tmp_path / "abi.cpp"
+    src.write_text('#include "DmSimApi.hpp"\n'
+                   'static_assert((int)DmSim::OP::RYY == 37 && (int)DmSim::OP::CH == (int)DMSim::OP::CH && '
+                   '(int)DmSim::OP::C4X == (int)DMSim::OP::C4X, "enum order");\n'
+                   'int main(int argc, char**){ std::shared_ptr<DmSim::DmSimBackend> b = DmSim::getGpuDmSim(); '
+                   'if (argc > 99) { b->init(2); b->addGate(DmSim::OP::H, {0}); b->measure(1); b->finalize(); } return b ? 0 : 1; }\n')
+    lib = os.path.join(ROOT, "dm-sim_b200", "lib")
+    exe = tmp_path / "abi"
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", lib, "-ldmsim_b200", "-Wl,-rpath," + lib], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "xacc_backend.cpp"), "-o", str(tmp_path / "x"), "-L", lib, "-ldmsim_b200",
+                    "-Wl,-rpath," + lib], check=True)
+
+
 def test_no_silent_fallback_without_gpu(dm):
     import torch
     if torch.cuda.is_available():

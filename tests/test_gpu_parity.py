@@ -285,6 +285,21 @@ def test_cxx_dropin_example_runs(dm, tmp_path):
     assert r.stdout.count("1000000010") == 5 and "nqubits:10, ngates:30" in r.stdout
 
 
+def test_xacc_plugin_backend_runs(dm, tmp_path):
+    """examples/xacc_backend.cpp: the reference's XACC plugin ABI (xacc/DmSimApi.hpp:47-62) on the B200 backend, with the
+    checks of xacc/nvidia_omp/tests/DmSimAcceleratorTester.cpp (Bell 0.5/0.5, <Z> of an RX sweep within 0.05)."""
+    import subprocess
+    root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    lib = _os.path.join(root, "dm-sim_b200", "lib")
+    exe = tmp_path / "xacc"
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-I", _os.path.join(root, "include"),
+                    _os.path.join(root, "examples", "xacc_backend.cpp"), "-o", str(exe), "-L", lib, "-ldmsim_b200",
+                    "-Wl,-rpath," + lib], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
+    assert "DM-Sim" not in r.stdout  # the XACC runners silence the per-sim() summary line
+
+
 def test_pybind_module_runs_a_generated_script(dm, tmp_path):
     """tool/dmsim_qasm.py output executed with the drop-in pybind11 module, as the reference's workflow does."""
     import subprocess
