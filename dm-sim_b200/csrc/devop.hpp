@@ -43,6 +43,9 @@ enum RegOpCode : int32_t
     RC_HAD = 11,      // unscaled butterfly [[1, 1], [1, -1]] (a' = a + b, b' = a' - 2 b: 2 FP64 instructions per pair and
                       // component, in place, no payload); the 1/sqrt(2) factors of the H gates of a round are folded by
                       // the encoder into the payload of a later op of the same round (scalars commute with everything)
+    RC_DIAGP = 12,    // diagonal whose non-unit entries all have register bit `pos` set (phases controlled by that
+                      // bit, e.g. the controlled phases between the register bits of a QFT round): m[j] multiplies the
+                      // element whose other three register bits spell j; skip mask (unit entries) in aux bits 0..7
     RC_STAR = 10      // controlled-phase star: for every register bit p in aux bits 0..3, the elements with that bit set
                       // are multiplied by  L_p[lane] * WO_p[warp, iteration]  (DevStar slot star[p]): the product of the
                       // phases of all controlled-phase ops between register bit p and the partner bits that are set in
@@ -84,6 +87,7 @@ inline int dev_op_payload_bytes(int code)
     case RC_DENSE2: return 256;
     case RC_PERM2: return 64;
     case RC_DIAGR: return 256;
+    case RC_DIAGP: return 128;
     case RC_DENSE1_RR: return 32;
     case RC_DENSE1_RI: return 32;
     default: return 0;

@@ -80,6 +80,9 @@ DevOp make_reg_op(const TileOp& t, int p0, int p1)
                 d.code = RC_DENSE1_RR;
                 const double d0 = t.m[0].real(), d1 = t.m[1].real(), d2 = t.m[2].real(), d3 = t.m[3].real();
                 d.m[0] = d0; d.m[1] = d1; d.m[2] = d2 / d0; d.m[3] = (d0 * d3 - d1 * d2) / d0;
+                // s*[[1,1],[1,-1]]: det/d0 is -2s exactly (the rounded quotient can be an ulp off, which would hide
+                // the Hadamard form from fold_hadamard_scales)
+                if (d1 == d0 && d2 == d0 && d3 == -d0) { d.m[2] = 1.0; d.m[3] = -2.0 * d0; }
             }
             else if (ri && pivot_ok)
             {
@@ -263,65 +266,63 @@ std::vector<RoundPlan> plan_rounds(const Sweep& sw, int R)
     return rounds;
 }
 
-// H gates of a round: every s*[[1,1],[1,-1]] that is followed (in the same round) by an op with a numeric payload becomes
-// the payload-free butterfly RC_HAD and its scale s multiplies that later payload (a scalar commutes with everything).
-// ops[first..] = the round's device ops; RC_DENSE1_RR payload = {d0, d1, d2/d0, det/d0}.
-void fold_hadamard_scales(std::vector<DevOp>& ops, size_t first)
+// H gates of a sweep: s*[[1,1],[1,-1]] becomes the payload-free butterfly RC_HAD (2 FP64 instructions per pair and
+// component instead of 4) and its scale s moves into the payload of a DENSE op of the same sweep: a real scalar
+// commutes with every op (SRN included, it is real-linear), across rounds too.  Only dense payloads carry scales
+// (scaling a diagonal table would turn its skipped unit entries into multiplications); when the sweep has none, its
+// last H stays a scaled real 2x2 and carries the product.  RC_DENSE1_RR payload = {d0, d1, d2/d0, det/d0}.
+void fold_hadamard_scales(std::vector<DevOp>& ops)
 {
-    auto scalable = [](const DevOp& d) {
-        switch (d.code)
-        {
-        case RC_DENSE1: case RC_DENSE2: case RC_DIAGR: case RC_DENSE1_RR: case RC_DENSE1_RI: return true;
-        default: return false;
-        }
+    auto is_had = [](const DevOp& d) {
+        return d.code == RC_DENSE1_RR && d.m[0] != 0.0 && d.m[1] == d.m[0] && d.m[2] == 1.0 && d.m[3] == -2.0 * d.m[0];
     };
-    auto scale_payload = [](DevOp& d, double f) {
-        switch (d.code)
-        {
-        case RC_DENSE1: for (int i = 0; i < 8; i++) d.m[i] *= f; break;
-        case RC_DENSE2: for (int i = 0; i < 32; i++) d.m[i] *= f; break;
-        case RC_DIAGR: for (int i = 0; i < 32; i++) d.m[i] *= f; d.aux = 0; break; // no entry is exactly 1 any more
-        case RC_DENSE1_RR: case RC_DENSE1_RI: d.m[0] *= f; d.m[1] *= f; d.m[3] *= f; break; // d2/d0 is scale free
-        default: break;
-        }
-    };
-    for (size_t i = first; i < ops.size(); i++)
+    int carrier = -1;
+    for (int i = (int)ops.size() - 1; i >= 0 && carrier < 0; i--)
+    {
+        const int c = ops[i].code;
+        if ((c == RC_DENSE1 || c == RC_DENSE2 || c == RC_DENSE1_RI || c == RC_DENSE1_RR) && !is_had(ops[i])) carrier = i;
+    }
+    if (carrier < 0)
+        for (int i = (int)ops.size() - 1; i >= 0 && carrier < 0; i--)
+            if (is_had(ops[i])) carrier = i;
+    if (carrier < 0) return;
+    double f = 1.0;
+    for (int i = 0; i < (int)ops.size(); i++)
     {
         DevOp& d = ops[i];
-        if (d.code != RC_DENSE1_RR) continue;
-        // s*[[1,1],[1,-1]] in pivoted form: {s, s, 1, -2 s}
-        const double sc = d.m[0];
-        if (!(d.m[1] == sc && d.m[2] == 1.0 && d.m[3] == -2.0 * sc) || sc == 0.0) continue;
-        size_t j = i + 1;
-        while (j < ops.size() && !scalable(ops[j])) j++;
-        if (j == ops.size()) continue; // nobody to carry the scale: stays a scaled real 2x2
-        scale_payload(ops[j], sc);
+        if (i == carrier || !is_had(d)) continue;
+        f *= d.m[0];
         d.code = RC_HAD;
         memset(d.m, 0, sizeof(d.m));
     }
+    if (f == 1.0) return;
+    DevOp& d = ops[carrier];
+    switch (d.code)
+    {
+    case RC_DENSE1: for (int i = 0; i < 8; i++) d.m[i] *= f; break;
+    case RC_DENSE2: for (int i = 0; i < 32; i++) d.m[i] *= f; break;
+    default: d.m[0] *= f; d.m[1] *= f; d.m[3] *= f; break; // pivoted forms: d2/d0 is scale free
+    }
 }
 
-// a run of consecutive diagonal-type ops of a round (they all commute): one 16-entry diagonal over the register bits
-// plus, per register bit, the controlled phases whose other bit is NOT a register bit of this round
+// The diagonal-type ops of a round all commute with each other, and each commutes with every op that touches none
+// of its register bits.  They are therefore kept PENDING and only materialise when a non-diagonal op needs one of
+// their register bits (or at the end of the round): one device op for many circuit ops.
 struct StarPartner
 {
     bool tile;  // partner is a tile-local bit (lane / iteration / warp bit), else a physical bit outside the tile
     int bit;
     cplx phi;
 };
-struct DiagRun
+struct DiagFactor // diagonal over the round's register bits
 {
-    bool have_diag = false;
+    unsigned support; // register bits it depends on
     cplx e[kRegElems];
-    std::vector<StarPartner> star[kRegBits];
-    bool any_star = false;
-    void reset()
-    {
-        have_diag = false;
-        any_star = false;
-        for (auto& v : star) v.clear();
-        for (auto& x : e) x = cplx(1.0, 0.0);
-    }
+};
+struct Pending
+{
+    std::vector<DiagFactor> diag;
+    std::vector<StarPartner> star[kRegBits]; // controlled phases whose other bit is NOT a register bit of the round
 };
 } // namespace
 
@@ -413,27 +414,63 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                 const auto it = std::find(rb.begin(), rb.end(), j);
                 return it == rb.end() ? -1 : (int)(it - rb.begin());
             };
-            DiagRun run;
-            run.reset();
-            auto flush_run = [&]() {
-                if (run.have_diag)
+            Pending pend;
+            // materialise the pending diagonal factors / stars that involve a register bit of `need`
+            auto flush = [&](unsigned need) {
+                cplx e[kRegElems];
+                for (auto& x : e) x = cplx(1.0, 0.0);
+                bool have = false;
+                for (size_t i = 0; i < pend.diag.size();)
                 {
-                    DevOp nd;
-                    memset(&nd, 0, sizeof(nd));
-                    nd.code = RC_DIAGR;
+                    if (!(pend.diag[i].support & need)) { i++; continue; }
+                    for (int c = 0; c < kRegElems; c++) e[c] *= pend.diag[i].e[c];
+                    have = true;
+                    pend.diag.erase(pend.diag.begin() + (long)i);
+                }
+                if (have)
+                {
                     int skip = 0;
+                    unsigned common = (1u << kRegBits) - 1u; // register bits set in every non-unit entry
                     for (int c = 0; c < kRegElems; c++)
                     {
-                        cplx v = run.e[c];
                         // entries within 1e-15 of 1 (e.g. u1(a)*u1(-a) inside a fused controlled phase) are exactly 1
-                        if (std::abs(v.real() - 1.0) < 1e-15 && std::abs(v.imag()) < 1e-15) v = cplx(1.0, 0.0);
-                        put(nd, c, v);
-                        if (v == cplx(1.0, 0.0)) skip |= 1 << c;
+                        if (std::abs(e[c].real() - 1.0) < 1e-15 && std::abs(e[c].imag()) < 1e-15) e[c] = cplx(1.0, 0.0);
+                        if (e[c] == cplx(1.0, 0.0)) skip |= 1 << c;
+                        else common &= (unsigned)c;
                     }
-                    nd.aux = skip;
-                    if (skip != (1 << kRegElems) - 1) out.ops.push_back(nd);
+                    DevOp nd;
+                    memset(&nd, 0, sizeof(nd));
+                    if (skip == (1 << kRegElems) - 1) {}
+                    else if (common)
+                    {
+                        // every non-unit entry has register bit P set (phases controlled by P): an 8-entry table
+                        // over the other register bits, so that no instruction is spent on the unit half
+                        int P = 0;
+                        while (!((common >> P) & 1u)) P++;
+                        nd.code = RC_DIAGP;
+                        nd.pos = P;
+                        int skip8 = 0;
+                        for (int j = 0; j < kRegElems / 2; j++)
+                        {
+                            const int c = ((j >> P) << (P + 1)) | (1 << P) | (j & ((1 << P) - 1));
+                            put(nd, j, e[c]);
+                            if ((skip >> c) & 1) skip8 |= 1 << j;
+                        }
+                        nd.aux = skip8;
+                        out.ops.push_back(nd);
+                    }
+                    else
+                    {
+                        nd.code = RC_DIAGR;
+                        for (int c = 0; c < kRegElems; c++) put(nd, c, e[c]);
+                        nd.aux = skip;
+                        out.ops.push_back(nd);
+                    }
                 }
-                if (run.any_star)
+                bool any_star = false;
+                for (int p = 0; p < kRegBits; p++)
+                    if (((need >> p) & 1u) && !pend.star[p].empty()) any_star = true;
+                if (any_star)
                 {
                     DevOp sd;
                     memset(&sd, 0, sizeof(sd));
@@ -442,7 +479,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                     const int nib = (int)iterp.size();
                     for (int p = 0; p < kRegBits; p++)
                     {
-                        if (run.star[p].empty()) continue;
+                        if (!((need >> p) & 1u) || pend.star[p].empty()) continue;
                         sd.aux |= 1 << p;
                         DevStar st;
                         memset(&st, 0, sizeof(st));
@@ -451,7 +488,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                             const unsigned itv = (unsigned)iw & ((1u << nib) - 1u), wv = (unsigned)iw >> nib;
                             const unsigned idx = deposit(itv, iterp) | deposit(wv, wpos);
                             cplx acc(1.0, 0.0);
-                            for (const StarPartner& sp : run.star[p])
+                            for (const StarPartner& sp : pend.star[p])
                                 if (sp.tile && ((idx >> sp.bit) & 1u)) acc *= sp.phi;
                             st.w[2 * iw] = acc.real();
                             st.w[2 * iw + 1] = acc.imag();
@@ -461,27 +498,37 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                             const unsigned lane = l < 8 ? (unsigned)l : (unsigned)(l - 8) << 3;
                             const unsigned idx = deposit(lane & ((1u << nl) - 1u), lanep);
                             cplx acc(1.0, 0.0);
-                            for (const StarPartner& sp : run.star[p])
+                            for (const StarPartner& sp : pend.star[p])
                                 if (sp.tile && ((idx >> sp.bit) & 1u)) acc *= sp.phi;
                             double* dst = l < 8 ? st.la + 2 * l : st.lb + 2 * (l - 8);
                             dst[0] = acc.real();
                             dst[1] = acc.imag();
                         }
-                        for (const StarPartner& sp : run.star[p])
+                        // partners outside the tile: one entry per physical bit
+                        for (const StarPartner& sp : pend.star[p])
                             if (!sp.tile)
                             {
-                                if (st.n_out >= kMaxStarOut) throw std::logic_error("too many outside partners in a star");
-                                st.bit[st.n_out] = sp.bit;
-                                st.phi[2 * st.n_out] = sp.phi.real();
-                                st.phi[2 * st.n_out + 1] = sp.phi.imag();
-                                st.n_out++;
+                                int j = 0;
+                                while (j < st.n_out && st.bit[j] != sp.bit) j++;
+                                if (j == st.n_out)
+                                {
+                                    if (st.n_out >= kMaxStarOut) throw std::logic_error("too many outside partners in a star");
+                                    st.bit[j] = sp.bit;
+                                    st.phi[2 * j] = 1.0;
+                                    st.phi[2 * j + 1] = 0.0;
+                                    st.n_out++;
+                                }
+                                const cplx acc = cplx(st.phi[2 * j], st.phi[2 * j + 1]) * sp.phi;
+                                st.phi[2 * j] = acc.real();
+                                st.phi[2 * j + 1] = acc.imag();
                             }
                         out.stars.push_back(st);
+                        pend.star[p].clear();
                     }
                     out.ops.push_back(sd);
                 }
-                run.reset();
             };
+            const unsigned all_regs = (1u << kRegBits) - 1u;
 
             for (int o : rp.ops)
             {
@@ -492,9 +539,10 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                     const int p0 = reg_pos(t.j0), p1 = t.j1 >= 0 ? reg_pos(t.j1) : -1;
                     if (p0 >= 0 && p1 >= 0)
                     {
-                        for (int c = 0; c < kRegElems; c++)
-                            if (((c >> p0) & 1) && ((c >> p1) & 1)) run.e[c] *= phi;
-                        run.have_diag = true;
+                        DiagFactor f;
+                        f.support = (1u << p0) | (1u << p1);
+                        for (int c = 0; c < kRegElems; c++) f.e[c] = (((c >> p0) & 1) && ((c >> p1) & 1)) ? phi : cplx(1.0, 0.0);
+                        pend.diag.push_back(f);
                     }
                     else if (p0 >= 0 || p1 >= 0)
                     {
@@ -502,8 +550,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                         sp.phi = phi;
                         if (p0 >= 0) { sp.tile = t.j1 >= 0; sp.bit = t.j1 >= 0 ? t.j1 : t.p1; }
                         else { sp.tile = true; sp.bit = t.j0; }
-                        run.star[p0 >= 0 ? p0 : p1].push_back(sp);
-                        run.any_star = true;
+                        pend.star[p0 >= 0 ? p0 : p1].push_back(sp);
                     }
                     else
                         throw std::logic_error("controlled phase without a register bit in its round");
@@ -514,27 +561,27 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                 DevOp d = make_reg_op(t, p0, p1);
                 if (d.code == RC_DIAG1 || d.code == RC_DIAG2)
                 {
-                    // every diagonal op becomes a 16-entry diagonal over the round's register bits, and the ones of
-                    // a run are multiplied together on the host: one device op, no position dispatch
+                    // every diagonal op becomes a 16-entry diagonal over the round's register bits; the pending
+                    // ones are multiplied together on the host: one device op, no position dispatch
+                    static const int hi[6] = {1, 2, 2, 3, 3, 3}, lo[6] = {0, 0, 1, 0, 1, 2};
+                    DiagFactor f;
+                    f.support = d.code == RC_DIAG1 ? (1u << d.pos) : ((1u << hi[d.pos]) | (1u << lo[d.pos]));
                     for (int c = 0; c < kRegElems; c++)
                     {
-                        int idx;
-                        if (d.code == RC_DIAG1) idx = (c >> d.pos) & 1;
-                        else
-                        {
-                            static const int hi[6] = {1, 2, 2, 3, 3, 3}, lo[6] = {0, 0, 1, 0, 1, 2};
-                            idx = 2 * ((c >> hi[d.pos]) & 1) + ((c >> lo[d.pos]) & 1);
-                        }
-                        run.e[c] *= cplx(d.m[2 * idx], d.m[2 * idx + 1]);
+                        const int idx = d.code == RC_DIAG1 ? ((c >> d.pos) & 1) : 2 * ((c >> hi[d.pos]) & 1) + ((c >> lo[d.pos]) & 1);
+                        f.e[c] = cplx(d.m[2 * idx], d.m[2 * idx + 1]);
                     }
-                    run.have_diag = true;
+                    pend.diag.push_back(f);
                     continue;
                 }
-                flush_run();
+                // SRN is real-linear only: it does not commute with complex factors on OTHER bits, so everything
+                // pending is materialised before it
+                unsigned need = all_regs;
+                if (d.code != RC_SRN1) need = t.nb == 2 ? ((1u << p0) | (1u << p1)) : (1u << p0);
+                flush(need);
                 out.ops.push_back(d);
             }
-            flush_run();
-            fold_hadamard_scales(out.ops, (size_t)rd_first);
+            flush(all_regs);
             out.rounds.back().count = (int32_t)out.ops.size() - rd_first;
         }
         g.count = (int32_t)out.rounds.size() - g.first;
@@ -542,6 +589,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
         first = end;
     }
     if ((int)out.stars.size() > kMaxStarsPerSweep) throw std::logic_error("too many controlled-phase stars in one sweep");
+    fold_hadamard_scales(out.ops);
 
     // ---- the device op stream: 16-byte header + the used part of the payload per op, a zero header at the end ----
     std::vector<int> offset16(out.ops.size() + 1, 0);

@@ -50,12 +50,14 @@ __device__ __forceinline__ void st_stream(double2* p, double2 v)
 // ------------------------------------------------------------------------------------------------
 constexpr int E = kRegElems;
 // an op in the shared-memory op stream: DevOpHdr (16 bytes) + payload
+// (the header travels in registers: it was fetched while the previous op ran)
 struct Op
 {
     const unsigned char* p;
-    __device__ __forceinline__ const DevOpHdr* hdr() const { return reinterpret_cast<const DevOpHdr*>(p); }
+    int aux_, star_;
     __device__ __forceinline__ const double* m() const { return reinterpret_cast<const double*>(p + 16); }
-    __device__ __forceinline__ int aux() const { return hdr()->aux; }
+    __device__ __forceinline__ int aux() const { return aux_; }
+    __device__ __forceinline__ int star() const { return star_; }
 };
 __device__ __forceinline__ const double2* op_m(Op op) { return reinterpret_cast<const double2*>(op.p + 16); }
 
@@ -236,6 +238,18 @@ __device__ __forceinline__ void r_diagr(double2 (&v)[E], Op op)
     for (int c = 0; c < E; c++)
         if (!((skip >> c) & 1)) v[c] = cmul(op_m(op)[c], v[c]);
 }
+// diagonal whose non-unit entries all have register bit P set: 8 entries over the other three register bits
+template <int P>
+__device__ __forceinline__ void r_diagp(double2 (&v)[E], Op op)
+{
+    const int skip = op.aux();
+#pragma unroll
+    for (int j = 0; j < E / 2; j++)
+    {
+        const int c = ((j >> P) << (P + 1)) | (1 << P) | (j & ((1 << P) - 1));
+        if (!((skip >> j) & 1)) v[c] = cmul(op_m(op)[j], v[c]);
+    }
+}
 
 // controlled-phase star: the elements whose register bit p is set get the phase  L_p[lane] * WO_p[iw]
 struct StarCtx
@@ -247,7 +261,7 @@ constexpr int kStarEntries = kStarSmemBytes / 16;
 __device__ __forceinline__ void r_star(double2 (&v)[E], Op op, const StarCtx& sc)
 {
     const int mask = op.aux() & 15;
-    int slot = op.hdr()->star[0];
+    int slot = op.star();
 #pragma unroll
     for (int p = 0; p < kRegBits; p++)
         if ((mask >> p) & 1)
@@ -292,6 +306,7 @@ __device__ __forceinline__ void apply_reg_op(double2 (&v)[E], Op op, int vid, co
         DMB_CASE1(RC_MONO1, r_mono1, v, op)
         DMB_CASE1(RC_SRN1, r_srn1, v)
         DMB_CASE1(RC_HAD, r_had, v)
+        DMB_CASE1(RC_DIAGP, r_diagp, v, op)
     case RC_DIAGR * 8: if (DMB_HAS(RC_DIAGR)) r_diagr(v, op); break;
     case RC_STAR * 8: if (DMB_HAS(RC_STAR)) r_star(v, op, sc); break;
     default: break;
@@ -422,15 +437,17 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
 #pragma unroll
                             for (int c = 0; c < E; c++) v[c] = tile[base ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)];
                             const StarCtx sc = {s_star, lane, (warp << nib) | it};
-                            Op op = {ops};
-                            int vid = op.hdr()->vid; // (a zero header follows the last op of the stream)
+                            // op headers {vid, aux, size16, star} are carried in registers: the next one is fetched
+                            // while the current op runs (a zero header follows the last op of the stream)
+                            const unsigned char* p = ops;
+                            int4 h = *reinterpret_cast<const int4*>(p);
                             for (int o = 0; o < n_ops; o++)
                             {
-                                const Op nxt = {op.p + op.hdr()->size16 * 16};
-                                const int next = nxt.hdr()->vid; // fetched while this op runs
+                                const Op op = {p, h.y, h.w};
+                                const int vid = h.x;
+                                p += h.z * 16;
+                                h = *reinterpret_cast<const int4*>(p);
                                 apply_reg_op<MASK>(v, op, vid, sc);
-                                op = nxt;
-                                vid = next;
                             }
 #pragma unroll
                             for (int c = 0; c < E; c++) tile[base ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)] = v[c];
@@ -477,13 +494,13 @@ static int g_num_sms = 0;
 constexpr unsigned kVariantMasks[] = {
     0u,                                                                              // pure data movement (remap pack)
     BIT(RC_DENSE2),                                                                  // random C2 blocks
-    BIT(RC_DIAGR) | BIT(RC_DENSE1_RR) | BIT(RC_HAD),                                               // H + diagonal
-    BIT(RC_DIAGR) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_STAR),                                // QFT-like
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_DENSE1_RR) | BIT(RC_HAD),                                               // H + diagonal
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_STAR),                                // QFT-like
     BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_PERM2),                                               // H / CX
     BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI),         // dense 1- and 2-qubit blocks
-    BIT(RC_DIAGR) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1),               // Clifford+T style
-    BIT(RC_DIAGR) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) | BIT(RC_STAR), // no dense 4x4
-    BIT(RC_DIAGR) | BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) |
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1),               // Clifford+T style
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) | BIT(RC_STAR), // no dense 4x4
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) |
         BIT(RC_SRN1) | BIT(RC_STAR),                                                 // everything
 };
 constexpr int kNumVariants = sizeof(kVariantMasks) / sizeof(kVariantMasks[0]);

@@ -70,7 +70,7 @@ def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = No
 
 
 (RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE2, RC_DIAG2, RC_PERM2, RC_DIAGR, RC_DENSE1_RR, RC_DENSE1_RI, RC_STAR,
- RC_HAD) = range(12)
+ RC_HAD, RC_DIAGP) = range(13)
 _POS2 = {0: (1, 0), 1: (2, 0), 2: (2, 1), 3: (3, 0), 4: (3, 1), 5: (3, 2)}
 _PERMS = {0: [0, 1, 3, 2], 1: [0, 3, 2, 1], 2: [0, 2, 1, 3]}
 
@@ -136,6 +136,12 @@ def _apply_reg_op(op, v):
         for c in range(E):
             if not (aux >> c) & 1:
                 v[c] = m[c] * v[c]
+        return
+    if code == RC_DIAGP:  # 8 entries over the other three register bits, for the elements with register bit `pos` set
+        for j in range(E // 2):
+            c = ((j >> pos) << (pos + 1)) | (1 << pos) | (j & ((1 << pos) - 1))
+            if not (aux >> j) & 1:
+                v[c] = m[j] * v[c]
         return
     if code in (RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE1_RR, RC_DENSE1_RI, RC_HAD):
         b = 1 << pos
