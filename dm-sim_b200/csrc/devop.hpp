@@ -46,6 +46,8 @@ enum RegOpCode : int32_t
     RC_DIAGP = 12,    // diagonal whose non-unit entries all have register bit `pos` set (phases controlled by that
                       // bit, e.g. the controlled phases between the register bits of a QFT round): m[j] multiplies the
                       // element whose other three register bits spell j; skip mask (unit entries) in aux bits 0..7
+    RC_CP2 = 13,      // one controlled phase between two register bits: the 4 elements with both bits set are multiplied
+                      // by m[0]; `pos` as for the other two-bit ops
     RC_STAR = 10      // controlled-phase star: for every register bit p in aux bits 0..3, the elements with that bit set
                       // are multiplied by  L_p[lane] * WO_p[warp, iteration]  (DevStar slot star[p]): the product of the
                       // phases of all controlled-phase ops between register bit p and the partner bits that are set in
@@ -78,7 +80,7 @@ struct alignas(16) DevOpHdr
     int32_t size16; // header + payload in 16-byte units
     int32_t star[1]; // RC_STAR: star[0] = first DevStar slot of this op (one per set aux bit, ascending)
 };
-inline int dev_op_payload_bytes(int code)
+constexpr int dev_op_payload_bytes(int code)
 {
     switch (code)
     {
@@ -88,6 +90,7 @@ inline int dev_op_payload_bytes(int code)
     case RC_PERM2: return 64;
     case RC_DIAGR: return 256;
     case RC_DIAGP: return 128;
+    case RC_CP2: return 16;
     case RC_DENSE1_RR: return 32;
     case RC_DENSE1_RI: return 32;
     default: return 0;
@@ -109,6 +112,7 @@ static_assert(sizeof(DevOp) == 272, "DevOp layout");
 // A round: the lane loads the 2^kRegBits elements  base ^ roff[c]  (base = lane_tab[lane] ^ iter_tab[iter] ^
 // wtab[warp], everything pre-swizzled), applies ops [first, first+count) in registers and stores them back:
 // ONE shared-memory round trip for `count` ops.
+constexpr int kMaxOpsPerRound = 16; // the encoder splits longer rounds (same tables, one more shared-memory round trip)
 struct alignas(16) DevRound
 {
     int32_t first, count; // first: offset of the round's first op in the op stream, in 16-byte units
@@ -117,8 +121,11 @@ struct alignas(16) DevRound
     uint16_t lane_tab[32];
     uint16_t iter_tab[8];
     uint16_t roff[16];
+    uint8_t vids[kMaxOpsPerRound]; // DevOpHdr::vid of the round's ops: the kernel dispatches from this packed list (in
+                                   // registers) and every op body advances the stream pointer by its static size, so
+                                   // that no shared-memory load sits on the dispatch path
 };
-static_assert(sizeof(DevRound) == 128, "DevRound layout");
+static_assert(sizeof(DevRound) == 144, "DevRound layout");
 
 // A run of consecutive rounds that leave kWarpBits tile bits untouched: warp w owns the sub-tile where those bits
 // equal w and runs the whole group with __syncwarp() only; CTA barriers happen between groups.
@@ -152,7 +159,7 @@ struct SweepArgs
     int k;                      // tile bits
     int n_comp;                 // M - k
     unsigned long long n_tiles; // 2^(M-k)
-    unsigned long long hin[kMaxIter];  // element offset contributed by iteration `it` when loading
+    unsigned long long hin[kMaxIter];  // BYTE offset contributed by iteration `it` when loading
     unsigned long long hout[kMaxIter]; // ... when storing
     unsigned short hs[kMaxIter];       // swizzled smem index contributed by iteration `it` when storing
     unsigned char gin[12];       // physical bit of loop bit i (< kThreadBits) when loading

@@ -440,7 +440,26 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                     }
                     DevOp nd;
                     memset(&nd, 0, sizeof(nd));
+                    // one controlled phase between two register bits: exactly the 4 entries with both bits set, equal
+                    int cp_hi = -1, cp_lo = -1;
+                    if (__builtin_popcount(common) == 2)
+                    {
+                        cp_lo = __builtin_ctz(common);
+                        cp_hi = 31 - __builtin_clz(common);
+                        for (int c = 0; c < kRegElems; c++)
+                        {
+                            const bool in = ((unsigned)c & common) == common;
+                            if (in != !((skip >> c) & 1) || (in && e[c] != e[common])) cp_hi = -1;
+                        }
+                    }
                     if (skip == (1 << kRegElems) - 1) {}
+                    else if (cp_hi >= 0)
+                    {
+                        nd.code = RC_CP2;
+                        nd.pos = cp_hi * (cp_hi - 1) / 2 + cp_lo;
+                        put(nd, 0, e[common]);
+                        out.ops.push_back(nd);
+                    }
                     else if (common)
                     {
                         // every non-unit entry has register bit P set (phases controlled by P): an 8-entry table
@@ -582,7 +601,19 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                 out.ops.push_back(d);
             }
             flush(all_regs);
-            out.rounds.back().count = (int32_t)out.ops.size() - rd_first;
+            // (first / count are op INDICES until the stream is laid out below; long rounds are split)
+            {
+                int left = (int32_t)out.ops.size() - rd_first, at = rd_first;
+                out.rounds.back().count = std::min(left, kMaxOpsPerRound);
+                while ((left -= kMaxOpsPerRound) > 0)
+                {
+                    DevRound more = out.rounds.back();
+                    at += kMaxOpsPerRound;
+                    more.first = at;
+                    more.count = std::min(left, kMaxOpsPerRound);
+                    out.rounds.push_back(more);
+                }
+            }
         }
         g.count = (int32_t)out.rounds.size() - g.first;
         out.groups.push_back(g);
@@ -612,7 +643,15 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
     }
     offset16[out.ops.size()] = (int)(out.stream.size() / 16);
     out.stream.insert(out.stream.end(), 16, (unsigned char)0);
-    for (DevRound& rd : out.rounds) rd.first = offset16[rd.first];
+    for (DevRound& rd : out.rounds)
+    {
+        for (int j = 0; j < rd.count; j++)
+        {
+            const DevOp& d = out.ops[(size_t)rd.first + j];
+            rd.vids[j] = (uint8_t)(d.code * 8 + (d.code == RC_STAR || d.code == RC_DIAGR ? 0 : d.pos));
+        }
+        rd.first = offset16[rd.first];
+    }
 }
 
 void fill_sweep_tables(const Sweep& sw, int M, SweepArgs& a)
@@ -643,8 +682,8 @@ void fill_sweep_tables(const Sweep& sw, int M, SweepArgs& a)
             ho |= bit << sw.out_pos[ord[i]];
             hs |= (unsigned)bit << ord[i];
         }
-        a.hin[it] = hi;
-        a.hout[it] = ho;
+        a.hin[it] = hi << 4; // BYTE offsets (16 B per element)
+        a.hout[it] = ho << 4;
         a.hs[it] = (unsigned short)swz_host(hs);
     }
     std::vector<char> used_in(M, 0), used_out(M, 0);
@@ -666,8 +705,10 @@ std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a)
         o << "]";
     };
     o << "{\"k\":" << a.k << ",\"n_comp\":" << a.n_comp << ",";
-    arr("hin", a.hin, kMaxIter); o << ",";
-    arr("hout", a.hout, kMaxIter); o << ",";
+    unsigned long long hin_e[kMaxIter], hout_e[kMaxIter]; // element offsets for the emulator
+    for (int it = 0; it < kMaxIter; it++) { hin_e[it] = a.hin[it] >> 4; hout_e[it] = a.hout[it] >> 4; }
+    arr("hin", hin_e, kMaxIter); o << ",";
+    arr("hout", hout_e, kMaxIter); o << ",";
     arr("hs", a.hs, kMaxIter); o << ",";
     arr("gin", a.gin, 12); o << ",";
     arr("gout", a.gout, 12); o << ",";

@@ -30,10 +30,23 @@ __device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) // a*b 
     return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
 }
 
+// v *= p, in place and without a temporary copy of v: both products with p.y are formed first, then each component is
+// updated by ONE read-modify-write FMA (ptxas otherwise parks the new real part in a temporary and moves it back)
+__device__ __forceinline__ void cmul_ip(double2& v, const double2 p)
+{
+    const double t1 = v.y * p.y, t2 = v.x * p.y;
+    v.x = fma(v.x, p.x, -t1);
+    v.y = fma(v.y, p.x, t2);
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_u32(unsigned smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -50,14 +63,14 @@ __device__ __forceinline__ void st_stream(double2* p, double2 v)
 // ------------------------------------------------------------------------------------------------
 constexpr int E = kRegElems;
 // an op in the shared-memory op stream: DevOpHdr (16 bytes) + payload
-// (the header travels in registers: it was fetched while the previous op ran)
+// (the kernel never reads vid / size16 from the stream: it dispatches from DevRound::vids and every body knows its size)
 struct Op
 {
     const unsigned char* p;
-    int aux_, star_;
+    __device__ __forceinline__ const DevOpHdr* hdr() const { return reinterpret_cast<const DevOpHdr*>(p); }
     __device__ __forceinline__ const double* m() const { return reinterpret_cast<const double*>(p + 16); }
-    __device__ __forceinline__ int aux() const { return aux_; }
-    __device__ __forceinline__ int star() const { return star_; }
+    __device__ __forceinline__ int aux() const { return hdr()->aux; }
+    __device__ __forceinline__ int star() const { return hdr()->star[0]; }
 };
 __device__ __forceinline__ const double2* op_m(Op op) { return reinterpret_cast<const double2*>(op.p + 16); }
 
@@ -213,12 +226,22 @@ __device__ __forceinline__ void r_perm2w(double2 (&v)[E], Op op)
         for (int q = 0; q < E; q++)
             if (!(q & (bh | bl)))
             {
-                v[q] = cmul(p0, v[q]);
-                v[q | bl] = cmul(p1, v[q | bl]);
-                v[q | bh] = cmul(p2, v[q | bh]);
-                v[q | bh | bl] = cmul(p3, v[q | bh | bl]);
+                cmul_ip(v[q], p0);
+                cmul_ip(v[q | bl], p1);
+                cmul_ip(v[q | bh], p2);
+                cmul_ip(v[q | bh | bl], p3);
             }
     }
+}
+// one controlled phase between register bits PH and PL
+template <int PH, int PL>
+__device__ __forceinline__ void r_cp2(double2 (&v)[E], Op op)
+{
+    constexpr int both = (1 << PH) | (1 << PL);
+    const double2 phi = op_m(op)[0];
+#pragma unroll
+    for (int c = 0; c < E; c++)
+        if ((c & both) == both) cmul_ip(v[c], phi);
 }
 template <int PH, int PL>
 __device__ __forceinline__ void r_perm2(double2 (&v)[E], Op op)
@@ -236,7 +259,7 @@ __device__ __forceinline__ void r_diagr(double2 (&v)[E], Op op)
     const int skip = op.aux() & 0xffff;
 #pragma unroll
     for (int c = 0; c < E; c++)
-        if (!((skip >> c) & 1)) v[c] = cmul(op_m(op)[c], v[c]);
+        if (!((skip >> c) & 1)) cmul_ip(v[c], op_m(op)[c]);
 }
 // diagonal whose non-unit entries all have register bit P set: 8 entries over the other three register bits
 template <int P>
@@ -247,7 +270,7 @@ __device__ __forceinline__ void r_diagp(double2 (&v)[E], Op op)
     for (int j = 0; j < E / 2; j++)
     {
         const int c = ((j >> P) << (P + 1)) | (1 << P) | (j & ((1 << P) - 1));
-        if (!((skip >> j) & 1)) v[c] = cmul(op_m(op)[j], v[c]);
+        if (!((skip >> j) & 1)) cmul_ip(v[c], op_m(op)[j]);
     }
 }
 
@@ -271,7 +294,7 @@ __device__ __forceinline__ void r_star(double2 (&v)[E], Op op, const StarCtx& sc
             slot++;
 #pragma unroll
             for (int c = 0; c < E; c++)
-                if (c & (1 << p)) v[c] = cmul(phi, v[c]);
+                if (c & (1 << p)) cmul_ip(v[c], phi);
         }
 }
 
@@ -280,26 +303,30 @@ __device__ __forceinline__ void r_star(double2 (&v)[E], Op op, const StarCtx& sc
 // bodies in one kernel it copies all 64 registers before and after every op (measured: 135 moves per op).
 // vid = code * 8 + pos (DevOp::vid, set by the encoder): one jump table for op kind and register position.
 #define DMB_HAS(c) ((MASK >> (c)) & 1u)
-#define DMB_CASE1(c, FN, ...)                                                \
-    case (c) * 8 + 0: if (DMB_HAS(c)) FN<0>(__VA_ARGS__); break;             \
-    case (c) * 8 + 1: if (DMB_HAS(c)) FN<1>(__VA_ARGS__); break;             \
-    case (c) * 8 + 2: if (DMB_HAS(c)) FN<2>(__VA_ARGS__); break;             \
-    case (c) * 8 + 3: if (DMB_HAS(c)) FN<3>(__VA_ARGS__); break;
-#define DMB_CASE2(c, FN, ...)                                                \
-    case (c) * 8 + 0: if (DMB_HAS(c)) FN<1, 0>(__VA_ARGS__); break;          \
-    case (c) * 8 + 1: if (DMB_HAS(c)) FN<2, 0>(__VA_ARGS__); break;          \
-    case (c) * 8 + 2: if (DMB_HAS(c)) FN<2, 1>(__VA_ARGS__); break;          \
-    case (c) * 8 + 3: if (DMB_HAS(c)) FN<3, 0>(__VA_ARGS__); break;          \
-    case (c) * 8 + 4: if (DMB_HAS(c)) FN<3, 1>(__VA_ARGS__); break;          \
-    case (c) * 8 + 5: if (DMB_HAS(c)) FN<3, 2>(__VA_ARGS__); break;
+#define DMB_SZ(c) (16 + dev_op_payload_bytes(c))
+#define DMB_CASE1(c, FN, ...)                                                                  \
+    case (c) * 8 + 0: if (DMB_HAS(c)) { FN<0>(__VA_ARGS__); p += DMB_SZ(c); } break;           \
+    case (c) * 8 + 1: if (DMB_HAS(c)) { FN<1>(__VA_ARGS__); p += DMB_SZ(c); } break;           \
+    case (c) * 8 + 2: if (DMB_HAS(c)) { FN<2>(__VA_ARGS__); p += DMB_SZ(c); } break;           \
+    case (c) * 8 + 3: if (DMB_HAS(c)) { FN<3>(__VA_ARGS__); p += DMB_SZ(c); } break;
+#define DMB_CASE2(c, FN, ...)                                                                  \
+    case (c) * 8 + 0: if (DMB_HAS(c)) { FN<1, 0>(__VA_ARGS__); p += DMB_SZ(c); } break;        \
+    case (c) * 8 + 1: if (DMB_HAS(c)) { FN<2, 0>(__VA_ARGS__); p += DMB_SZ(c); } break;        \
+    case (c) * 8 + 2: if (DMB_HAS(c)) { FN<2, 1>(__VA_ARGS__); p += DMB_SZ(c); } break;        \
+    case (c) * 8 + 3: if (DMB_HAS(c)) { FN<3, 0>(__VA_ARGS__); p += DMB_SZ(c); } break;        \
+    case (c) * 8 + 4: if (DMB_HAS(c)) { FN<3, 1>(__VA_ARGS__); p += DMB_SZ(c); } break;        \
+    case (c) * 8 + 5: if (DMB_HAS(c)) { FN<3, 2>(__VA_ARGS__); p += DMB_SZ(c); } break;
 
+// applies the op at stream position p and advances p past it (header + payload: a compile-time size per op code)
 template <unsigned MASK>
-__device__ __forceinline__ void apply_reg_op(double2 (&v)[E], Op op, int vid, const StarCtx& sc)
+__device__ __forceinline__ void apply_reg_op(double2 (&v)[E], const unsigned char*& p, int vid, const StarCtx& sc)
 {
+    const Op op = {p};
     switch (vid)
     {
         DMB_CASE2(RC_DENSE2, r_dense2, v, op)
         DMB_CASE2(RC_PERM2, r_perm2, v, op)
+        DMB_CASE2(RC_CP2, r_cp2, v, op)
         DMB_CASE1(RC_DENSE1, r_dense1, v, op)
         DMB_CASE1(RC_DENSE1_RR, r_dense1_rr, v, op)
         DMB_CASE1(RC_DENSE1_RI, r_dense1_ri, v, op)
@@ -307,8 +334,8 @@ __device__ __forceinline__ void apply_reg_op(double2 (&v)[E], Op op, int vid, co
         DMB_CASE1(RC_SRN1, r_srn1, v)
         DMB_CASE1(RC_HAD, r_had, v)
         DMB_CASE1(RC_DIAGP, r_diagp, v, op)
-    case RC_DIAGR * 8: if (DMB_HAS(RC_DIAGR)) r_diagr(v, op); break;
-    case RC_STAR * 8: if (DMB_HAS(RC_STAR)) r_star(v, op, sc); break;
+    case RC_DIAGR * 8: if (DMB_HAS(RC_DIAGR)) { r_diagr(v, op); p += DMB_SZ(RC_DIAGR); } break;
+    case RC_STAR * 8: if (DMB_HAS(RC_STAR)) { r_star(v, op, sc); p += DMB_SZ(RC_STAR); } break;
     default: break;
     }
 }
@@ -361,6 +388,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
     }
     s_out_lo = swz(s_out_lo);
     const unsigned s_in = swz((unsigned)t);
+    const unsigned tile_u32 = (unsigned)__cvta_generic_to_shared(tile);
     const double2* __restrict__ gin = reinterpret_cast<const double2*>(a.in);
     double2* __restrict__ gout = reinterpret_cast<double2*>(a.out);
     __syncthreads(); // program tables visible
@@ -377,25 +405,52 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
         // ---- load: 128-bit async copies straight into the swizzled tile; runs of >= 2^low_bits * 16 B ----
         if (t_active)
         {
-            const double2* src = gin + (base_in | g_in_lo);
+            const char* src = reinterpret_cast<const char*>(gin + (base_in | g_in_lo));
+            if (n_it == kMaxIter)
+            {
+                // full-size tile: no per-iteration predicates.  swz(it << 7) = (it << 7) | l3(it) with a 3-bit l3, and
+                // s_in < 128: the shared address is  tile + 16 * (s_in ^ l3(it)) + (it << 11)
 #pragma unroll
-            for (int it = 0; it < kMaxIter; it++)
-                if (it < n_it) cp_async16(&tile[swz((unsigned)(it << kThreadBits)) ^ s_in], src + a.hin[it]);
+                for (int it = 0; it < kMaxIter; it++)
+                {
+                    const unsigned l3 = (((unsigned)it << 1) ^ ((unsigned)it >> 2)) & 7u;
+                    cp_async16_u32(tile_u32 + ((s_in ^ l3) << 4) + ((unsigned)it << 11), src + a.hin[it]);
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int it = 0; it < kMaxIter; it++)
+                    if (it < n_it) cp_async16(&tile[swz((unsigned)(it << kThreadBits)) ^ s_in], src + a.hin[it]);
+            }
         }
         cp_async_commit();
         // controlled-phase stars: fold the partner bits OUTSIDE the tile (fixed for this tile) into the per-warp /
         // per-iteration table while the tile is in flight
         if (DMB_HAS(RC_STAR))
         {
+            // WO[iw] = w[iw] * X,  X = product of phi[j] over the outside partner bits set in this tile's index: 8
+            // lanes per star, each multiplies every 8th partner, then a 3-step shuffle product
             const unsigned long long full = base_in | a.rank_bits;
-            for (int i = t; i < a.n_stars * 8; i += NT)
+            for (int i0 = 0; i0 < a.n_stars * 8; i0 += NT)
             {
-                const DevStar* st = a.stars + (i >> 3);
-                double2 acc = __ldg(reinterpret_cast<const double2*>(st->w) + (i & 7));
-                const int n_out = st->n_out;
-                for (int j = 0; j < n_out; j++)
-                    if ((full >> st->bit[j]) & 1ull) acc = cmul(acc, __ldg(reinterpret_cast<const double2*>(st->phi) + j));
-                s_star[(i >> 3) * kStarEntries + (i & 7)] = acc;
+                const int i = i0 + t;
+                const bool on = i < a.n_stars * 8;
+                const DevStar* st = a.stars + (on ? (i >> 3) : 0);
+                double2 acc = make_double2(1.0, 0.0);
+                if (on)
+                {
+                    const int n_out = st->n_out;
+                    for (int j = i & 7; j < n_out; j += 8)
+                        if ((full >> st->bit[j]) & 1ull) acc = cmul(acc, __ldg(reinterpret_cast<const double2*>(st->phi) + j));
+                }
+#pragma unroll
+                for (int m = 1; m < 8; m <<= 1)
+                {
+                    const double ox = __shfl_xor_sync(0xffffffffu, acc.x, m), oy = __shfl_xor_sync(0xffffffffu, acc.y, m);
+                    acc = cmul(acc, make_double2(ox, oy));
+                }
+                if (on) s_star[(i >> 3) * kStarEntries + (i & 7)] = cmul(acc, __ldg(reinterpret_cast<const double2*>(st->w) + (i & 7)));
             }
         }
         cp_async_wait<0>();
@@ -421,6 +476,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                         const int n_ops = rd->count;
                         int nib = 0;
                         while ((1 << nib) < n_iter) nib++;
+                        const ulonglong2 vids = *reinterpret_cast<const ulonglong2*>(rd->vids);
                         // the 16 register offsets, packed two per word (kept in 8 registers: re-reading them from
                         // shared memory at store time would serialise every STS behind an LDS)
                         unsigned rw[E / 2];
@@ -437,17 +493,16 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
 #pragma unroll
                             for (int c = 0; c < E; c++) v[c] = tile[base ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)];
                             const StarCtx sc = {s_star, lane, (warp << nib) | it};
-                            // op headers {vid, aux, size16, star} are carried in registers: the next one is fetched
-                            // while the current op runs (a zero header follows the last op of the stream)
+                            // dispatch from the round's packed vid list (one byte per op, two registers pairs):
+                            // no shared-memory load on the dispatch path
                             const unsigned char* p = ops;
-                            int4 h = *reinterpret_cast<const int4*>(p);
+                            unsigned long long v0 = vids.x, v1 = vids.y;
                             for (int o = 0; o < n_ops; o++)
                             {
-                                const Op op = {p, h.y, h.w};
-                                const int vid = h.x;
-                                p += h.z * 16;
-                                h = *reinterpret_cast<const int4*>(p);
-                                apply_reg_op<MASK>(v, op, vid, sc);
+                                const int vid = (int)(v0 & 0xffull);
+                                v0 = (v0 >> 8) | (v1 << 56);
+                                v1 >>= 8;
+                                apply_reg_op<MASK>(v, p, vid, sc);
                             }
 #pragma unroll
                             for (int c = 0; c < E; c++) tile[base ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)] = v[c];
@@ -464,10 +519,26 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
         {
             if (a.peer_shift < 0)
             {
-                double2* dst = gout + (base_out | g_out_lo);
+                char* dst = reinterpret_cast<char*>(gout + (base_out | g_out_lo));
+                if (n_it == kMaxIter)
+                {
+                    // full-size tile: batches of 8 shared-memory loads, then their 8 streaming stores
 #pragma unroll
-                for (int it = 0; it < kMaxIter; it++)
-                    if (it < n_it) st_stream(dst + a.hout[it], tile[s_out_lo ^ a.hs[it]]);
+                    for (int b = 0; b < kMaxIter; b += 8)
+                    {
+                        double2 r[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) r[j] = tile[s_out_lo ^ a.hs[b + j]];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) st_stream(reinterpret_cast<double2*>(dst + a.hout[b + j]), r[j]);
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int it = 0; it < kMaxIter; it++)
+                        if (it < n_it) st_stream(reinterpret_cast<double2*>(dst + a.hout[it]), tile[s_out_lo ^ a.hs[it]]);
+                }
             }
             else
             {
@@ -477,7 +548,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                 const unsigned long long mine = (unsigned long long)a.peer_rank << a.peer_shift;
                 for (int it = 0; it < n_it; it++)
                 {
-                    const unsigned long long off = o_lo | a.hout[it];
+                    const unsigned long long off = o_lo | (a.hout[it] >> 4);
                     double2* dst = reinterpret_cast<double2*>(a.peer_out[off >> a.peer_shift]) + (mine | (off & low_mask));
                     st_stream(dst, tile[s_out_lo ^ a.hs[it]]);
                 }
@@ -494,13 +565,13 @@ static int g_num_sms = 0;
 constexpr unsigned kVariantMasks[] = {
     0u,                                                                              // pure data movement (remap pack)
     BIT(RC_DENSE2),                                                                  // random C2 blocks
-    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_DENSE1_RR) | BIT(RC_HAD),                                               // H + diagonal
-    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_STAR),                                // QFT-like
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_DENSE1_RR) | BIT(RC_HAD),                                               // H + diagonal
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_STAR),                                // QFT-like
     BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_PERM2),                                               // H / CX
     BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI),         // dense 1- and 2-qubit blocks
-    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1),               // Clifford+T style
-    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) | BIT(RC_STAR), // no dense 4x4
-    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) |
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1),               // Clifford+T style
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) | BIT(RC_STAR), // no dense 4x4
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) |
         BIT(RC_SRN1) | BIT(RC_STAR),                                                 // everything
 };
 constexpr int kNumVariants = sizeof(kVariantMasks) / sizeof(kVariantMasks[0]);

@@ -70,7 +70,7 @@ def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = No
 
 
 (RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE2, RC_DIAG2, RC_PERM2, RC_DIAGR, RC_DENSE1_RR, RC_DENSE1_RI, RC_STAR,
- RC_HAD, RC_DIAGP) = range(13)
+ RC_HAD, RC_DIAGP, RC_CP2) = range(14)
 _POS2 = {0: (1, 0), 1: (2, 0), 2: (2, 1), 3: (3, 0), 4: (3, 1), 5: (3, 2)}
 _PERMS = {0: [0, 1, 3, 2], 1: [0, 3, 2, 1], 2: [0, 2, 1, 3]}
 
@@ -187,6 +187,8 @@ def _apply_reg_op(op, v):
             for r in range(4):
                 if not (skip >> r) & 1:
                     v[ids[r]] = m[r] * a[r]
+        elif code == RC_CP2:
+            v[ids[3]] = m[0] * a[3]
         elif code == RC_PERM2:
             src = _PERMS[aux & 3]
             for r in range(4):

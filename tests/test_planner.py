@@ -175,3 +175,56 @@ def test_controlled_phase_stars(dm, oracle_mod, opts, n, world, o):
         assert np.abs(ke.run_plan_dev(plan0, zero_state(n)) - ref).max() < TOL
     finally:
         dm.set_option("cphase", 1)
+
+
+def test_deferred_diagonals_and_new_device_ops(dm, oracle_mod):
+    """Pending diagonal factors materialise only when a non-diagonal op needs their register bit: QFT rounds become
+    HAD / CP2 / STAR, controlled diagonals RC_DIAGP, Hadamard scales fold across the sweep (RC_HAD), and rounds with
+    more than 16 device ops are split.  Every variant is checked against the oracle through the kernel mirror."""
+    import importlib
+    circuits = importlib.import_module("dm-sim_b200.circuits")
+    RC = dict(DIAGR=7, RR=8, STAR=10, HAD=11, DIAGP=12, CP2=13)
+    rng = np.random.default_rng(5)
+
+    def codes(plan):
+        return [o["code"] for st in plan["steps"] if st["kind"] == "sweep" for o in st["dev"]["ops"]]
+
+    # QFT: butterflies + pair phases + stars; at most one scaled H per sweep carries the folded scales
+    n = 7
+    gates = circuits.qft(n)
+    plan = dm.plan_json(n, 1, gates)
+    c = codes(plan)
+    assert RC["HAD"] in c and RC["CP2"] in c and RC["STAR"] in c
+    for st in plan["steps"]:
+        assert sum(1 for o in st["dev"]["ops"] if o["code"] == RC["RR"]) <= 1
+    re, im = oracle_mod.Oracle(n).sim(gates).dm()
+    assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - to_complex(re, im)).max() < TOL
+
+    # phases controlled by one qubit with several partners inside a round -> RC_DIAGP; T/S/Z on top -> RC_DIAGR
+    n = 4
+    gates = [("H", [q], 0, 0, 0) for q in range(n)]
+    gates += [("CU1", [3, q], 0, 0, 0.3 + 0.2 * q) for q in range(3)] + [("H", [3], 0, 0, 0)]
+    gates += [("T", [0], 0, 0, 0), ("S", [1], 0, 0, 0), ("CZ", [0, 1], 0, 0, 0), ("U1", [2], 0, 0, 0.7), ("H", [0], 0, 0, 0)]
+    plan = dm.plan_json(n, 1, gates)
+    c = codes(plan)
+    assert RC["DIAGP"] in c
+    re, im = oracle_mod.Oracle(n).sim(gates).dm()
+    assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - to_complex(re, im)).max() < TOL
+
+    # 24 non-commuting 2-qubit blocks cycling through the pairs of 3 qubits: their L parts share one register round
+    # (3 register bits) with more than 16 device ops, which the encoder splits
+    n = 3
+    gates = []
+    for i in range(24):
+        a, b = [(0, 1), (1, 2), (2, 0)][i % 3]
+        gates.append(("CU3", [a, b], float(rng.uniform(-2, 2)), float(rng.uniform(-2, 2)), float(rng.uniform(-2, 2))))
+    plan = dm.plan_json(n, 1, gates)
+    re, im = oracle_mod.Oracle(n).sim(gates).dm()
+    assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - to_complex(re, im)).max() < TOL
+    split = False
+    for st in plan["steps"]:
+        rounds = st["dev"]["rounds"]
+        for r in rounds:
+            assert r["count"] <= 16
+        split |= any(a["roff"] == b["roff"] and a["lane_tab"] == b["lane_tab"] and a["count"] == 16 for a, b in zip(rounds, rounds[1:]))
+    assert split
