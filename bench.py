@@ -228,18 +228,25 @@ def main():
 
     # ---- end to end through the C-ABI with HOST buffers: reset + circuit upload (H2D) + run + diagonal (D2H)
     diag = np.empty(1 << n)
-    e2e_ms = []
+    e2e_ms, parts = [], [0.0, 0.0, 0.0, 0.0]
     for i in range(2 + min(args.steps, 3)):
         barrier()
         t1 = time.perf_counter()
         sim.reset_dm()
+        t2 = time.perf_counter()
         set_circuit()
+        t3 = time.perf_counter()
         sim.run()
+        t4 = time.perf_counter()
         dm._check(L.dmb_get_diag(sim._h, diag.ctypes.data))
         barrier()
+        t5 = time.perf_counter()
         if i >= 2:
-            e2e_ms.append((time.perf_counter() - t1) * 1e3)
+            e2e_ms.append((t5 - t1) * 1e3)
+            for j, dt in enumerate((t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+                parts[j] += dt * 1e3
     e2e = sum(e2e_ms) / len(e2e_ms)
+    parts = [x / len(e2e_ms) for x in parts]
     if dist is not None:
         t = torch.tensor([e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -276,8 +283,11 @@ def main():
                      "traffic": _ncu_traffic(args.workload)},
         "e2e": {"value": n_gates / (e2e * 1e-3), "unit": "gates/s", "ms_per_step": e2e,
                 "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": 8 * (1 << n),
+                "host_call_ms": {"reset_dm": parts[0], "set_circuit": parts[1], "run": parts[2], "get_diag": parts[3]},
                 "what": "host gate list in, host diagonal out: dmb_reset_dm + dmb_set_circuit (plan + H2D of the device op "
                         "tables) + dmb_run + dmb_get_diag (D2H of the 2^n probabilities), wall clock"},
+        # size-independent rate (gates/s shrinks 4x per added qubit): gates x density-matrix elements updated per second
+        "work_rate": {"value": n_gates * float(4 ** n) / (ms_step * 1e-3), "unit": "gate x element updates/s"},
         "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
         "trace_after_run": trace, "clocks": clocks,
     }

@@ -40,9 +40,10 @@ enum RegOpCode : int32_t
     RC_DENSE1_RR = 8, // 2x2 with four REAL entries [[d0,d1],[d2,d3]] (H, RY, ...), |d0| not small, in the pivoted in-place
                       // form m[0..3] = {d0, d1, d2/d0, det/d0}: half the FP64 work of RC_DENSE1 and no register copies
     RC_DENSE1_RI = 9, // [[d0, i d1], [i d2, d3]] with real d (RX, W, ...), same form with det = d0 d3 + d1 d2
-    RC_HAD = 11,      // unscaled butterfly [[1, 1], [1, -1]] (a' = a + b, b' = a' - 2 b: 2 FP64 instructions per pair and
-                      // component, in place, no payload); the 1/sqrt(2) factors of the H gates of a round are folded by
-                      // the encoder into the payload of a later op of the same round (scalars commute with everything)
+    RC_HAD = 11,      // unscaled butterflies [[1, 1], [1, -1]] (a' = a + b, b' = a' - 2 b: 2 FP64 instructions per pair and
+                      // component, in place, no payload) on every register bit of the mask in aux bits 0..3; the
+                      // 1/sqrt(2) factors of the H gates of a SWEEP are folded by the encoder into the payload of a dense
+                      // op of the same sweep (scalars commute with everything)
     RC_DIAGP = 12,    // diagonal whose non-unit entries all have register bit `pos` set (phases controlled by that
                       // bit, e.g. the controlled phases between the register bits of a QFT round): m[j] multiplies the
                       // element whose other three register bits spell j; skip mask (unit entries) in aux bits 0..7
@@ -75,11 +76,34 @@ constexpr int kStarSmemBytes = 320;
 // Device op stream: 16-byte header + payload (the used part of DevOp::m), 16-byte granularity; a zero header ends it.
 struct alignas(16) DevOpHdr
 {
-    int32_t vid;    // code * 8 + pos
+    int32_t vid;    // dev_vid(code, pos, aux)
     int32_t aux;
     int32_t size16; // header + payload in 16-byte units
     int32_t star[1]; // RC_STAR: star[0] = first DevStar slot of this op (one per set aux bit, ascending)
 };
+// The kernel's jump-table index of an op: dense over (code, position) -- and over the register-bit MASK for RC_HAD and
+// RC_STAR, so that those two need no header read at all.
+constexpr int kVidDense2 = 0, kVidPerm2 = 6, kVidCp2 = 12, kVidDense1 = 18, kVidRR = 22, kVidRI = 26, kVidMono1 = 30,
+              kVidSrn1 = 34, kVidDiagP = 38, kVidDiagR = 42, kVidHad = 43, kVidStar = 58, kNumVids = 73;
+constexpr int dev_vid(int code, int pos, int aux)
+{
+    switch (code)
+    {
+    case RC_DENSE2: return kVidDense2 + pos;
+    case RC_PERM2: return kVidPerm2 + pos;
+    case RC_CP2: return kVidCp2 + pos;
+    case RC_DENSE1: return kVidDense1 + pos;
+    case RC_DENSE1_RR: return kVidRR + pos;
+    case RC_DENSE1_RI: return kVidRI + pos;
+    case RC_MONO1: return kVidMono1 + pos;
+    case RC_SRN1: return kVidSrn1 + pos;
+    case RC_DIAGP: return kVidDiagP + pos;
+    case RC_DIAGR: return kVidDiagR;
+    case RC_HAD: return kVidHad + (aux & 15) - 1;
+    case RC_STAR: return kVidStar + (aux & 15) - 1;
+    default: return kNumVids;
+    }
+}
 constexpr int dev_op_payload_bytes(int code)
 {
     switch (code)
@@ -121,11 +145,13 @@ struct alignas(16) DevRound
     uint16_t lane_tab[32];
     uint16_t iter_tab[8];
     uint16_t roff[16];
-    uint8_t vids[kMaxOpsPerRound]; // DevOpHdr::vid of the round's ops: the kernel dispatches from this packed list (in
+    uint8_t vids[kMaxOpsPerRound]; // dev_vid() of the round's ops: the kernel dispatches from this packed list (in
                                    // registers) and every op body advances the stream pointer by its static size, so
                                    // that no shared-memory load sits on the dispatch path
+    int32_t star0;                 // DevStar slot of the round's first star bit (the following ones are consecutive)
+    int32_t pad[3];
 };
-static_assert(sizeof(DevRound) == 144, "DevRound layout");
+static_assert(sizeof(DevRound) == 160, "DevRound layout");
 
 // A run of consecutive rounds that leave kWarpBits tile bits untouched: warp w owns the sub-tile where those bits
 // equal w and runs the whole group with __syncwarp() only; CTA barriers happen between groups.

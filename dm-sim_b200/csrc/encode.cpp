@@ -293,6 +293,7 @@ void fold_hadamard_scales(std::vector<DevOp>& ops)
         if (i == carrier || !is_had(d)) continue;
         f *= d.m[0];
         d.code = RC_HAD;
+        d.aux = 1 << d.pos;
         memset(d.m, 0, sizeof(d.m));
     }
     if (f == 1.0) return;
@@ -303,6 +304,46 @@ void fold_hadamard_scales(std::vector<DevOp>& ops)
     case RC_DENSE2: for (int i = 0; i < 32; i++) d.m[i] *= f; break;
     default: d.m[0] *= f; d.m[1] *= f; d.m[3] *= f; break; // pivoted forms: d2/d0 is scale free
     }
+}
+
+// register bits a device op acts on (conservative for the table diagonals)
+unsigned reg_support(const DevOp& d)
+{
+    static const int hi[6] = {1, 2, 2, 3, 3, 3}, lo[6] = {0, 0, 1, 0, 1, 2};
+    switch (d.code)
+    {
+    case RC_DENSE2: case RC_PERM2: case RC_CP2: return (1u << hi[d.pos]) | (1u << lo[d.pos]);
+    case RC_HAD: case RC_STAR: return (unsigned)d.aux & 15u;
+    case RC_DIAGR: case RC_DIAGP: return 15u;
+    default: return 1u << d.pos;
+    }
+}
+
+// Butterflies on different register bits commute with each other and with every op on other bits: an RC_HAD moves back
+// over ops that do not touch its bit and joins the previous RC_HAD of its round (one dispatch for up to 4 butterflies).
+void merge_butterflies(EncodedSweep& out)
+{
+    std::vector<DevOp> ops;
+    ops.reserve(out.ops.size());
+    for (DevRound& rd : out.rounds)
+    {
+        const size_t begin = ops.size();
+        for (int j = 0; j < rd.count; j++)
+        {
+            const DevOp& d = out.ops[(size_t)rd.first + j];
+            bool merged = false;
+            if (d.code == RC_HAD)
+                for (size_t i = ops.size(); i-- > begin;)
+                {
+                    if (ops[i].code == RC_HAD) { ops[i].aux |= d.aux; merged = true; break; }
+                    if (reg_support(ops[i]) & (unsigned)d.aux) break;
+                }
+            if (!merged) ops.push_back(d);
+        }
+        rd.first = (int32_t)begin;
+        rd.count = (int32_t)(ops.size() - begin);
+    }
+    out.ops.swap(ops);
 }
 
 // The diagonal-type ops of a round all commute with each other, and each commutes with every op that touches none
@@ -541,6 +582,11 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                                 st.phi[2 * j] = acc.real();
                                 st.phi[2 * j + 1] = acc.imag();
                             }
+                        for (int j = st.n_out; j < kMaxStarOut; j++) // padding: bit 63 of an index is never set
+                        {
+                            st.bit[j] = 63;
+                            st.phi[2 * j] = 1.0;
+                        }
                         out.stars.push_back(st);
                         pend.star[p].clear();
                     }
@@ -621,6 +667,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
     }
     if ((int)out.stars.size() > kMaxStarsPerSweep) throw std::logic_error("too many controlled-phase stars in one sweep");
     fold_hadamard_scales(out.ops);
+    merge_butterflies(out);
 
     // ---- the device op stream: 16-byte header + the used part of the payload per op, a zero header at the end ----
     std::vector<int> offset16(out.ops.size() + 1, 0);
@@ -629,7 +676,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
         DevOp& d = out.ops[i];
         const int star0 = d.code == RC_STAR ? d.vid : 0;
         DevOpHdr h;
-        h.vid = d.code * 8 + (d.code == RC_STAR || d.code == RC_DIAGR ? 0 : d.pos);
+        h.vid = dev_vid(d.code, d.pos, d.aux);
         h.aux = d.aux;
         const int payload = dev_op_payload_bytes(d.code);
         h.size16 = 1 + payload / 16;
@@ -645,11 +692,15 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
     out.stream.insert(out.stream.end(), 16, (unsigned char)0);
     for (DevRound& rd : out.rounds)
     {
+        memset(rd.vids, 0, sizeof(rd.vids));
+        rd.star0 = -1;
         for (int j = 0; j < rd.count; j++)
         {
             const DevOp& d = out.ops[(size_t)rd.first + j];
-            rd.vids[j] = (uint8_t)(d.code * 8 + (d.code == RC_STAR || d.code == RC_DIAGR ? 0 : d.pos));
+            rd.vids[j] = (uint8_t)dev_vid(d.code, d.pos, d.aux);
+            if (d.code == RC_STAR && rd.star0 < 0) rd.star0 = d.vid; // host-side vid of RC_STAR = its first slot
         }
+        if (rd.star0 < 0) rd.star0 = 0;
         rd.first = offset16[rd.first];
     }
 }

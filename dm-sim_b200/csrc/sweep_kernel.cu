@@ -281,21 +281,39 @@ struct StarCtx
     int lane, iw;
 };
 constexpr int kStarEntries = kStarSmemBytes / 16;
-__device__ __forceinline__ void r_star(double2 (&v)[E], Op op, const StarCtx& sc)
+// mask = the register bits with a star; their DevStar slots are consecutive from `slot` (advanced past them)
+__device__ __forceinline__ void r_star(double2 (&v)[E], int mask, int& slot, const StarCtx& sc)
 {
-    const int mask = op.aux() & 15;
-    int slot = op.star();
+    // two register bits at a time: their table reads first (independent addresses), then the multiplications
 #pragma unroll
-    for (int p = 0; p < kRegBits; p++)
-        if ((mask >> p) & 1)
-        {
-            const double2* tb = sc.tab + slot * kStarEntries;
-            const double2 phi = cmul(cmul(tb[8 + (sc.lane & 7)], tb[16 + (sc.lane >> 3)]), tb[sc.iw]);
-            slot++;
+    for (int h = 0; h < kRegBits; h += 2)
+    {
+        double2 ph[2];
 #pragma unroll
-            for (int c = 0; c < E; c++)
-                if (c & (1 << p)) cmul_ip(v[c], phi);
-        }
+        for (int q = 0; q < 2; q++)
+            if ((mask >> (h + q)) & 1)
+            {
+                const double2* tb = sc.tab + slot * kStarEntries;
+                ph[q] = cmul(cmul(tb[8 + (sc.lane & 7)], tb[16 + (sc.lane >> 3)]), tb[sc.iw]);
+                slot++;
+            }
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+            if ((mask >> (h + q)) & 1)
+            {
+#pragma unroll
+                for (int c = 0; c < E; c++)
+                    if (c & (1 << (h + q))) cmul_ip(v[c], ph[q]);
+            }
+    }
+}
+// butterflies on every register bit of the mask
+__device__ __forceinline__ void r_hadm(double2 (&v)[E], int mask)
+{
+    if (mask & 1) r_had<0>(v);
+    if (mask & 2) r_had<1>(v);
+    if (mask & 4) r_had<2>(v);
+    if (mask & 8) r_had<3>(v);
 }
 
 // MASK = the register-op codes compiled into this instantiation of the kernel (bit c <-> RegOpCode c).  ptxas keeps
@@ -304,39 +322,45 @@ __device__ __forceinline__ void r_star(double2 (&v)[E], Op op, const StarCtx& sc
 // vid = code * 8 + pos (DevOp::vid, set by the encoder): one jump table for op kind and register position.
 #define DMB_HAS(c) ((MASK >> (c)) & 1u)
 #define DMB_SZ(c) (16 + dev_op_payload_bytes(c))
-#define DMB_CASE1(c, FN, ...)                                                                  \
-    case (c) * 8 + 0: if (DMB_HAS(c)) { FN<0>(__VA_ARGS__); p += DMB_SZ(c); } break;           \
-    case (c) * 8 + 1: if (DMB_HAS(c)) { FN<1>(__VA_ARGS__); p += DMB_SZ(c); } break;           \
-    case (c) * 8 + 2: if (DMB_HAS(c)) { FN<2>(__VA_ARGS__); p += DMB_SZ(c); } break;           \
-    case (c) * 8 + 3: if (DMB_HAS(c)) { FN<3>(__VA_ARGS__); p += DMB_SZ(c); } break;
-#define DMB_CASE2(c, FN, ...)                                                                  \
-    case (c) * 8 + 0: if (DMB_HAS(c)) { FN<1, 0>(__VA_ARGS__); p += DMB_SZ(c); } break;        \
-    case (c) * 8 + 1: if (DMB_HAS(c)) { FN<2, 0>(__VA_ARGS__); p += DMB_SZ(c); } break;        \
-    case (c) * 8 + 2: if (DMB_HAS(c)) { FN<2, 1>(__VA_ARGS__); p += DMB_SZ(c); } break;        \
-    case (c) * 8 + 3: if (DMB_HAS(c)) { FN<3, 0>(__VA_ARGS__); p += DMB_SZ(c); } break;        \
-    case (c) * 8 + 4: if (DMB_HAS(c)) { FN<3, 1>(__VA_ARGS__); p += DMB_SZ(c); } break;        \
-    case (c) * 8 + 5: if (DMB_HAS(c)) { FN<3, 2>(__VA_ARGS__); p += DMB_SZ(c); } break;
+#define DMB_CASE1(base, c, FN, ...)                                                            \
+    case (base) + 0: if (DMB_HAS(c)) { FN<0>(__VA_ARGS__); p += DMB_SZ(c); } break;            \
+    case (base) + 1: if (DMB_HAS(c)) { FN<1>(__VA_ARGS__); p += DMB_SZ(c); } break;            \
+    case (base) + 2: if (DMB_HAS(c)) { FN<2>(__VA_ARGS__); p += DMB_SZ(c); } break;            \
+    case (base) + 3: if (DMB_HAS(c)) { FN<3>(__VA_ARGS__); p += DMB_SZ(c); } break;
+#define DMB_CASE2(base, c, FN, ...)                                                            \
+    case (base) + 0: if (DMB_HAS(c)) { FN<1, 0>(__VA_ARGS__); p += DMB_SZ(c); } break;         \
+    case (base) + 1: if (DMB_HAS(c)) { FN<2, 0>(__VA_ARGS__); p += DMB_SZ(c); } break;         \
+    case (base) + 2: if (DMB_HAS(c)) { FN<2, 1>(__VA_ARGS__); p += DMB_SZ(c); } break;         \
+    case (base) + 3: if (DMB_HAS(c)) { FN<3, 0>(__VA_ARGS__); p += DMB_SZ(c); } break;         \
+    case (base) + 4: if (DMB_HAS(c)) { FN<3, 1>(__VA_ARGS__); p += DMB_SZ(c); } break;         \
+    case (base) + 5: if (DMB_HAS(c)) { FN<3, 2>(__VA_ARGS__); p += DMB_SZ(c); } break;
+#define DMB_CASE15(base)                                                                                              \
+    case (base) + 0: case (base) + 1: case (base) + 2: case (base) + 3: case (base) + 4: case (base) + 5: case (base) + 6:  \
+    case (base) + 7: case (base) + 8: case (base) + 9: case (base) + 10: case (base) + 11: case (base) + 12:               \
+    case (base) + 13: case (base) + 14:
 
-// applies the op at stream position p and advances p past it (header + payload: a compile-time size per op code)
+// applies the op at stream position p and advances p past it (header + payload: a compile-time size per op code).
+// vid = dev_vid(): ONE dense jump table; RC_HAD / RC_STAR carry their register-bit mask in the vid (no header read).
 template <unsigned MASK>
-__device__ __forceinline__ void apply_reg_op(double2 (&v)[E], const unsigned char*& p, int vid, const StarCtx& sc)
+__device__ __forceinline__ void apply_reg_op(double2 (&v)[E], const unsigned char*& p, int vid, int& slot, const StarCtx& sc)
 {
     const Op op = {p};
+    // the two mask-carrying ops first (two compares), everything else through one dense jump table
+    if (DMB_HAS(RC_STAR) && vid >= kVidStar) { r_star(v, vid - kVidStar + 1, slot, sc); p += DMB_SZ(RC_STAR); return; }
+    if (DMB_HAS(RC_HAD) && vid >= kVidHad) { r_hadm(v, vid - kVidHad + 1); p += DMB_SZ(RC_HAD); return; }
     switch (vid)
     {
-        DMB_CASE2(RC_DENSE2, r_dense2, v, op)
-        DMB_CASE2(RC_PERM2, r_perm2, v, op)
-        DMB_CASE2(RC_CP2, r_cp2, v, op)
-        DMB_CASE1(RC_DENSE1, r_dense1, v, op)
-        DMB_CASE1(RC_DENSE1_RR, r_dense1_rr, v, op)
-        DMB_CASE1(RC_DENSE1_RI, r_dense1_ri, v, op)
-        DMB_CASE1(RC_MONO1, r_mono1, v, op)
-        DMB_CASE1(RC_SRN1, r_srn1, v)
-        DMB_CASE1(RC_HAD, r_had, v)
-        DMB_CASE1(RC_DIAGP, r_diagp, v, op)
-    case RC_DIAGR * 8: if (DMB_HAS(RC_DIAGR)) { r_diagr(v, op); p += DMB_SZ(RC_DIAGR); } break;
-    case RC_STAR * 8: if (DMB_HAS(RC_STAR)) { r_star(v, op, sc); p += DMB_SZ(RC_STAR); } break;
-    default: break;
+        DMB_CASE2(kVidDense2, RC_DENSE2, r_dense2, v, op)
+        DMB_CASE2(kVidPerm2, RC_PERM2, r_perm2, v, op)
+        DMB_CASE2(kVidCp2, RC_CP2, r_cp2, v, op)
+        DMB_CASE1(kVidDense1, RC_DENSE1, r_dense1, v, op)
+        DMB_CASE1(kVidRR, RC_DENSE1_RR, r_dense1_rr, v, op)
+        DMB_CASE1(kVidRI, RC_DENSE1_RI, r_dense1_ri, v, op)
+        DMB_CASE1(kVidMono1, RC_MONO1, r_mono1, v, op)
+        DMB_CASE1(kVidSrn1, RC_SRN1, r_srn1, v)
+        DMB_CASE1(kVidDiagP, RC_DIAGP, r_diagp, v, op)
+    case kVidDiagR: if (DMB_HAS(RC_DIAGR)) { r_diagr(v, op); p += DMB_SZ(RC_DIAGR); } break;
+    default: __builtin_unreachable();
     }
 }
 
@@ -437,12 +461,22 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                 const int i = i0 + t;
                 const bool on = i < a.n_stars * 8;
                 const DevStar* st = a.stars + (on ? (i >> 3) : 0);
+                // (bit[] is padded with 63 and phi[] with 1 up to kMaxStarOut: every load below is independent)
                 double2 acc = make_double2(1.0, 0.0);
                 if (on)
                 {
-                    const int n_out = st->n_out;
-                    for (int j = i & 7; j < n_out; j += 8)
-                        if ((full >> st->bit[j]) & 1ull) acc = cmul(acc, __ldg(reinterpret_cast<const double2*>(st->phi) + j));
+                    int bj[(kMaxStarOut + 7) / 8];
+                    double2 fj[(kMaxStarOut + 7) / 8];
+#pragma unroll
+                    for (int q = 0; q < (kMaxStarOut + 7) / 8; q++)
+                    {
+                        const int j = (i & 7) + 8 * q;
+                        bj[q] = j < kMaxStarOut ? __ldg(st->bit + j) : 63;
+                        fj[q] = j < kMaxStarOut ? __ldg(reinterpret_cast<const double2*>(st->phi) + j) : make_double2(1.0, 0.0);
+                    }
+#pragma unroll
+                    for (int q = 0; q < (kMaxStarOut + 7) / 8; q++)
+                        if ((full >> bj[q]) & 1ull) acc = cmul(acc, fj[q]);
                 }
 #pragma unroll
                 for (int m = 1; m < 8; m <<= 1)
@@ -477,6 +511,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                         int nib = 0;
                         while ((1 << nib) < n_iter) nib++;
                         const ulonglong2 vids = *reinterpret_cast<const ulonglong2*>(rd->vids);
+                        const int star0 = rd->star0;
                         // the 16 register offsets, packed two per word (kept in 8 registers: re-reading them from
                         // shared memory at store time would serialise every STS behind an LDS)
                         unsigned rw[E / 2];
@@ -496,13 +531,14 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                             // dispatch from the round's packed vid list (one byte per op, two registers pairs):
                             // no shared-memory load on the dispatch path
                             const unsigned char* p = ops;
+                            int slot = star0;
                             unsigned long long v0 = vids.x, v1 = vids.y;
                             for (int o = 0; o < n_ops; o++)
                             {
                                 const int vid = (int)(v0 & 0xffull);
                                 v0 = (v0 >> 8) | (v1 << 56);
                                 v1 >>= 8;
-                                apply_reg_op<MASK>(v, p, vid, sc);
+                                apply_reg_op<MASK>(v, p, vid, slot, sc);
                             }
 #pragma unroll
                             for (int c = 0; c < E; c++) tile[base ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)] = v[c];

@@ -143,6 +143,18 @@ def _apply_reg_op(op, v):
             if not (aux >> j) & 1:
                 v[c] = m[j] * v[c]
         return
+    if code == RC_HAD:  # unscaled butterflies on every register bit of the mask; the scale sits in a dense op of the sweep
+        for pb in range(4):
+            if not (aux >> pb) & 1:
+                continue
+            b = 1 << pb
+            for q in range(E):
+                if q & b:
+                    continue
+                a0, a1 = v[q].copy(), v[q | b].copy()
+                v[q] = a0 + a1
+                v[q | b] = v[q] - 2.0 * a1
+        return
     if code in (RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE1_RR, RC_DENSE1_RI, RC_HAD):
         b = 1 << pos
         d = op["m"]

@@ -17,4 +17,4 @@ for s in p["steps"]:
     for r in d["rounds"]:
         i0 = offs.get(r["first"], 0)
         ops = d["ops"][i0:i0 + r["count"]]
-        print("   round n_iter", r["n_iter"], " ".join(f"{NAMES.get(o['code'], o['code'])}{o['pos'] if o['code'] not in (7, 10) else ''}" + (f"[{bin(o['aux'] & 15).count('1')}]" if o["code"] == 10 else (f"[{8 - bin(o['aux'] & 255).count('1')}]" if o["code"] == 12 else (f"[{16 - bin(o['aux'] & 0xffff).count('1')}]" if o["code"] == 7 else ""))) for o in ops))
+        print("   round n_iter", r["n_iter"], " ".join(f"{NAMES.get(o['code'], o['code'])}{o['pos'] if o['code'] not in (7, 10) else ''}" + (f"[{bin(o["aux"] & 15).count("1")}]" if o["code"] in (10, 11) else (f"[{8 - bin(o['aux'] & 255).count('1')}]" if o["code"] == 12 else (f"[{16 - bin(o['aux'] & 0xffff).count('1')}]" if o["code"] == 7 else ""))) for o in ops))
