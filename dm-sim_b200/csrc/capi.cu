@@ -42,6 +42,7 @@ static int fail(int code, const std::string& msg)
 
 static PlanOptions g_opt;
 static int g_use_graph = 1;
+static int g_sparse_start = 1; // skip the tiles that are still all-zero after dmb_reset_dm (DMB_SPARSE=0 / option "sparse")
 static bool g_opt_init = false;
 static void init_options()
 {
@@ -52,6 +53,7 @@ static void init_options()
     if (const char* e = getenv("DMB_MIN_TILES_LOG2")) g_opt.min_tiles_log2 = atoi(e);
     if (const char* e = getenv("DMB_GRAPH")) g_use_graph = atoi(e);
     if (const char* e = getenv("DMB_CPHASE")) g_opt.cphase = atoi(e) != 0;
+    if (const char* e = getenv("DMB_SPARSE")) g_sparse_start = atoi(e);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -148,6 +150,11 @@ struct dmb_sim
     size_t d_rounds_cap = 0, d_groups_cap = 0;
     cudaGraphExec_t graph_exec = nullptr;
     int graph_cur = -1;
+    // Sparse start: every element whose shard index has a 1 in a physical bit OUTSIDE `support` is exactly zero (after
+    // dmb_reset_dm only element 0 is non-zero: support = 0).  A sweep maps each tile onto itself, so tiles with such a
+    // bit set stay zero and are not launched at all; the sweep adds its tile bits to the support.  Single GPU only.
+    unsigned long long support = ~0ull;
+    unsigned long long graph_support = ~0ull; // support at the start of the captured run
     uint64_t h2d_bytes = 0;
 
     // scratch for results
@@ -208,6 +215,7 @@ int dmb_set_option(const char* name, int64_t value)
     else if (!strcmp(name, "min_tiles_log2")) g_opt.min_tiles_log2 = (int)value;
     else if (!strcmp(name, "graph")) g_use_graph = (int)value;
     else if (!strcmp(name, "cphase")) g_opt.cphase = value != 0;
+    else if (!strcmp(name, "sparse")) g_sparse_start = (int)value;
     else return fail(DMB_EINVAL, std::string("unknown option ") + name);
     return DMB_OK;
 }
@@ -284,6 +292,7 @@ int dmb_reset_dm(dmb_handle s)
     s->conj_flag = false;
     s->non_hermitian = false;
     s->cur = 0;
+    s->support = (s->world == 1 && g_sparse_start) ? 0ull : ~0ull;
     launch_init_state(s->buf[0], s->shard_elems, s->rank == 0, s->stream);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));
@@ -298,6 +307,7 @@ int dmb_set_dm(dmb_handle s, const double* real, const double* imag)
     for (int l = 0; l < s->N; l++) s->layout[l] = l;
     s->conj_flag = false;
     s->non_hermitian = true; // arbitrary input: keep the reference's exact frame semantics from here on
+    s->support = ~0ull;
     const unsigned long long total = 1ull << s->N;
     const unsigned long long chunk = std::min<unsigned long long>(total, 1ull << 24);
     int rc = ensure_scratch(s, chunk * 2 * sizeof(double));
@@ -451,11 +461,27 @@ int dmb_clear_circuit(dmb_handle s)
 }
 
 // ---- execution --------------------------------------------------------------------------------
-static void fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, double2* out, SweepArgs& a)
+static void fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, double2* out, SweepArgs& a,
+                            unsigned long long support = ~0ull)
 {
     memset(&a, 0, sizeof(a));
     const Sweep& sw = s->plan.steps[step].sweep;
     fill_sweep_tables(sw, s->M, a);
+    if (~support & ((s->M >= 64 ? 0ull : (1ull << s->M)) - 1ull))
+    {
+        // sparse start: enumerate only the tiles whose bits outside the tile lie inside the support (in-place sweeps:
+        // cin == cout); the others hold zeros before and after
+        int nc = 0;
+        for (int i = 0; i < a.n_comp; i++)
+            if ((support >> a.cin[i]) & 1ull)
+            {
+                a.cin[nc] = a.cin[i];
+                a.cout[nc] = a.cout[i];
+                nc++;
+            }
+        a.n_comp = nc;
+        a.n_tiles = 1ull << nc;
+    }
     a.in = in;
     a.out = out;
     a.ops = s->d_ops + s->op_offset[step];
@@ -472,9 +498,10 @@ static void fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, do
 }
 
 // enqueue every step of the plan on s->stream; cur is updated as buffers flip
-static int enqueue_steps(dmb_sim* s, int& cur, uint64_t& launches, bool allow_exchange)
+static int enqueue_steps(dmb_sim* s, int& cur, uint64_t& launches, bool allow_exchange, unsigned long long& support)
 {
     size_t comm_idx = 0;
+    if (s->world != 1) support = ~0ull;
     for (size_t i = 0; i < s->plan.steps.size(); i++)
     {
         const Step& st = s->plan.steps[i];
@@ -522,7 +549,9 @@ static int enqueue_steps(dmb_sim* s, int& cur, uint64_t& launches, bool allow_ex
                 out = s->buf[cur ^ 1];
             }
             SweepArgs a;
-            fill_sweep_args(s, i, in, out, a);
+            if (sw.out_of_place) support = ~0ull; // (only multi-GPU remaps permute; kept general)
+            fill_sweep_args(s, i, in, out, a, support);
+            for (int j = 0; j < sw.k; j++) support |= 1ull << sw.in_pos[j];
             const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)sweep_max_grid(a));
             launch_sweep(a, grid, s->stream);
             CU(cudaGetLastError());
@@ -583,7 +612,7 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
     int cur = s->cur;
     if (graphable)
     {
-        if (!s->graph_exec || s->graph_cur != s->cur)
+        if (!s->graph_exec || s->graph_cur != s->cur || s->graph_support != s->support)
         {
             drop_graph(s);
             for (const Step& st : s->plan.steps)
@@ -597,25 +626,31 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
             CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
             int c2 = s->cur;
             uint64_t l2 = 0;
-            int rc = enqueue_steps(s, c2, l2, false);
+            unsigned long long sup2 = s->support;
+            int rc = enqueue_steps(s, c2, l2, false, sup2);
             cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
             if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
             CU(ce);
             CU(cudaGraphInstantiate(&s->graph_exec, graph, 0));
             cudaGraphDestroy(graph);
             s->graph_cur = s->cur;
+            s->graph_support = s->support;
         }
         CU(cudaEventRecord(s->ev_begin, s->stream));
         CU(cudaGraphLaunch(s->graph_exec, s->stream));
         CU(cudaEventRecord(s->ev_end, s->stream));
         launches = s->plan.n_sweeps;
         for (const Step& st : s->plan.steps)
-            if (st.kind == 0 && st.sweep.out_of_place) cur ^= 1;
+        {
+            if (st.kind != 0) continue;
+            if (st.sweep.out_of_place) cur ^= 1;
+            for (int j = 0; j < st.sweep.k; j++) s->support |= 1ull << st.sweep.in_pos[j];
+        }
     }
     else
     {
         CU(cudaEventRecord(s->ev_begin, s->stream));
-        int rc = enqueue_steps(s, cur, launches, true);
+        int rc = enqueue_steps(s, cur, launches, true, s->support);
         if (rc) return rc;
         CU(cudaEventRecord(s->ev_end, s->stream));
     }

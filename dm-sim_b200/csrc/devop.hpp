@@ -70,8 +70,8 @@ struct alignas(16) DevStar
     double phi[2 * kMaxStarOut]; // (re, im)
 };
 static_assert(sizeof(DevStar) == 896, "DevStar layout");
-constexpr int kMaxStarsPerSweep = 160; // 320 bytes of shared memory each (w + la + lb staged once, WO rebuilt per tile)
-constexpr int kStarSmemBytes = 320;
+constexpr int kMaxStarsPerSweep = 160; // 640 bytes of shared memory each: WO[8] (rebuilt per tile) | L[32] = la x lb (once)
+constexpr int kStarSmemBytes = 640;
 
 // Device op stream: 16-byte header + payload (the used part of DevOp::m), 16-byte granularity; a zero header ends it.
 struct alignas(16) DevOpHdr

@@ -277,7 +277,7 @@ __device__ __forceinline__ void r_diagp(double2 (&v)[E], Op op)
 // controlled-phase star: the elements whose register bit p is set get the phase  L_p[lane] * WO_p[iw]
 struct StarCtx
 {
-    const double2* tab; // shared, per slot 20 entries: WO[8] (rebuilt per tile) | la[8] | lb[4] (staged once)
+    const double2* tab; // shared, per slot 40 entries: WO[8] (rebuilt per tile) | L[32] = la x lb per lane (built once)
     int lane, iw;
 };
 constexpr int kStarEntries = kStarSmemBytes / 16;
@@ -294,7 +294,7 @@ __device__ __forceinline__ void r_star(double2 (&v)[E], int mask, int& slot, con
             if ((mask >> (h + q)) & 1)
             {
                 const double2* tb = sc.tab + slot * kStarEntries;
-                ph[q] = cmul(cmul(tb[8 + (sc.lane & 7)], tb[16 + (sc.lane >> 3)]), tb[sc.iw]);
+                ph[q] = cmul(tb[8 + sc.lane], tb[sc.iw]);
                 slot++;
             }
 #pragma unroll
@@ -393,8 +393,12 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
         stage(a.rounds, s_rounds, a.n_rounds * (int)sizeof(DevRound));
         stage(a.groups, s_groups, a.n_groups * (int)sizeof(DevGroup));
         if (DMB_HAS(RC_STAR))
-            for (int i = t; i < a.n_stars * 12; i += NT) // la | lb are contiguous in DevStar
-                s_star[(i / 12) * kStarEntries + 8 + i % 12] = __ldg(reinterpret_cast<const double2*>(a.stars[i / 12].la) + i % 12);
+            for (int i = t; i < a.n_stars * 32; i += NT) // the lane part L[lane] = la[lane & 7] * lb[lane >> 3], once per CTA
+            {
+                const DevStar* st = a.stars + (i >> 5);
+                s_star[(i >> 5) * kStarEntries + 8 + (i & 31)] = cmul(__ldg(reinterpret_cast<const double2*>(st->la) + (i & 7)),
+                                                                      __ldg(reinterpret_cast<const double2*>(st->lb) + ((i & 31) >> 3)));
+            }
     }
 
     // per-thread part of the address maps (the low kThreadBits loop bits come from the thread index)

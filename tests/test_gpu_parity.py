@@ -187,6 +187,33 @@ def test_graph_and_stream_paths_agree(dm):
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
 
 
+@pytest.mark.parametrize("n,tile_bits", [(9, 8), (10, 12), (7, 5)])
+def test_sparse_start_matches_dense_execution(dm, oracle_mod, n, tile_bits):
+    """After dmb_reset_dm only element 0 is non-zero: the leading sweeps launch just the tiles that can hold non-zeros
+    (support tracking, option "sparse").  Bit-identical to launching every tile, also for a second run on the evolved
+    state, and equal to the oracle; a circuit that leaves most qubits untouched exercises the partially grown support."""
+    import importlib
+    circuits = importlib.import_module("dm-sim_b200.circuits")
+    rng = np.random.default_rng(100 + n)
+    cases = [circuits.qft(n), random_gates(n, 40, rng), [("H", [1], 0, 0, 0), ("CX", [1, n - 1], 0, 0, 0), ("T", [0], 0, 0, 0)]]
+    for gates in cases:
+        outs = []
+        for sparse in (1, 0):
+            dm.set_option("sparse", sparse)
+            dm.set_option("tile_bits", tile_bits)
+            try:
+                sim = run_gpu(dm, n, gates)
+                first = sim.get_dm()
+                sim.run()  # second run: dense path, same graph key handling
+                outs.append((first, sim.get_dm()))
+            finally:
+                dm.set_option("sparse", 1); dm.set_option("tile_bits", 12)
+        for a, b in zip(outs[0], outs[1]):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        ore, oim = oracle_mod.Oracle(n).sim(gates).dm()
+        assert max(np.abs(outs[0][0][0] - ore).max(), np.abs(outs[0][0][1] - oim).max()) < TOL
+
+
 def test_large_n13_properties_and_parity(dm, oracle_mod):
     """n = 13 (1 GiB state): full-matrix parity on a short circuit (oracle needs ~4 GiB and a few seconds)."""
     n = 13
