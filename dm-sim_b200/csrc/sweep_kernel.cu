@@ -447,9 +447,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
             }
             else
             {
-#pragma unroll
-                for (int it = 0; it < kMaxIter; it++)
-                    if (it < n_it) cp_async16(&tile[swz((unsigned)(it << kThreadBits)) ^ s_in], src + a.hin[it]);
+#pragma unroll 1 // (small tiles: a rolled loop keeps the kernel's instruction footprint down)
+                for (int it = 0; it < n_it; it++) cp_async16(&tile[swz((unsigned)(it << kThreadBits)) ^ s_in], src + a.hin[it]);
             }
         }
         cp_async_commit();
@@ -575,9 +574,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                 }
                 else
                 {
-#pragma unroll
-                    for (int it = 0; it < kMaxIter; it++)
-                        if (it < n_it) st_stream(reinterpret_cast<double2*>(dst + a.hout[it]), tile[s_out_lo ^ a.hs[it]]);
+#pragma unroll 1
+                    for (int it = 0; it < n_it; it++) st_stream(reinterpret_cast<double2*>(dst + a.hout[it]), tile[s_out_lo ^ a.hs[it]]);
                 }
             }
             else
@@ -586,6 +584,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                 const unsigned long long o_lo = base_out | g_out_lo;
                 const unsigned long long low_mask = (1ull << a.peer_shift) - 1ull;
                 const unsigned long long mine = (unsigned long long)a.peer_rank << a.peer_shift;
+#pragma unroll 1
                 for (int it = 0; it < n_it; it++)
                 {
                     const unsigned long long off = o_lo | (a.hout[it] >> 4);
