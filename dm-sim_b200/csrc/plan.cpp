@@ -666,7 +666,8 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
         }
         else if (strategy == 0)
         {
-            for (size_t i = first_pending; i < ops.size() && n_free_bits > 0; i++) visit(i);
+            const size_t end = std::min(ops.size(), first_pending + (size_t)opt.scan_window);
+            for (size_t i = first_pending; i < end && n_free_bits > 0; i++) visit(i);
         }
         else
         {
@@ -674,7 +675,8 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
             for (int pass = 0; pass < 2; pass++)
             {
                 const int side = pass == 0 ? first_side : 1 - first_side;
-                for (size_t i = first_pending; i < ops.size() && n_free_bits > 0; i++)
+                const size_t end = std::min(ops.size(), first_pending + (size_t)opt.scan_window);
+                for (size_t i = first_pending; i < end && n_free_bits > 0; i++)
                     if (ops[i].side == side) visit(i);
             }
         }
@@ -746,10 +748,14 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
         for (int l = 0; l < N; l++) n_open += in_tile[l] ? 1 : 0;
         long score = 0;
         int n_picked = 0, n_cp = 0;
-        for (size_t i = first_pending; i < ops.size() && n_open > 0; i++)
+        // (a sweep holds at most max_ops ops: looking further than a few thousand pending ops ahead only costs time --
+        // the scans of a 10^4-gate circuit were quadratic without the window)
+        int visited = 0;
+        for (size_t i = first_pending; i < ops.size() && n_open > 0 && visited < opt.scan_window; i++)
         {
             const FlatOp& f = ops[i];
             if (f.done) continue;
+            visited++;
             bool ok = n_picked + (f.cp ? 1 : 8) <= 8 * opt.max_ops && (!f.cp || n_cp < opt.max_cphase);
             if (f.cp)
             {
