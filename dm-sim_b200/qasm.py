@@ -356,3 +356,59 @@ def translate(text: str, module: str = "dmsim_py_omp_wrapper"):
     out.append("\nsim.upload()\nsim.run()\nsim.measure(10)\n")
     stats = {"n_qubits": prog.n_qubits, "basic_gates": prog.gate_num, "cnot_gates": prog.cx_num}
     return "".join(out), stats
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# C++ emitter: the reference's tool/dmsim_qasm_cplus.py (OpenQASM -> a C++ driver on the Simulation API, :308-382) for
+# include/dmsim_b200.hpp.  Same structure (user gates become functions, the main circuit becomes prepare_circuit(),
+# main() = upload / sim / measure(5) / print_measurement), with three repairs: gate functions get typed parameters (the
+# reference emits untyped ones, :286-291), every factory object is deleted after append() copied it (:331-344), and
+# long circuits are PARTITIONED into segments of `segment` statements (the paper's "Partitioner": one huge function
+# takes the C++ compiler minutes).
+def translate_cplus(text: str, header: str = "dmsim_b200.hpp", segment: int = 4096):
+    """Returns (cpp_text, stats) where stats = dict(n_qubits, basic_gates, cnot_gates, segments)."""
+    prog = parse(text)
+    out = ["#include <stdio.h>\n", f'#include "{header}"\n', "//Use the DMSim namespace to enable C++/CUDA APIs\n",
+           "using namespace DMSim;\n\n",
+           "// append() deep-copies the gate: the factory object is released right away\n",
+           "#define DMSIM_APPEND(G) do { Gate* g_ = Simulation::G; sim.append(g_); delete g_; } while (0)\n\n"]
+    body = []  # statements of the main circuit
+    for it in prog.items:
+        if it[0] == "comment":
+            (body if body else out).append("//" + it[1] + "\n")
+        elif it[0] == "gatedef":
+            name = it[1]
+            params, qargs, ops = prog.user_gates[name]
+            s = "void " + name + "(Simulation &sim" + "".join(", const ValType " + p for p in params) + \
+                "".join(", const IdxType " + q for q in qargs) + ")\n{\n"
+            for op, pex, qa in ops:
+                ptxt = [_fmt_param(e, params) for e in pex]
+                ptxt = [re.sub(r"\bpi\b", "PI", p) for p in ptxt]
+                args = ", ".join(ptxt + list(qa))
+                if op in prog.user_gates:
+                    s += "\t" + op + "(sim, " + args + ");\n"
+                else:
+                    s += "\tDMSIM_APPEND(" + op.upper() + "(" + args + "));\n"
+            out.append(s + "}\n\n")
+        else:
+            _, op, pex, qargs = it
+            ptxt = [repr(float(_eval_raw(e))) for e in pex]
+            for qubits in _broadcast(prog, qargs):
+                args = ", ".join(ptxt + [str(q) for q in qubits])
+                if op in prog.user_gates:
+                    body.append("\t" + op + "(sim, " + args + ");\n")
+                else:
+                    body.append("\tDMSIM_APPEND(" + op.upper() + "(" + args + "));\n")
+    segment = max(1, int(segment))
+    n_seg = max(1, (len(body) + segment - 1) // segment)
+    if n_seg == 1:
+        out.append("void prepare_circuit(Simulation &sim)\n{\n" + "".join(body) + "}\n\n")
+    else:
+        for k in range(n_seg):
+            out.append(f"static void prepare_circuit_{k}(Simulation &sim)\n{{\n" + "".join(body[k * segment:(k + 1) * segment]) + "}\n\n")
+        out.append("void prepare_circuit(Simulation &sim)\n{\n" + "".join(f"\tprepare_circuit_{k}(sim);\n" for k in range(n_seg)) + "}\n\n")
+    out.append("int main()\n{\n\tsrand(RAND_SEED);\n\tint n_qubits=" + str(prog.n_qubits) + ";\n\tint n_gpus=1;\n"
+               "\tSimulation sim(n_qubits, n_gpus);\n\tprepare_circuit(sim);\n\tsim.upload();\n\tsim.sim();\n"
+               "\tauto* res = sim.measure(5);\n\tprint_measurement(res, n_qubits, 5);\n\tdelete[] res;\n\treturn 0;\n}\n")
+    stats = {"n_qubits": prog.n_qubits, "basic_gates": prog.gate_num, "cnot_gates": prog.cx_num, "segments": n_seg}
+    return "".join(out), stats

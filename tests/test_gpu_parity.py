@@ -327,6 +327,27 @@ def test_xacc_plugin_backend_runs(dm, tmp_path):
     assert "DM-Sim" not in r.stdout  # the XACC runners silence the per-sim() summary line
 
 
+def test_cplus_translator_output_runs(dm, tmp_path):
+    """OpenQASM -> C++ driver (tool/dmsim_qasm_cplus.py) -> built against the drop-in header -> run: a deterministic
+    circuit with a user-defined gate prints the expected basis state 5 times (MSB first, as print_measurement does)."""
+    import importlib
+    import subprocess
+    qasm = importlib.import_module("dm-sim_b200.qasm")
+    text = ("OPENQASM 2.0;\ninclude \"qelib1.inc\";\nqreg q[4];\ngate flip2 a, b { x a; cx a, b; }\n"
+            "flip2 q[0], q[1];\nccx q[0], q[1], q[3];\nh q[2];\nh q[2];\n")
+    cpp, stats = qasm.translate_cplus(text, segment=2)
+    assert stats["segments"] == 2
+    root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    lib = _os.path.join(root, "dm-sim_b200", "lib")
+    src, exe = tmp_path / "c.cpp", tmp_path / "c"
+    src.write_text(cpp)
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-I", _os.path.join(root, "include"), str(src), "-o", str(exe),
+                    "-L", lib, "-ldmsim_b200", "-Wl,-rpath," + lib], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("1011") == 5, r.stdout   # qubits 0, 1, 3 set
+
+
 def test_pybind_module_runs_a_generated_script(dm, tmp_path):
     """tool/dmsim_qasm.py output executed with the drop-in pybind11 module, as the reference's workflow does."""
     import subprocess

@@ -129,3 +129,30 @@ def test_qasm_circuit_against_oracle(dm, oracle_mod):
     v0 = np.zeros(4 ** n, dtype=np.complex128); v0[0] = 1
     out = ke.run_plan_dev(dm.plan_json(n, 1, g), v0)
     assert np.abs(out - (re + 1j * im).reshape(-1)).max() < 1e-12
+
+
+def test_cplus_translator_emits_a_buildable_driver(tmp_path):
+    """tool/dmsim_qasm_cplus.py (reference tool/dmsim_qasm_cplus.py:308-382): user gates become typed functions, the
+    main circuit prepare_circuit() -- split into segments when long --, same statistics; the program compiles and links
+    against the drop-in header."""
+    cpp, stats = qasm.translate_cplus(SMALL, segment=3)
+    assert stats["n_qubits"] == 5 and stats["segments"] == 3
+    _, py_stats = qasm.translate(SMALL)
+    assert (stats["basic_gates"], stats["cnot_gates"]) == (py_stats["basic_gates"], py_stats["cnot_gates"])
+    assert "void foo(Simulation &sim, const ValType theta, const ValType phi, const IdxType x, const IdxType y)" in cpp
+    assert "DMSIM_APPEND(U3(theta, phi, 1.5707963267948966, x));" in cpp and "DMSIM_APPEND(RZ(-theta/2, y));" in cpp
+    assert "\tfoo(sim, 1.0471975511965976, 0.25, 1, 4);" in cpp
+    assert cpp.count("DMSIM_APPEND(H(") == 2 and "DMSIM_APPEND(CX(1, 3));" in cpp       # broadcast over the register
+    assert "prepare_circuit_2(sim);" in cpp and "int n_qubits=5;" in cpp
+    src = tmp_path / "c.cpp"
+    src.write_text(cpp)
+    lib = os.path.join(ROOT, "dm-sim_b200", "lib")
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o",
+                    str(tmp_path / "c"), "-L", lib, "-ldmsim_b200", "-Wl,-rpath," + lib], check=True)
+    out = tmp_path / "cli.cpp"
+    q = tmp_path / "in.qasm"
+    q.write_text(SMALL)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tool", "dmsim_qasm_cplus.py"), "-i", str(q), "-o", str(out)],
+                       capture_output=True, text=True, check=True)
+    assert "Number of qubits: 5" in r.stdout and "Number of basic gates: " + str(stats["basic_gates"]) in r.stdout
+    assert "void prepare_circuit(Simulation &sim)" in out.read_text()
