@@ -309,6 +309,75 @@ void swap_roles(const cplx* m, cplx* o)
 bool is_identity2(const cplx* u) { return u[0] == cplx(1) && u[3] == cplx(1) && u[1] == cplx(0) && u[2] == cplx(0); }
 } // namespace
 
+// Peephole on the primitive list: on a wire t,  H_t  CX(c1,t) ... CX(ck,t)  H_t  ==  CZ(c1,t) ... CZ(ck,t)
+// (H X H = Z, inserted pairwise: H CX H = CZ), when nothing else touches t between the two Hadamards.  The CZs are
+// diagonal: they become controlled phases that need only ONE of their bits in a tile / register round, instead of
+// register permutations that need both (Bernstein-Vazirani, parity / fan-in circuits).  Exact as an operator identity
+// (H H = 1 up to one rounding of 2 * S2I^2), valid for any state; circuits with SRN are left alone.
+void rewrite_hadamard_cx(int n, std::vector<Block>& prims)
+{
+    for (const Block& p : prims)
+        if (p.srn) return;
+    auto is_h = [](const Block& b) {
+        return b.nq == 1 && b.m[0] == cplx(kS2I, 0) && b.m[1] == cplx(kS2I, 0) && b.m[2] == cplx(kS2I, 0) && b.m[3] == cplx(-kS2I, 0);
+    };
+    auto is_cx_onto = [](const Block& b, int t) { // CX exactly as Expander::cx builds it, target t
+        if (b.nq != 2 || b.q[1] != t) return false;
+        for (int i = 0; i < 16; i++)
+            if (b.m[i] != cplx((i == 0 || i == 5 || i == 11 || i == 14) ? 1.0 : 0.0, 0.0)) return false;
+        return true;
+    };
+    std::vector<char> drop(prims.size(), 0);
+    std::vector<int> open_h(n, -1);             // index of a Hadamard on this wire that may start a pattern
+    std::vector<std::vector<int>> fan(n);       // the CXs onto the wire since that Hadamard
+    for (size_t i = 0; i < prims.size(); i++)
+    {
+        Block& b = prims[i];
+        if (is_h(b))
+        {
+            const int t = b.q[0];
+            if (open_h[t] >= 0 && !fan[t].empty())
+            {
+                int w = prims[open_h[t]].weight + b.weight; // keep the primitive count of the sweep statistics
+                for (int j : fan[t])
+                {
+                    Block& c = prims[j];
+                    for (auto& e : c.m) e = 0;
+                    c.m[0] = c.m[5] = c.m[10] = 1;
+                    c.m[15] = -1;
+                    c.weight += w;
+                    w = 0;
+                }
+                drop[open_h[t]] = 1;
+                drop[i] = 1;
+                open_h[t] = -1;
+                fan[t].clear();
+                continue;
+            }
+            open_h[t] = (int)i;
+            fan[t].clear();
+            continue;
+        }
+        for (int k = 0; k < b.nq; k++)
+        {
+            const int q = b.q[k];
+            if (open_h[q] < 0) continue;
+            if (is_cx_onto(b, q)) fan[q].push_back((int)i);
+            else
+            {
+                // anything else on the wire ends its pattern (also being the CONTROL of a CX: diagonal on this wire,
+                // it does not commute with the Hadamards)
+                open_h[q] = -1;
+                fan[q].clear();
+            }
+        }
+    }
+    size_t o = 0;
+    for (size_t i = 0; i < prims.size(); i++)
+        if (!drop[i]) prims[o++] = prims[i];
+    prims.resize(o);
+}
+
 void fuse_blocks(int n, const std::vector<Block>& prims, std::vector<Block>& blocks, bool split_cphase)
 {
     struct Pend { bool have = false; cplx u[4]; int weight = 0; };
@@ -527,6 +596,7 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
     std::vector<Block> prims, blocks;
     expand_gates(n, gates, n_gates, mats, n_mats, prims);
     plan.n_primitives = prims.size();
+    if (opt.cphase) rewrite_hadamard_cx(n, prims);
     fuse_blocks(n, prims, blocks, opt.cphase);
     plan.n_blocks = blocks.size();
 
