@@ -68,6 +68,48 @@ for rep in sorted(glob.glob(os.path.join(G, f"{tag}_sweep_full_*.ncu-rep"))):
         f.write("\n".join(txt) + "\n")
     print("ncu summary:", wl, "traffic/launch", traffic[wl])
 json.dump(traffic, open(traffic_path, "w"), indent=1)
+# ---- profiles/README.md: index + table of the round's bench lines
+def row(d):
+    r, e = d.get("roofline") or {}, d.get("e2e") or {}
+    cfg = d.get("config", {})
+    if d.get("impl") == "reference":
+        return f"| {cfg.get('workload')} (reference `dmsim_cpu_omp`, {d['cpu_baseline']['cores']} host threads) | {d['n_gpus']} | – | {d['ms_per_step']:.0f} | {d['value']:.2f} | – | – | – | {d['cpu_baseline']['sample']} |"
+    res = (e.get("resident_state") or {}).get("ms_per_step")
+    return (f"| {cfg.get('workload')} | {d['n_gpus']} | {cfg.get('sweeps_per_step')} | {d['ms_per_step']:.2f} | {d['value']:.0f} | "
+            f"{r.get('achieved', 0):.0f} ({r.get('frac', 0):.3f}) | {e.get('ms_per_step', 0):.2f} ({e.get('value', 0):.0f}) | "
+            f"{'' if res is None else format(res, '.2f')} | {(d.get('comm') or {}).get('GBps_per_direction') or ''} |")
+
+md = ["# profiles/ -- measured on B200 (round 1)", "",
+      "Every number here was printed by `bench.py` / `ncu` on a `gpurun` B200 box; nothing is taken under a profiler except",
+      "the ncu files themselves. `value` = device time of `dmb_run` on the DENSE resident state (CUDA events on the engine's",
+      "stream); `e2e` = wall clock of reset + circuit upload + run + diagonal readback from |0><0| (sparse start on, single",
+      "GPU); `resident e2e` = the same calls without the reset, on the dense state.", "",
+      "| workload | GPUs | sweeps/step | ms/step | gates/s | achieved GB/s (frac of measured HBM peak) | e2e ms (gates/s) | resident e2e ms | exchange GB/s per direction |",
+      "|---|---|---|---|---|---|---|---|---|"]
+seen = set()
+for f in sorted(glob.glob(os.path.join(P, "*bench_lines*.jsonl"))):
+    if "older_kernel" in f or (os.path.basename(f).startswith("r1_bench_lines_1gpu") and lines):
+        continue
+    for l in open(f):
+        l = l.strip()
+        if l.startswith("{"):
+            d = json.loads(l)
+            key = (d["config"]["workload"], d["n_gpus"], d.get("impl"), os.path.basename(f))
+            if key not in seen:
+                seen.add(key)
+                md.append(row(d))
+md += ["", "Files:", ""]
+for f in sorted(os.listdir(P)):
+    if f != "README.md":
+        md.append(f"* `{f}`")
+md += ["", "`*_sweep_full_<workload>.txt`: per-launch key metrics of `ncu --set full --clock-control none --import-source on` on",
+       "consecutive `sweep_kernel` launches, then the executed SASS of the first launch by opcode and by basic block with the",
+       "stall reasons (tools/ncu_sass_summary.py, tools/ncu_blocks.py). `*_launches_*.csv`: the ncu launch list",
+       "(`--metrics gpu__time_duration.sum`) of `bench.py --steps 2 --warmup 1`. `ncu_traffic.json`: DRAM bytes per launch.",
+       "`r1_bench_lines_8gpu_nccl_path_older_kernel.jsonl`: the 8-GPU lines of an earlier session (NCCL exchange, sweep kernel",
+       "before this session's rewrite); 2- and 4-GPU lines are from this session (peer-memory remap)."]
+open(os.path.join(P, "README.md"), "w").write("\n".join(md) + "\n")
+print("README.md rows:", len(seen))
 for f in glob.glob(os.path.join(G, f"{tag}_launches_*.csv")):
     dst = os.path.join(P, os.path.basename(f).replace(tag, out, 1))
     open(dst, "w").write(open(f).read())
