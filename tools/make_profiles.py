@@ -88,7 +88,7 @@ md = ["# profiles/ -- measured on B200 (round 1)", "",
       "|---|---|---|---|---|---|---|---|---|"]
 seen = set()
 for f in sorted(glob.glob(os.path.join(P, "*bench_lines*.jsonl"))):
-    if "older_kernel" in f or (os.path.basename(f).startswith("r1_bench_lines_1gpu") and lines):
+    if "older_kernel" in f:
         continue
     for l in open(f):
         l = l.strip()
