@@ -17,6 +17,7 @@ from __future__ import annotations
 import ctypes
 import json
 import os
+import sys
 
 import numpy as np
 
@@ -84,6 +85,7 @@ def lib():
     L.dmb_comm_init.argtypes = [vp, vp]
     L.dmb_comm_export.argtypes = [vp, vp]
     L.dmb_comm_import.argtypes = [vp, vp]
+    L.dmb_comm_p2p.argtypes = [vp, i32]
     L.dmb_get_shard.argtypes = [vp, vp, vp]
     L.dmb_plan_json.argtypes = [i32, i32, vp, sz, vp, sz, vp, i32, ctypes.c_char_p, sz]
     L.dmb_plan_json.restype = ctypes.c_int64
@@ -207,17 +209,24 @@ class Simulation:
         dist.broadcast_object_list(obj, src=0)
         ident = np.frombuffer(obj[0], dtype=np.uint8).copy()
         _check(lib().dmb_comm_init(self._h, ident.ctypes.data))
-        del torch
-        # peer-memory exchange (fused pack + all-to-all over NVLink); DMB_P2P=0 keeps the NCCL send/recv path
+        # peer-memory exchange (fused pack + all-to-all over NVLink); DMB_P2P=0 keeps the NCCL send/recv path.  Every
+        # rank must end up with the same form: the outcome of the import is agreed on collectively.
         self.p2p = False
         if os.environ.get("DMB_P2P", "1") != "0":
             mine = np.zeros(128, dtype=np.uint8)
-            _check(lib().dmb_comm_export(self._h, mine.ctypes.data))
+            ok = lib().dmb_comm_export(self._h, mine.ctypes.data) == 0
             everyone = [None] * self.n_gpus
             dist.all_gather_object(everyone, mine.tobytes())
             blob = np.frombuffer(b"".join(everyone), dtype=np.uint8).copy()
-            _check(lib().dmb_comm_import(self._h, blob.ctypes.data))
-            self.p2p = True
+            ok = ok and lib().dmb_comm_import(self._h, blob.ctypes.data) == 0
+            why = "" if ok else lib().dmb_last_error().decode()
+            flag = torch.tensor([1 if ok else 0], device="cuda", dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            self.p2p = bool(int(flag.item()))
+            _check(lib().dmb_comm_p2p(self._h, 1 if self.p2p else 0))
+            if not self.p2p and self.rank == 0:
+                print(f"dmsim_b200: peer-memory remap unavailable ({why or 'another rank failed'}); using NCCL send/recv",
+                      file=sys.stderr)
 
     def __del__(self):
         h = getattr(self, "_h", None)

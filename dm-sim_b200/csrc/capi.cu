@@ -889,6 +889,14 @@ int dmb_comm_import(dmb_handle s, const uint8_t* all_handles)
     return DMB_OK;
 }
 
+int dmb_comm_p2p(dmb_handle s, int enable)
+{
+    if (!s) return fail(DMB_EINVAL, "null handle");
+    if (enable && !s->d_barrier) return fail(DMB_ESTATE, "dmb_comm_p2p(1) needs a successful dmb_comm_import first");
+    s->p2p = enable != 0;
+    return DMB_OK;
+}
+
 // ---- planner introspection (host only) ----------------------------------------------------------
 int64_t dmb_plan_json(int n_qubits, int world_size, const dmb_gate* gates, size_t n_gates, const double* mats,
                       size_t n_mats, const int32_t* start_layout, int conj_state, char* out, size_t cap)

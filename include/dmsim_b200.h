@@ -131,6 +131,9 @@ int dmb_comm_init(dmb_handle h, const uint8_t id[128]);
  * the cross-GPU barrier.  Without it the remap is pack sweep + ncclSend/ncclRecv. */
 int dmb_comm_export(dmb_handle h, uint8_t out[128]);
 int dmb_comm_import(dmb_handle h, const uint8_t* all_handles);
+/* Switches the peer-memory form of the remap on (only after a successful dmb_comm_import) or off.  EVERY rank must use
+ * the same form: a host that could not import the handles on some rank calls dmb_comm_p2p(h, 0) on all of them. */
+int dmb_comm_p2p(dmb_handle h, int enable);
 /* Raw shard + layout, for tests and host-side gathers: copies the local shard (interleaved complex,
  * 2 * 4^n / world_size doubles, PHYSICAL order) and the logical->physical bit map (2n ints). */
 int dmb_get_shard(dmb_handle h, double* interleaved, int32_t* phys_of_logical);
