@@ -309,11 +309,14 @@ void swap_roles(const cplx* m, cplx* o)
 bool is_identity2(const cplx* u) { return u[0] == cplx(1) && u[3] == cplx(1) && u[1] == cplx(0) && u[2] == cplx(0); }
 } // namespace
 
-// Peephole on the primitive list: on a wire t,  H_t  CX(c1,t) ... CX(ck,t)  H_t  ==  CZ(c1,t) ... CZ(ck,t)
-// (H X H = Z, inserted pairwise: H CX H = CZ), when nothing else touches t between the two Hadamards.  The CZs are
-// diagonal: they become controlled phases that need only ONE of their bits in a tile / register round, instead of
-// register permutations that need both (Bernstein-Vazirani, parity / fan-in circuits).  Exact as an operator identity
-// (H H = 1 up to one rounding of 2 * S2I^2), valid for any state; circuits with SRN are left alone.
+// Peephole on the primitive list.  With H X H = Z inserted pairwise (H CX(c,t) H = CZ(c,t) for H on the TARGET wire t):
+//   H_t  CX(c1,t) ... CX(ck,t)  H_t   ==  CZ(c1,t) ... CZ(ck,t)                 (both Hadamards vanish)
+//   H_t  CX(c1,t) ... CX(ck,t)        ==  CZ(c1,t) ... CZ(ck,t)  H_t            (the Hadamard moves behind a fan with
+//                                                                                 at least two different controls)
+// when nothing else touches t in between.  The CZs are diagonal: they become controlled phases that need only ONE of
+// their bits in a tile / register round, instead of register permutations that need both (Bernstein-Vazirani, parity /
+// fan-in circuits; the reference builds CZ itself as H CX H, :1493-1499).  Exact operator identities (H H = 1 up to one
+// rounding of 2 * S2I^2), valid for any state; circuits with SRN are left alone.
 void rewrite_hadamard_cx(int n, std::vector<Block>& prims)
 {
     for (const Block& p : prims)
@@ -328,26 +331,44 @@ void rewrite_hadamard_cx(int n, std::vector<Block>& prims)
         return true;
     };
     std::vector<char> drop(prims.size(), 0);
+    std::vector<std::pair<int, Block>> moved;   // Hadamards re-inserted AFTER primitive index .first
     std::vector<int> open_h(n, -1);             // index of a Hadamard on this wire that may start a pattern
     std::vector<std::vector<int>> fan(n);       // the CXs onto the wire since that Hadamard
+    auto to_cz = [&](int t, int extra_weight) {
+        for (int j : fan[t])
+        {
+            Block& c = prims[j];
+            for (auto& e : c.m) e = 0;
+            c.m[0] = c.m[5] = c.m[10] = 1;
+            c.m[15] = -1;
+            c.weight += extra_weight; // keep the primitive count of the sweep statistics
+            extra_weight = 0;
+        }
+    };
+    auto end_pattern = [&](int t) { // something else arrives on wire t (or the circuit ends): second identity
+        // only for a real fan (two or more DIFFERENT controls): a single CX after H is left to the pair fusion, which
+        // often finds more structure there (H | CX U1 CX U1 = H | controlled phase)
+        bool real_fan = false;
+        for (size_t j = 1; j < fan[t].size(); j++)
+            if (prims[fan[t][j]].q[0] != prims[fan[t][0]].q[0]) real_fan = true;
+        if (open_h[t] >= 0 && real_fan)
+        {
+            to_cz(t, 0);
+            moved.push_back({fan[t].back(), prims[open_h[t]]});
+            drop[open_h[t]] = 1;
+        }
+        open_h[t] = -1;
+        fan[t].clear();
+    };
     for (size_t i = 0; i < prims.size(); i++)
     {
         Block& b = prims[i];
         if (is_h(b))
         {
             const int t = b.q[0];
-            if (open_h[t] >= 0 && !fan[t].empty())
+            if (open_h[t] >= 0 && !fan[t].empty()) // first identity
             {
-                int w = prims[open_h[t]].weight + b.weight; // keep the primitive count of the sweep statistics
-                for (int j : fan[t])
-                {
-                    Block& c = prims[j];
-                    for (auto& e : c.m) e = 0;
-                    c.m[0] = c.m[5] = c.m[10] = 1;
-                    c.m[15] = -1;
-                    c.weight += w;
-                    w = 0;
-                }
+                to_cz(t, prims[open_h[t]].weight + b.weight);
                 drop[open_h[t]] = 1;
                 drop[i] = 1;
                 open_h[t] = -1;
@@ -363,19 +384,20 @@ void rewrite_hadamard_cx(int n, std::vector<Block>& prims)
             const int q = b.q[k];
             if (open_h[q] < 0) continue;
             if (is_cx_onto(b, q)) fan[q].push_back((int)i);
-            else
-            {
-                // anything else on the wire ends its pattern (also being the CONTROL of a CX: diagonal on this wire,
-                // it does not commute with the Hadamards)
-                open_h[q] = -1;
-                fan[q].clear();
-            }
+            else end_pattern(q); // (also being the CONTROL of a CX: diagonal on this wire, it does not commute with H)
         }
     }
-    size_t o = 0;
+    for (int t = 0; t < n; t++) end_pattern(t);
+    std::stable_sort(moved.begin(), moved.end(), [](const std::pair<int, Block>& a, const std::pair<int, Block>& b) { return a.first < b.first; });
+    std::vector<Block> out;
+    out.reserve(prims.size());
+    size_t mi = 0;
     for (size_t i = 0; i < prims.size(); i++)
-        if (!drop[i]) prims[o++] = prims[i];
-    prims.resize(o);
+    {
+        if (!drop[i]) out.push_back(prims[i]);
+        while (mi < moved.size() && moved[mi].first == (int)i) out.push_back(moved[mi++].second);
+    }
+    prims.swap(out);
 }
 
 void fuse_blocks(int n, const std::vector<Block>& prims, std::vector<Block>& blocks, bool split_cphase)
@@ -458,6 +480,10 @@ void fuse_blocks(int n, const std::vector<Block>& prims, std::vector<Block>& blo
             if (open[q] >= 0 && classify(1, p.m, nullptr) == CLS_DENSE1 &&
                 classify(2, work[open[q]].m, nullptr) != CLS_DENSE2)
                 close_block(open[q]);
+            // likewise a monomial 1-qubit gate (X, Y) stays out of a DIAGONAL 2-qubit block: the block would stop being
+            // a controlled phase (which needs only one of its bits in a tile)
+            if (open[q] >= 0 && classify(1, p.m, nullptr) != CLS_DIAG1 && classify(2, work[open[q]].m, nullptr) == CLS_DIAG2)
+                close_block(open[q]);
             if (open[q] >= 0)
             {
                 Block& b = work[open[q]];
@@ -493,14 +519,15 @@ void fuse_blocks(int n, const std::vector<Block>& prims, std::vector<Block>& blo
         close_block(open[a]);
         close_block(open[b_]);
         Block nb = p;
-        const bool nb_dense = classify(2, p.m, nullptr) == CLS_DENSE2;
+        const bool nb_dense = classify(2, p.m, nullptr) == CLS_DENSE2, nb_diag = classify(2, p.m, nullptr) == CLS_DIAG2;
         for (int side = 0; side < 2; side++)
         {
             const int q = side == 0 ? a : b_;
             if (!pend[q].have) continue;
-            if (!nb_dense && classify(1, pend[q].u, nullptr) == CLS_DENSE1)
+            const int pc = classify(1, pend[q].u, nullptr);
+            if ((!nb_dense && pc == CLS_DENSE1) || (nb_diag && pc != CLS_DIAG1))
             {
-                flush_pending(q); // keep the dense 1-qubit product as its own block (see above)
+                flush_pending(q); // keep the 1-qubit product as its own block (see above)
                 continue;
             }
             if (!is_identity2(pend[q].u))

@@ -228,3 +228,40 @@ def test_deferred_diagonals_and_new_device_ops(dm, oracle_mod):
             assert r["count"] <= 16
         split |= any(a["roff"] == b["roff"] and a["lane_tab"] == b["lane_tab"] and a["count"] == 16 for a, b in zip(rounds, rounds[1:]))
     assert split
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_hadamard_cx_fans_become_controlled_phases(dm, oracle_mod, world):
+    """rewrite_hadamard_cx: H_t CX(c_i,t).. H_t -> CZ(c_i,t)..  and  H_t CX(c_i,t).. -> CZ(c_i,t).. H_t for fans with
+    two or more controls (Bernstein-Vazirani); a monomial 1-qubit gate is kept out of a diagonal 2-qubit block.  Same
+    state as the oracle, and the device programs contain controlled phases instead of register permutations."""
+    import importlib
+    circuits = importlib.import_module("dm-sim_b200.circuits")
+    n = 6
+    cases = {
+        "bv": circuits.bv(n),
+        "closed_fan": [("H", [q], 0, 0, 0) for q in range(n)] + [("CX", [q, n - 1], 0, 0, 0) for q in range(3)] +
+                      [("H", [n - 1], 0, 0, 0), ("T", [n - 1], 0, 0, 0), ("H", [0], 0, 0, 0)],
+        "fan_then_control": [("H", [2], 0, 0, 0), ("CX", [0, 2], 0, 0, 0), ("CX", [1, 2], 0, 0, 0), ("CX", [2, 3], 0, 0, 0),
+                             ("RY", [2], 0.4, 0, 0), ("H", [0], 0, 0, 0)],
+        "single_cx_untouched": [("H", [1], 0, 0, 0), ("CU1", [0, 1], 0, 0, 0.7), ("X", [1], 0, 0, 0), ("CZ", [0, 1], 0, 0, 0)],
+    }
+    for name, gates in cases.items():
+        re, im = oracle_mod.Oracle(n).sim(gates).dm()
+        ref = to_complex(re, im)
+        plan = dm.plan_json(n, world, gates)
+        assert np.abs(pe.run_plan(plan, zero_state(n)) - ref).max() < TOL, name
+        assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - ref).max() < TOL, name
+        dev_codes = [o["code"] for st in plan["steps"] if st["kind"] == "sweep" for o in st["dev"]["ops"]]
+        n_cp = sum(1 for st in plan["steps"] if st["kind"] == "sweep" for op in st["ops"] if op["cls"] == 7)
+        if name in ("bv", "closed_fan"):
+            assert n_cp >= 3 and 6 not in dev_codes, (name, dev_codes)   # 6 = RC_PERM2
+    # with the controlled-phase machinery switched off the circuits are left as they are
+    dm.set_option("cphase", 0)
+    try:
+        plan0 = dm.plan_json(n, 1, cases["bv"])
+        assert 6 in [o["code"] for st in plan0["steps"] for o in st["dev"]["ops"]]
+        re, im = oracle_mod.Oracle(n).sim(cases["bv"]).dm()
+        assert np.abs(ke.run_plan_dev(plan0, zero_state(n)) - to_complex(re, im)).max() < TOL
+    finally:
+        dm.set_option("cphase", 1)
