@@ -312,12 +312,13 @@ bool is_identity2(const cplx* u) { return u[0] == cplx(1) && u[3] == cplx(1) && 
 // Peephole on the primitive list.  With H X H = Z inserted pairwise (H CX(c,t) H = CZ(c,t) for H on the TARGET wire t):
 //   H_t  CX(c1,t) ... CX(ck,t)  H_t   ==  CZ(c1,t) ... CZ(ck,t)                 (both Hadamards vanish)
 //   H_t  CX(c1,t) ... CX(ck,t)        ==  CZ(c1,t) ... CZ(ck,t)  H_t            (the Hadamard moves behind a fan with
-//                                                                                 at least two different controls)
+//                                                                                 at least two different controls; off by
+//                                                                                 default, option "move_h")
 // when nothing else touches t in between.  The CZs are diagonal: they become controlled phases that need only ONE of
 // their bits in a tile / register round, instead of register permutations that need both (Bernstein-Vazirani, parity /
 // fan-in circuits; the reference builds CZ itself as H CX H, :1493-1499).  Exact operator identities (H H = 1 up to one
 // rounding of 2 * S2I^2), valid for any state; circuits with SRN are left alone.
-void rewrite_hadamard_cx(int n, std::vector<Block>& prims)
+void rewrite_hadamard_cx(int n, std::vector<Block>& prims, bool move_h)
 {
     for (const Block& p : prims)
         if (p.srn) return;
@@ -346,12 +347,13 @@ void rewrite_hadamard_cx(int n, std::vector<Block>& prims)
         }
     };
     auto end_pattern = [&](int t) { // something else arrives on wire t (or the circuit ends): second identity
-        // only for a real fan (two or more DIFFERENT controls): a single CX after H is left to the pair fusion, which
-        // often finds more structure there (H | CX U1 CX U1 = H | controlled phase)
+        // The second identity,  H_t CX(c1,t) .. CX(ck,t) == CZ(c1,t) .. CZ(ck,t) H_t,  is implemented (opt.move_h) but off:
+        // measured on bv_n15 it trades k register permutations for k single-bit stars at about the same cost (45.2 vs
+        // 43.0 ms) and makes the sparse start less effective (the target bit enters the first sweep).
         bool real_fan = false;
         for (size_t j = 1; j < fan[t].size(); j++)
             if (prims[fan[t][j]].q[0] != prims[fan[t][0]].q[0]) real_fan = true;
-        if (open_h[t] >= 0 && real_fan)
+        if (move_h && open_h[t] >= 0 && real_fan)
         {
             to_cz(t, 0);
             moved.push_back({fan[t].back(), prims[open_h[t]]});
@@ -623,7 +625,7 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
     std::vector<Block> prims, blocks;
     expand_gates(n, gates, n_gates, mats, n_mats, prims);
     plan.n_primitives = prims.size();
-    if (opt.cphase) rewrite_hadamard_cx(n, prims);
+    if (opt.cphase) rewrite_hadamard_cx(n, prims, opt.move_h);
     fuse_blocks(n, prims, blocks, opt.cphase);
     plan.n_blocks = blocks.size();
 

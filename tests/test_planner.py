@@ -238,6 +238,7 @@ def test_hadamard_cx_fans_become_controlled_phases(dm, oracle_mod, world):
     import importlib
     circuits = importlib.import_module("dm-sim_b200.circuits")
     n = 6
+    dm.set_option("move_h", 1)   # the second identity is off by default (see plan.cpp)
     cases = {
         "bv": circuits.bv(n),
         "closed_fan": [("H", [q], 0, 0, 0) for q in range(n)] + [("CX", [q, n - 1], 0, 0, 0) for q in range(3)] +
@@ -257,6 +258,7 @@ def test_hadamard_cx_fans_become_controlled_phases(dm, oracle_mod, world):
         if name in ("bv", "closed_fan"):
             assert n_cp >= 3 and 6 not in dev_codes, (name, dev_codes)   # 6 = RC_PERM2
     # with the controlled-phase machinery switched off the circuits are left as they are
+    dm.set_option("move_h", 0)
     dm.set_option("cphase", 0)
     try:
         plan0 = dm.plan_json(n, 1, cases["bv"])
