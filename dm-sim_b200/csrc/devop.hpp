@@ -49,6 +49,8 @@ enum RegOpCode : int32_t
                       // element whose other three register bits spell j; skip mask (unit entries) in aux bits 0..7
     RC_CP2 = 13,      // one controlled phase between two register bits: the 4 elements with both bits set are multiplied
                       // by m[0]; `pos` as for the other two-bit ops
+    RC_QFT2 = 14,     // butterfly on the LOWER register bit of the pair, controlled phase m[0] between the two, butterfly on
+                      // the HIGHER bit: the radix-4 step of a QFT round as ONE dispatch (`pos` as for the two-bit ops)
     RC_STAR = 10      // controlled-phase star: for every register bit p in aux bits 0..3, the elements with that bit set
                       // are multiplied by  L_p[lane] * WO_p[warp, iteration]  (DevStar slot star[p]): the product of the
                       // phases of all controlled-phase ops between register bit p and the partner bits that are set in
@@ -84,7 +86,7 @@ struct alignas(16) DevOpHdr
 // The kernel's jump-table index of an op: dense over (code, position) -- and over the register-bit MASK for RC_HAD and
 // RC_STAR, so that those two need no header read at all.
 constexpr int kVidDense2 = 0, kVidPerm2 = 6, kVidCp2 = 12, kVidDense1 = 18, kVidRR = 22, kVidRI = 26, kVidMono1 = 30,
-              kVidSrn1 = 34, kVidDiagP = 38, kVidDiagR = 42, kVidHad = 43, kVidStar = 58, kNumVids = 73;
+              kVidSrn1 = 34, kVidDiagP = 38, kVidDiagR = 42, kVidQft2 = 43, kVidHad = 49, kVidStar = 64, kNumVids = 79;
 constexpr int dev_vid(int code, int pos, int aux)
 {
     switch (code)
@@ -99,6 +101,7 @@ constexpr int dev_vid(int code, int pos, int aux)
     case RC_SRN1: return kVidSrn1 + pos;
     case RC_DIAGP: return kVidDiagP + pos;
     case RC_DIAGR: return kVidDiagR;
+    case RC_QFT2: return kVidQft2 + pos;
     case RC_HAD: return kVidHad + (aux & 15) - 1;
     case RC_STAR: return kVidStar + (aux & 15) - 1;
     default: return kNumVids;
@@ -115,6 +118,7 @@ constexpr int dev_op_payload_bytes(int code)
     case RC_DIAGR: return 256;
     case RC_DIAGP: return 128;
     case RC_CP2: return 16;
+    case RC_QFT2: return 16;
     case RC_DENSE1_RR: return 32;
     case RC_DENSE1_RI: return 32;
     default: return 0;

@@ -312,7 +312,7 @@ unsigned reg_support(const DevOp& d)
     static const int hi[6] = {1, 2, 2, 3, 3, 3}, lo[6] = {0, 0, 1, 0, 1, 2};
     switch (d.code)
     {
-    case RC_DENSE2: case RC_PERM2: case RC_CP2: return (1u << hi[d.pos]) | (1u << lo[d.pos]);
+    case RC_DENSE2: case RC_PERM2: case RC_CP2: case RC_QFT2: return (1u << hi[d.pos]) | (1u << lo[d.pos]);
     case RC_HAD: case RC_STAR: return (unsigned)d.aux & 15u;
     case RC_DIAGR: case RC_DIAGP: return 15u;
     default: return 1u << d.pos;
@@ -339,6 +339,19 @@ void merge_butterflies(EncodedSweep& out)
                     if (reg_support(ops[i]) & (unsigned)d.aux) break;
                 }
             if (!merged) ops.push_back(d);
+        }
+        // butterfly(lo) . controlled phase(hi, lo) . butterfly(hi)  ->  one RC_QFT2 (the radix-4 step of a QFT round)
+        static const int hi[6] = {1, 2, 2, 3, 3, 3}, lo[6] = {0, 0, 1, 0, 1, 2};
+        for (size_t j = begin + 1; j + 1 < ops.size(); j++)
+        {
+            if (ops[j].code != RC_CP2 || ops[j - 1].code != RC_HAD || ops[j + 1].code != RC_HAD) continue;
+            const int bl = 1 << lo[ops[j].pos], bh = 1 << hi[ops[j].pos];
+            if (!(ops[j - 1].aux & bl) || !(ops[j + 1].aux & bh) || (ops[j - 1].aux & bh) || (ops[j + 1].aux & bl)) continue;
+            ops[j].code = RC_QFT2;
+            ops[j - 1].aux &= ~bl;
+            ops[j + 1].aux &= ~bh;
+            if (!ops[j + 1].aux) ops.erase(ops.begin() + (long)j + 1);
+            if (!ops[j - 1].aux) { ops.erase(ops.begin() + (long)j - 1); j--; }
         }
         rd.first = (int32_t)begin;
         rd.count = (int32_t)(ops.size() - begin);

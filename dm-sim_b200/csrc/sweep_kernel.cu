@@ -252,6 +252,18 @@ __device__ __forceinline__ void r_cp2(double2 (&v)[E], Op op)
     for (int c = 0; c < E; c++)
         if ((c & both) == both) cmul_ip(v[c], phi);
 }
+// radix-4 step of a QFT round: butterfly on PL, controlled phase between PH and PL, butterfly on PH
+template <int PH, int PL>
+__device__ __forceinline__ void r_qft2(double2 (&v)[E], Op op)
+{
+    const double2 phi = op_m(op)[0]; // (in flight while the first butterfly runs)
+    r_had<PL>(v);
+    constexpr int both = (1 << PH) | (1 << PL);
+#pragma unroll
+    for (int c = 0; c < E; c++)
+        if ((c & both) == both) cmul_ip(v[c], phi);
+    r_had<PH>(v);
+}
 template <int PH, int PL>
 __device__ __forceinline__ void r_perm2(double2 (&v)[E], Op op)
 {
@@ -362,6 +374,7 @@ __device__ __forceinline__ void apply_reg_op(double2 (&v)[E], const unsigned cha
         DMB_CASE2(kVidDense2, RC_DENSE2, r_dense2, v, op)
         DMB_CASE2(kVidPerm2, RC_PERM2, r_perm2, v, op)
         DMB_CASE2(kVidCp2, RC_CP2, r_cp2, v, op)
+        DMB_CASE2(kVidQft2, RC_QFT2, r_qft2, v, op)
         DMB_CASE1(kVidDense1, RC_DENSE1, r_dense1, v, op)
         DMB_CASE1(kVidRR, RC_DENSE1_RR, r_dense1_rr, v, op)
         DMB_CASE1(kVidRI, RC_DENSE1_RI, r_dense1_ri, v, op)
@@ -613,13 +626,13 @@ static int g_num_sms = 0;
 constexpr unsigned kVariantMasks[] = {
     0u,                                                                              // pure data movement (remap pack)
     BIT(RC_DENSE2),                                                                  // random C2 blocks
-    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_DENSE1_RR) | BIT(RC_HAD),                                               // H + diagonal
-    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_STAR),                                // QFT-like
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_QFT2) | BIT(RC_DENSE1_RR) | BIT(RC_HAD),                                               // H + diagonal
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_QFT2) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_STAR),                                // QFT-like
     BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_PERM2),                                               // H / CX
     BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI),         // dense 1- and 2-qubit blocks
-    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1),               // Clifford+T style
-    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) | BIT(RC_STAR), // no dense 4x4
-    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) |
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_QFT2) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1),               // Clifford+T style
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_QFT2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) | BIT(RC_STAR), // no dense 4x4
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_QFT2) | BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) |
         BIT(RC_SRN1) | BIT(RC_STAR),                                                 // everything
 };
 constexpr int kNumVariants = sizeof(kVariantMasks) / sizeof(kVariantMasks[0]);

@@ -70,7 +70,7 @@ def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = No
 
 
 (RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE2, RC_DIAG2, RC_PERM2, RC_DIAGR, RC_DENSE1_RR, RC_DENSE1_RI, RC_STAR,
- RC_HAD, RC_DIAGP, RC_CP2) = range(14)
+ RC_HAD, RC_DIAGP, RC_CP2, RC_QFT2) = range(15)
 _POS2 = {0: (1, 0), 1: (2, 0), 2: (2, 1), 3: (3, 0), 4: (3, 1), 5: (3, 2)}
 _PERMS = {0: [0, 1, 3, 2], 1: [0, 3, 2, 1], 2: [0, 2, 1, 3]}
 
@@ -187,6 +187,20 @@ def _apply_reg_op(op, v):
         return
     ph_, pl_ = _POS2[pos]
     bh, bl = 1 << ph_, 1 << pl_
+    if code == RC_QFT2:  # butterfly on the lower bit, controlled phase, butterfly on the higher bit
+        for b in (bl, None, bh):
+            if b is None:
+                for q in range(E):
+                    if (q & (bh | bl)) == (bh | bl):
+                        v[q] = m[0] * v[q]
+                continue
+            for q in range(E):
+                if q & b:
+                    continue
+                a0, a1 = v[q].copy(), v[q | b].copy()
+                v[q] = a0 + a1
+                v[q | b] = v[q] - 2.0 * a1
+        return
     for q in range(E):
         if q & (bh | bl):
             continue

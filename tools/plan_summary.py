@@ -4,7 +4,7 @@ import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 dm = importlib.import_module("dm-sim_b200")
-NAMES = {0: "D1", 2: "MONO1", 3: "SRN", 4: "D2", 6: "PERM2", 7: "DIAGR", 8: "RR", 9: "RI", 10: "STAR", 11: "HAD", 12: "DIAGP", 13: "CP2"}
+NAMES = {0: "D1", 2: "MONO1", 3: "SRN", 4: "D2", 6: "PERM2", 7: "DIAGR", 8: "RR", 9: "RI", 10: "STAR", 11: "HAD", 12: "DIAGP", 13: "CP2", 14: "QFT2"}
 n, gates = bench.workload(sys.argv[1])
 p = dm.plan_json(n, int(sys.argv[2]) if len(sys.argv) > 2 else 1, gates)
 print({k: v for k, v in p.items() if not isinstance(v, (list, dict))})
