@@ -587,11 +587,13 @@ int classify(int nb, const cplx* m, int* src_out)
 // ------------------------------------------------------------------------------------------------
 namespace
 {
+// (the matrices live in a side array: the tile-selection scans walk thousands of these per candidate, and 32-byte
+// records keep them in L1 -- with the 256-byte matrix inline a 10^4-gate circuit spent most of its planning time on
+// cache misses)
 struct FlatOp
 {
     int nb;
     int bit[2]; // logical bits of the 2n-bit index; bit[0] carries the matrix MSB
-    cplx m[16];
     bool srn;
     int weight;
     int side; // 0 = L (row bits), 1 = R (column bits)
@@ -631,7 +633,10 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
 
     // mirror: L part on bit q, R part (conjugated) on bit q+n.  SRN is real-linear and self-conjugate.
     std::vector<FlatOp> ops;
+    struct Mat16 { cplx m[16]; };
+    std::vector<Mat16> op_m; // op_m[i].m = matrix of ops[i] (already conjugated for R parts)
     ops.reserve(blocks.size() * 2);
+    op_m.reserve(blocks.size() * 2);
     for (const Block& b : blocks)
         if (b.srn) plan.has_srn = true;
     // With SRN in the circuit the run is strictly "all L parts, then all R parts" in program order
@@ -642,28 +647,32 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
         for (int side = (plan.has_srn ? pass : 0); side < (plan.has_srn ? pass + 1 : 2); side++)
         {
             FlatOp f;
+            Mat16 fm;
+            cplx* const f_m = fm.m;
             f.nb = b.nq; f.srn = b.srn; f.weight = b.weight; f.side = side;
             f.bit[0] = b.q[0] + side * n;
             f.bit[1] = b.nq == 2 ? b.q[1] + side * n : 0;
+            for (auto& e : fm.m) e = 0;
             const int cnt = b.nq == 1 ? 4 : 16;
             // on a conjugated store (conj_state) E acts as conj(E): conj(E conj(x)) = conj(E) x
-            for (int e = 0; e < cnt; e++) f.m[e] = ((side == 1) != conj_state) ? std::conj(b.m[e]) : b.m[e];
+            for (int e = 0; e < cnt; e++) f_m[e] = ((side == 1) != conj_state) ? std::conj(b.m[e]) : b.m[e];
             if (!b.srn)
             {
-                const int cls = classify(b.nq, f.m, nullptr);
+                const int cls = classify(b.nq, f_m, nullptr);
                 f.diag = !plan.has_srn && (cls == CLS_DIAG1 || cls == CLS_DIAG2);
                 if (f.diag && cls == CLS_DIAG2 && opt.cphase)
                 {
                     // entries within 1e-15 of 1 (u1(a) u1(-a) inside a fused controlled phase) are exactly 1
                     auto is_one = [](cplx v) { return std::abs(v.real() - 1.0) < 1e-15 && std::abs(v.imag()) < 1e-15; };
-                    if (is_one(f.m[0]) && is_one(f.m[5]) && is_one(f.m[10]))
+                    if (is_one(f_m[0]) && is_one(f_m[5]) && is_one(f_m[10]))
                     {
                         f.cp = true;
-                        f.m[0] = f.m[5] = f.m[10] = cplx(1.0, 0.0);
+                        f_m[0] = f_m[5] = f_m[10] = cplx(1.0, 0.0);
                     }
                 }
             }
             ops.push_back(f);
+            op_m.push_back(fm);
         }
     }
 
@@ -816,8 +825,8 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
             t.j0 = local_of[f.bit[0]];
             t.j1 = f.nb == 2 ? local_of[f.bit[1]] : 0;
             t.weight = f.weight;
-            memcpy(t.m, f.m, sizeof(t.m));
-            t.cls = f.srn ? (int)CLS_SRN1 : classify(f.nb, f.m, nullptr);
+            memcpy(t.m, op_m[i].m, sizeof(t.m));
+            t.cls = f.srn ? (int)CLS_SRN1 : classify(f.nb, op_m[i].m, nullptr);
             if (f.cp)
             {
                 t.cls = CLS_CPHASE; // symmetric in its two bits: keep the in-tile one first
@@ -854,6 +863,7 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
         {
             const FlatOp& f = ops[i];
             if (f.done) continue;
+            if (n_picked >= 8 * opt.max_ops) break; // the sweep's op table is full: nothing further can be picked
             visited++;
             bool ok = n_picked + (f.cp ? 1 : 8) <= 8 * opt.max_ops && (!f.cp || n_cp < opt.max_cphase);
             if (f.cp)
