@@ -217,6 +217,7 @@ int dmb_set_option(const char* name, int64_t value)
     else if (!strcmp(name, "cphase")) g_opt.cphase = value != 0;
     else if (!strcmp(name, "sparse")) g_sparse_start = (int)value;
     else if (!strcmp(name, "move_h")) g_opt.move_h = value != 0;
+    else if (!strcmp(name, "hot_low")) g_opt.hot_low = value != 0;
     else return fail(DMB_EINVAL, std::string("unknown option ") + name);
     return DMB_OK;
 }

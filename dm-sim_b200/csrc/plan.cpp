@@ -792,7 +792,7 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
     };
 
     auto emit_sweep = [&](const std::vector<int>& tile_logical_in, const std::vector<int>& picked,
-                          const std::vector<std::pair<int, int>>& moves /* logical -> new phys */) {
+                          const std::vector<std::pair<int, int>>& moves /* logical -> new phys */, bool in_place = false) {
         // pad the tile with the lowest free physical bits: longer contiguous runs, fewer larger tiles --
         // but keep at least 2^min_tiles_log2 tiles when the state is small.
         std::vector<int> tile_logical = tile_logical_in;
@@ -841,7 +841,8 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
         }
         for (auto& mv : moves) phys[mv.first] = mv.second;
         for (int j = 0; j < sw.k; j++) sw.out_pos.push_back(phys[order[j]]);
-        sw.out_of_place = !moves.empty();
+        sw.out_of_place = !moves.empty() && !in_place; // a permutation INSIDE the tile may run in place: every tile is read
+                                                       // completely before it is written, to the same set of addresses
         plan.steps.push_back(st);
         plan.n_sweeps++;
         while (first_pending < ops.size() && ops[first_pending].done) first_pending++;
@@ -977,7 +978,36 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
         }
         if (!best.picked.empty())
         {
-            emit_sweep(best.tile_logical, best.picked, {});
+            // Hot bits to the low positions.  The lowest `lowb` physical bits belong to EVERY tile (coalescing), so a
+            // logical bit sitting there costs the later sweeps nothing.  When this sweep finishes the work of the bit
+            // at such a position while another bit of the tile still has ops that need it inside a tile (a shared
+            // target, a carry, ...), the two swap positions in this sweep's store phase (in place, no extra pass):
+            // bv_n15 4 -> 3 sweeps.  Controlled phases do not count: they need only one of their bits in a tile.
+            std::vector<std::pair<int, int>> moves;
+            if (opt.hot_low && lowb > 0 && !plan.has_srn)
+            {
+                std::vector<char> taken(ops.size(), 0);
+                for (int i : best.picked) taken[i] = 1;
+                std::vector<long> pend_w(N, 0);
+                for (size_t i = first_pending; i < ops.size(); i++)
+                    if (!ops[i].done && !taken[i] && !ops[i].cp)
+                        for (int b = 0; b < ops[i].nb; b++) pend_w[ops[i].bit[b]] += ops[i].weight;
+                std::vector<int> hot;
+                for (int l : best.tile_logical)
+                    if (phys[l] >= lowb && pend_w[l] > 0) hot.push_back(l);
+                std::stable_sort(hot.begin(), hot.end(), [&](int a, int b) { return pend_w[a] > pend_w[b]; });
+                for (int l = 0; l < N; l++) logical_at[phys[l]] = l;
+                size_t h = 0;
+                for (int p = 0; p < lowb && h < hot.size(); p++)
+                {
+                    const int dead = logical_at[p];
+                    if (pend_w[dead] > 0) continue;
+                    moves.push_back({dead, phys[hot[h]]});
+                    moves.push_back({hot[h], p});
+                    h++;
+                }
+            }
+            emit_sweep(best.tile_logical, best.picked, moves, true);
             continue;
         }
         // Stuck: every pending op needs a rank bit.  Qubit remap: pick the g local logical bits with the

@@ -79,6 +79,7 @@ struct PlanOptions
     int low_bits = 3;   // physical bits 0..low_bits-1 are always tile bits (2^3 * 16 B = 128 B runs)
     int min_tiles_log2 = 10; // prefer >= 2^10 tiles when the state is small (keeps 148 SMs busy)
     int max_ops = 112;       // ops per sweep (the kernel keeps the sweep's op table in shared memory)
+    bool hot_low = true;     // swap bits with pending work into the always-in-tile low positions (plan.cpp)
     bool move_h = false;     // second identity of rewrite_hadamard_cx (plan.cpp)
     int scan_window = 1536;  // pending ops a tile-selection scan looks at
     int max_cphase = 160;    // controlled phases per sweep (<= kMaxStarsPerSweep: each may need its own star slot)

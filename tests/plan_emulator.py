@@ -86,8 +86,7 @@ def run_plan(plan: dict, vec_logical: np.ndarray) -> np.ndarray:
             if nb == 2:  # a controlled phase may have its second bit outside the tile (even on a rank bit)
                 bits.append(in_pos[op["j1"]] if op["j1"] >= 0 else op["p1"])
             v = _apply_matrix(v, N, m, bits)
-        if in_pos != out_pos:
-            assert st["out_of_place"]
+        if in_pos != out_pos:  # out of place (remap pack) or a permutation inside the tile done in place
             v = _permute_bits(v, N, {in_pos[j]: out_pos[j] for j in range(len(in_pos))})
     v = physical_to_logical(v, plan["end_layout"])
     return np.conj(v) if plan.get("conj_end") else v
