@@ -84,8 +84,8 @@ md = ["# profiles/ -- measured on B200 (round 1)", "",
       "the ncu files themselves. `value` = device time of `dmb_run` on the DENSE resident state (CUDA events on the engine's",
       "stream); `e2e` = wall clock of reset + circuit upload + run + diagonal readback from |0><0| (sparse start on, single",
       "GPU); `resident e2e` = the same calls without the reset, on the dense state.", "",
-      "| workload | GPUs | sweeps/step | ms/step | gates/s | achieved GB/s (frac of measured HBM peak) | e2e ms (gates/s) | resident e2e ms | exchange GB/s per direction |",
-      "|---|---|---|---|---|---|---|---|---|"]
+      "| workload | GPUs | sweeps/step | ms/step | gates/s | achieved GB/s (frac of measured HBM peak) | e2e ms (gates/s) | resident e2e ms | exchange GB/s per direction | file |",
+      "|---|---|---|---|---|---|---|---|---|---|"]
 seen = set()
 for f in sorted(glob.glob(os.path.join(P, "*bench_lines*.jsonl"))):
     if "older_kernel" in f:
@@ -97,7 +97,7 @@ for f in sorted(glob.glob(os.path.join(P, "*bench_lines*.jsonl"))):
             key = (d["config"]["workload"], d["n_gpus"], d.get("impl"), os.path.basename(f))
             if key not in seen:
                 seen.add(key)
-                md.append(row(d))
+                md.append(row(d) + f" `{os.path.basename(f)}` |")
 md += ["", "Files:", ""]
 for f in sorted(os.listdir(P)):
     if f != "README.md":
@@ -108,8 +108,11 @@ md += ["", "`*_sweep_full_<workload>.txt`: per-launch key metrics of `ncu --set 
        "(`--metrics gpu__time_duration.sum`) of `bench.py --steps 2 --warmup 1`. `ncu_traffic.json`: DRAM bytes per launch.",
        "`r1_bench_lines_8gpu_nccl_path_older_kernel.jsonl`: the 8-GPU lines of an earlier session (NCCL exchange, sweep kernel",
        "before this session's rewrite); 2- and 4-GPU lines are from this session (peer-memory remap).", "",
-       "The 1-GPU lines and the ncu captures were taken one commit before the `RC_QFT2` fusion; with it qft_n15 measures",
-       "26.53 ms/step (20 351 gates/s, frac 0.602), the other workloads are unchanged within noise."]
+       "`r1_bench_lines_1gpu.jsonl`, the launch list and the ncu captures belong to one run (tools/gpu_round.sh) taken before",
+       "the last two changes of the round; `r1_bench_lines_1gpu_final_code.jsonl` is the same bench on the final code:",
+       "`RC_QFT2` fusion (qft_n15 26.96 -> 26.57 ms) and hot bits in the low tile positions (bv_n15 4 -> 3 sweeps, 33.4 ->",
+       "29.4 ms; random_c1c2_n15 19 -> 15 sweeps, 389 -> 372 ms; adder_n10 4 -> 2 sweeps).  Fewer sweeps lower",
+       "`roofline.frac` (it counts sweeps x bytes / time) while the circuit gets faster."]
 open(os.path.join(P, "README.md"), "w").write("\n".join(md) + "\n")
 print("README.md rows:", len(seen))
 for f in glob.glob(os.path.join(G, f"{tag}_launches_*.csv")):
