@@ -267,3 +267,42 @@ def test_hadamard_cx_fans_become_controlled_phases(dm, oracle_mod, world):
         assert np.abs(ke.run_plan_dev(plan0, zero_state(n)) - to_complex(re, im)).max() < TOL
     finally:
         dm.set_option("cphase", 1)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_hot_bits_move_to_the_low_tile_positions(dm, oracle_mod, opts, world):
+    """Option "hot_low": a bit that still has ops needing it inside a tile swaps into one of the always-in-tile low
+    physical positions when the bit sitting there is finished (in-place permutation in the sweep's store phase).  Same
+    state as the oracle through both interpreters, never more sweeps than without, fewer for a shared-target circuit."""
+    import importlib
+    circuits = importlib.import_module("dm-sim_b200.circuits")
+    n = 7
+    opts(tile_bits=6, low_bits=2, min_tiles_log2=2)
+    rng = np.random.default_rng(3 + world)
+    for gates in (circuits.bv(n), random_gates(n, 80, rng), circuits.qft(n) + circuits.bv(n)):
+        re, im = oracle_mod.Oracle(n).sim(gates).dm()
+        ref = to_complex(re, im)
+        sweeps = {}
+        for hot in (1, 0):
+            dm.set_option("hot_low", hot)
+            try:
+                plan = dm.plan_json(n, world, gates)
+            finally:
+                dm.set_option("hot_low", 1)
+            sweeps[hot] = plan["n_sweeps"]
+            permuting = [st for st in plan["steps"] if st["kind"] == "sweep" and st["in_pos"] != st["out_pos"] and not st["out_of_place"]]
+            assert hot or not permuting
+            for st in permuting:
+                assert sorted(st["in_pos"]) == sorted(st["out_pos"])
+            assert np.abs(pe.run_plan(plan, zero_state(n)) - ref).max() < TOL
+            assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - ref).max() < TOL
+        if world == 1:
+            assert sweeps[1] <= sweeps[0]
+    dm.set_option("hot_low", 1)
+    p1 = dm.plan_json(n, 1, circuits.bv(n))
+    dm.set_option("hot_low", 0)
+    try:
+        p0 = dm.plan_json(n, 1, circuits.bv(n))
+    finally:
+        dm.set_option("hot_low", 1)
+    assert p1["n_sweeps"] < p0["n_sweeps"]
