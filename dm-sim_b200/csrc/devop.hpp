@@ -132,7 +132,7 @@ struct alignas(16) DevOp
     int32_t code; // RegOpCode
     int32_t aux;
     int32_t pos;  // 1-bit ops: register bit 0..3; 2-bit ops: (msb, lsb) = (1,0) (2,0) (2,1) (3,0) (3,1) (3,2) -> 0..5
-    int32_t vid;  // code * 8 + pos: the kernel's jump-table index; RC_STAR: first DevStar slot (host side)
+    int32_t vid;  // host side: RC_STAR: first DevStar slot (the kernel's jump-table index is dev_vid(code, pos, aux))
     double m[32]; // up to 16 complex entries (re, im)
 };
 static_assert(sizeof(DevOp) == 272, "DevOp layout");

@@ -4,17 +4,18 @@
 // src/dmsim_nvgpu_omp.cuh:989-1813), its per-gate grid.sync (:1001) and its block_transpose (:825-855):
 // ONE HBM pass applies a whole fused block of 1-/2-bit ops.
 //
-//   * persistent CTAs of 256 threads, 2-3 resident per SM (they overlap each other's load / compute / store
+//   * persistent CTAs of 128 threads, 3 resident per SM (they overlap each other's load / compute / store
 //     phases); tile = 2^k complex FP64 (k <= 12, 64 KiB) staged in shared memory with 128-bit cp.async (LDGSTS)
 //     into an XOR-swizzled layout, results streamed back with evict-first 128-bit stores -- optionally to
-//     permuted bit positions (the pack step of the multi-GPU qubit remap, reference packing :858-882).
-//     HBM runs are >= 2^low_bits * 16 B contiguous.
-//   * ops run in warp-local GROUPS (each of the 8 warps owns the sub-tile selected by 3 tile bits no op of the
-//     group touches, so only __syncwarp() separates ops; CTA barriers only between groups) made of register
-//     ROUNDS (a lane keeps 8 elements = 3 tile bits in registers, applies every op of the round there: one
+//     permuted bit positions (in place for a permutation inside the tile; the pack step of the multi-GPU qubit remap,
+//     reference packing :858-882, optionally straight into the peers' shards).  HBM runs are >= 2^low_bits * 16 B.
+//   * ops run in warp-local GROUPS (each of the 4 warps owns the sub-tile selected by 2 tile bits no op of the
+//     group touches, so only __syncwarp() separates rounds; CTA barriers only between groups) made of register
+//     ROUNDS (a lane keeps 16 elements = 4 tile bits in registers, applies every op of the round there: one
 //     shared-memory round trip per round instead of one per gate).
 //   * all index arithmetic is pre-computed on the host as pre-swizzled XOR tables (encode.cpp); the sweep's
-//     program (ops / rounds / groups) is staged once per CTA in shared memory.
+//     program (op stream / rounds / groups / star tables) is staged once per CTA in shared memory; a round's ops are
+//     dispatched from a packed list of jump-table indices held in registers.
 #include "kernels.cuh"
 
 namespace dmb
@@ -340,7 +341,7 @@ __device__ __forceinline__ void r_hadm(double2 (&v)[E], int mask)
 // MASK = the register-op codes compiled into this instantiation of the kernel (bit c <-> RegOpCode c).  ptxas keeps
 // the 16 resident elements in ONE register assignment across the dispatch only when few bodies meet there; with all
 // bodies in one kernel it copies all 64 registers before and after every op (measured: 135 moves per op).
-// vid = code * 8 + pos (DevOp::vid, set by the encoder): one jump table for op kind and register position.
+// vid = dev_vid(code, pos, aux) (devop.hpp): one dense jump table for op kind and register position.
 #define DMB_HAS(c) ((MASK >> (c)) & 1u)
 #define DMB_SZ(c) (16 + dev_op_payload_bytes(c))
 #define DMB_CASE1(base, c, FN, ...)                                                            \
