@@ -905,8 +905,12 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
         while ((int)c.tile_logical.size() < kmax)
         {
             const int room = kmax - (int)c.tile_logical.size();
-            // candidate additions: the missing bits of the pending ops near the front (deduplicated)
-            std::vector<std::vector<int>> cands;
+            // candidate additions: the missing bits of the pending ops near the front (deduplicated; bit sets as 64-bit
+            // masks in first-seen order -- small vectors here cost a 10^4-gate circuit most of its planning time)
+            std::vector<unsigned long long> cands;
+            auto add_cand = [&](unsigned long long m) {
+                if (std::find(cands.begin(), cands.end(), m) == cands.end()) cands.push_back(m);
+            };
             int looked = 0;
             for (size_t i = first_pending; i < ops.size() && looked < 512; i++)
             {
@@ -918,40 +922,38 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
                     // one bit in the tile is enough: each local bit is a candidate on its own
                     if (in_tile[f.bit[0]] || in_tile[f.bit[1]]) continue;
                     for (int b = 0; b < 2; b++)
-                    {
-                        if (phys[f.bit[b]] >= M) continue;
-                        std::vector<int> one(1, f.bit[b]);
-                        if (std::find(cands.begin(), cands.end(), one) == cands.end()) cands.push_back(one);
-                    }
+                        if (phys[f.bit[b]] < M) add_cand(1ull << f.bit[b]);
                     continue;
                 }
-                std::vector<int> miss;
+                unsigned long long miss = 0;
                 bool local = true;
                 for (int b = 0; b < f.nb; b++)
                 {
                     if (phys[f.bit[b]] >= M) local = false;
-                    if (!in_tile[f.bit[b]] && std::find(miss.begin(), miss.end(), f.bit[b]) == miss.end()) miss.push_back(f.bit[b]);
+                    if (!in_tile[f.bit[b]]) miss |= 1ull << f.bit[b];
                 }
-                if (!local || miss.empty() || (int)miss.size() > room) continue;
-                std::sort(miss.begin(), miss.end());
-                if (std::find(cands.begin(), cands.end(), miss) == cands.end()) cands.push_back(miss);
+                if (!local || !miss || __builtin_popcountll(miss) > room) continue;
+                add_cand(miss);
             }
             long best_gain = 0;
             double best_rate = 0;
             int best_i = -1;
             for (size_t ci = 0; ci < cands.size(); ci++)
             {
-                for (int b : cands[ci]) in_tile[b] = 1;
+                for (int l = 0; l < N; l++)
+                    if ((cands[ci] >> l) & 1ull) in_tile[l] = 1;
                 const long gain = scan_fixed(in_tile, nullptr) - cur;
-                for (int b : cands[ci]) in_tile[b] = 0;
-                const double rate = (double)gain / (double)cands[ci].size();
+                for (int l = 0; l < N; l++)
+                    if ((cands[ci] >> l) & 1ull) in_tile[l] = 0;
+                const double rate = (double)gain / (double)__builtin_popcountll(cands[ci]);
                 if (gain > 0 && (rate > best_rate || (rate == best_rate && gain > best_gain)))
                 {
                     best_rate = rate; best_gain = gain; best_i = (int)ci;
                 }
             }
             if (best_i < 0) break;
-            for (int b : cands[best_i]) { in_tile[b] = 1; c.tile_logical.push_back(b); }
+            for (int l = 0; l < N; l++)
+                if ((cands[best_i] >> l) & 1ull) { in_tile[l] = 1; c.tile_logical.push_back(l); }
             cur += best_gain;
         }
         c.score = scan_fixed(in_tile, &c.picked);
