@@ -156,3 +156,54 @@ def test_cplus_translator_emits_a_buildable_driver(tmp_path):
                        capture_output=True, text=True, check=True)
     assert "Number of qubits: 5" in r.stdout and "Number of basic gates: " + str(stats["basic_gates"]) in r.stdout
     assert "void prepare_circuit(Simulation &sim)" in out.read_text()
+
+
+def _run_reference_cplus_translator(path, out):
+    """The reference's tool/dmsim_qasm_cplus.py executed under Python 3 (same in-memory patches as above)."""
+    with open(os.path.join(REF, "tool", "dmsim_qasm_cplus.py")) as f:
+        src = f.read()
+    src = src.replace("dict(STANDARD_GATE_TABLE.items() + COMPOSITION_GATE_TABLE.items())",
+                      "dict(list(STANDARD_GATE_TABLE.items()) + list(COMPOSITION_GATE_TABLE.items()))")
+    src = src.replace("dict(STANDARD_CX_TABLE.items() + COMPOSITION_CX_TABLE.items())",
+                      "dict(list(STANDARD_CX_TABLE.items()) + list(COMPOSITION_CX_TABLE.items()))")
+    argv, stdout = sys.argv, sys.stdout
+    sys.argv, sys.stdout = ["dmsim_qasm_cplus.py", "-i", path, "-o", out], io.StringIO()
+    try:
+        exec(compile(src, "ref_dmsim_qasm_cplus.py", "exec"), {"__name__": "__main__"})
+        printed = sys.stdout.getvalue()
+    finally:
+        sys.argv, sys.stdout = argv, stdout
+    with open(out) as f:
+        return f.read(), printed
+
+
+@pytest.mark.parametrize("name", ["bv_n15", "qft_n15", "adder_n9", "cc_n15", "qec_n5", "w_state_n3", "grover_n3", "sat_n10"])
+def test_cplus_translator_against_the_reference(tmp_path, name):
+    """Same gate statements (factory name + arguments, in order) and the same statistics as the reference's
+    tool/dmsim_qasm_cplus.py for the main circuit of the benchmark files."""
+    import re
+    if not os.path.exists(REF):
+        pytest.skip("reference tree not present")
+    path = os.path.join(REF, "benchmark", name + ".qasm")
+    ref_cpp, ref_printed = _run_reference_cplus_translator(path, str(tmp_path / "ref.cpp"))
+    with open(path) as f:
+        mine, stats = qasm.translate_cplus(f.read())
+
+    def calls(s, pat):  # (NAME, [numeric args]) of every appended gate
+        out = []
+        for m in re.finditer(pat, s):
+            try:
+                out.append((m.group(1), [float(a) for a in m.group(2).split(",")]))
+            except ValueError:     # symbolic arguments inside a user-defined gate: compare as text
+                out.append((m.group(1), [a.strip() for a in m.group(2).split(",")]))
+        return out
+    ref_calls = calls(ref_cpp, r"sim\.append\(Simulation::([A-Z0-9]+)\(([^)]*)\)\)")
+    my_calls = calls(mine, r"DMSIM_APPEND\(([A-Z0-9]+)\(([^)]*)\)\)")
+    assert len(my_calls) == len(ref_calls) and len(my_calls) > 0
+    for (a, pa), (b, pb) in zip(my_calls, ref_calls):
+        assert a == b
+        if all(isinstance(x, float) for x in pa + pb):
+            assert np.allclose(pa, pb, rtol=0, atol=1e-12)
+    assert f"Number of qubits: {stats['n_qubits']}" in ref_printed
+    assert f"Number of basic gates: {stats['basic_gates']}" in ref_printed
+    assert f"Number of cnot gates: {stats['cnot_gates']}" in ref_printed
