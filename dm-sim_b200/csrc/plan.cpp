@@ -851,33 +851,30 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
     // ---- gain-driven tile selection --------------------------------------------------------------------------
     // scan_fixed: with the tile bit set FIXED, which pending ops can run (program order per bit, diagonal ops may hop
     // over skipped diagonal ops)?  Returns the total weight; fills picked when asked.
+    // (bit sets as 64-bit masks: `tile` = bits in the tile, `b2` = bits blocked by a skipped non-diagonal op, `b1` = by a
+    // skipped diagonal op; a visit is a handful of mask operations)
+    std::vector<unsigned long long> op_bits(ops.size());
+    for (size_t i = 0; i < ops.size(); i++)
+        op_bits[i] = (1ull << ops[i].bit[0]) | (ops[i].nb == 2 ? 1ull << ops[i].bit[1] : 0ull);
     auto scan_fixed = [&](const std::vector<char>& in_tile, std::vector<int>* picked) -> long {
-        std::vector<char> blocked(N, 0);
-        int n_open = 0;
-        for (int l = 0; l < N; l++) n_open += in_tile[l] ? 1 : 0;
+        unsigned long long tile = 0, b1 = 0, b2 = 0;
+        for (int l = 0; l < N; l++)
+            if (in_tile[l]) tile |= 1ull << l;
         long score = 0;
         int n_picked = 0, n_cp = 0;
         // (a sweep holds at most max_ops ops: looking further than a few thousand pending ops ahead only costs time --
         // the scans of a 10^4-gate circuit were quadratic without the window)
         int visited = 0;
-        for (size_t i = first_pending; i < ops.size() && n_open > 0 && visited < opt.scan_window; i++)
+        for (size_t i = first_pending; i < ops.size() && (tile & ~b2) && visited < opt.scan_window; i++)
         {
             const FlatOp& f = ops[i];
             if (f.done) continue;
             if (n_picked >= 8 * opt.max_ops) break; // the sweep's op table is full: nothing further can be picked
             visited++;
+            const unsigned long long bm = op_bits[i];
             bool ok = n_picked + (f.cp ? 1 : 8) <= 8 * opt.max_ops && (!f.cp || n_cp < opt.max_cphase);
-            if (f.cp)
-            {
-                if (blocked[f.bit[0]] == 2 || blocked[f.bit[1]] == 2) ok = false;
-                if (!in_tile[f.bit[0]] && !in_tile[f.bit[1]]) ok = false;
-            }
-            else
-                for (int b = 0; b < f.nb; b++)
-                {
-                    const int lvl = blocked[f.bit[b]];
-                    if (!in_tile[f.bit[b]] || lvl == 2 || (lvl == 1 && !f.diag)) ok = false;
-                }
+            if (f.cp) ok = ok && !(bm & b2) && (bm & tile);
+            else ok = ok && !(bm & ~tile) && !(bm & b2) && (f.diag || !(bm & b1));
             if (ok)
             {
                 score += 1000L * f.weight + 1;
@@ -886,13 +883,8 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
                 if (picked) picked->push_back((int)i);
                 continue;
             }
-            const char lvl = f.diag ? 1 : 2;
-            for (int b = 0; b < f.nb; b++)
-                if (blocked[f.bit[b]] < lvl)
-                {
-                    if (lvl == 2 && in_tile[f.bit[b]]) n_open--;
-                    blocked[f.bit[b]] = lvl;
-                }
+            if (f.diag) b1 |= bm;
+            else b2 |= bm;
         }
         return score;
     };
