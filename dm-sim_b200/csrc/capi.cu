@@ -2,6 +2,7 @@
 // NCCL qubit-remap exchange, result readback.  Replaces Simulation::{ctor,upload,sim,measure}
 // (reference src/dmsim_nvgpu_omp.cuh:196-549).  There is no CPU fallback: every compute entry point
 // fails with DMB_ECUDA when no usable GPU / driver is present.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -54,6 +55,59 @@ static void init_options()
     if (const char* e = getenv("DMB_GRAPH")) g_use_graph = atoi(e);
     if (const char* e = getenv("DMB_CPHASE")) g_opt.cphase = atoi(e) != 0;
     if (const char* e = getenv("DMB_SPARSE")) g_sparse_start = atoi(e);
+    if (const char* e = getenv("DMB_TMA")) g_opt.tma = atoi(e) != 0;
+    if (const char* e = getenv("DMB_TMA_BOX_BITS")) set_sweep_tma_box_bits(atoi(e));
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA tensor maps (driver entry point fetched through the runtime: no link against libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tma_encoder()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried)
+    {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+// the shard `buf` (2^M complex FP64) as the dense 5-D FP64 tensor TmaGeom describes; box = the tile bits of each dimension
+static bool make_tile_map(const TmaGeom& g, int M, const void* buf, TmaDesc& out, std::string& why)
+{
+    static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "CUtensorMap size");
+    EncodeTiledFn enc = tma_encoder();
+    if (!enc) { why = "cuTensorMapEncodeTiled is not available"; return false; }
+    cuuint64_t dim[5], stride[4];
+    cuuint32_t box[5], estride[5] = {1, 1, 1, 1, 1};
+    for (int d = 0; d < 5; d++)
+    {
+        dim[d] = (cuuint64_t)1 << g.span[d];
+        box[d] = (cuuint32_t)1 << g.box_log2[d];
+        if (d > 0) stride[d - 1] = (cuuint64_t)16 << g.start[d];
+    }
+    dim[0] *= 2; // FP64 units: two per complex element
+    box[0] *= 2;
+    CUtensorMap m;
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, const_cast<void*>(buf), dim, stride, box, estride,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+    {
+        why = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " (M=" + std::to_string(M) + ")";
+        return false;
+    }
+    memcpy(&out, &m, sizeof(out));
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -218,6 +272,8 @@ int dmb_set_option(const char* name, int64_t value)
     else if (!strcmp(name, "sparse")) g_sparse_start = (int)value;
     else if (!strcmp(name, "move_h")) g_opt.move_h = value != 0;
     else if (!strcmp(name, "hot_low")) g_opt.hot_low = value != 0;
+    else if (!strcmp(name, "tma")) g_opt.tma = value != 0;
+    else if (!strcmp(name, "tma_box_bits")) set_sweep_tma_box_bits((int)value);
     else return fail(DMB_EINVAL, std::string("unknown option ") + name);
     return DMB_OK;
 }
@@ -464,8 +520,8 @@ int dmb_clear_circuit(dmb_handle s)
 }
 
 // ---- execution --------------------------------------------------------------------------------
-static void fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, double2* out, SweepArgs& a,
-                            unsigned long long support = ~0ull)
+static int fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, double2* out, SweepArgs& a,
+                           unsigned long long support = ~0ull)
 {
     memset(&a, 0, sizeof(a));
     const Sweep& sw = s->plan.steps[step].sweep;
@@ -498,6 +554,13 @@ static void fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, do
     a.n_rounds = s->n_dev_rounds[step];
     a.n_groups = s->n_dev_groups[step];
     a.op_mask = s->op_masks[step];
+    if (a.tma_load)
+    {
+        std::string why;
+        if (!make_tile_map(a.tma, s->M, in, a.tmap_in, why)) return fail(DMB_ECUDA, why);
+        if (a.tma_store && !make_tile_map(a.tma, s->M, out, a.tmap_out, why)) return fail(DMB_ECUDA, why);
+    }
+    return DMB_OK;
 }
 
 // enqueue every step of the plan on s->stream; cur is updated as buffers flip
@@ -524,12 +587,13 @@ static int enqueue_steps(dmb_sim* s, int& cur, uint64_t& launches, bool allow_ex
             }
             CU(cudaEventRecord(s->ev_comm[2 * comm_idx], s->stream));
             SweepArgs a;
-            fill_sweep_args(s, i, s->buf[cur], s->buf[cur ^ 1], a);
+            int rca = fill_sweep_args(s, i, s->buf[cur], s->buf[cur ^ 1], a);
+            if (rca) return rca;
             a.peer_shift = s->M - s->g;
             a.peer_rank = s->rank;
             for (int r = 0; r < s->world; r++) a.peer_out[r] = (unsigned long long)s->peer[cur ^ 1][r];
             const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)sweep_max_grid(a));
-            launch_sweep(a, grid, s->stream);
+            CU(launch_sweep(a, grid, s->stream));
             CU(cudaGetLastError());
             const int nr = g_nccl.AllReduce(s->d_barrier, s->d_barrier + 1, 1, kNcclDouble, 0 /* ncclSum */, s->comm, s->stream);
             if (nr != 0) return fail(DMB_ECOMM, std::string("NCCL barrier failed: ") + g_nccl.GetErrorString(nr));
@@ -553,10 +617,11 @@ static int enqueue_steps(dmb_sim* s, int& cur, uint64_t& launches, bool allow_ex
             }
             SweepArgs a;
             if (sw.out_of_place) support = ~0ull; // (only multi-GPU remaps permute; kept general)
-            fill_sweep_args(s, i, in, out, a, support);
+            int rca = fill_sweep_args(s, i, in, out, a, support);
+            if (rca) return rca;
             for (int j = 0; j < sw.k; j++) support |= 1ull << sw.in_pos[j];
             const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)sweep_max_grid(a));
-            launch_sweep(a, grid, s->stream);
+            CU(launch_sweep(a, grid, s->stream));
             CU(cudaGetLastError());
             launches++;
             if (sw.out_of_place) cur ^= 1;

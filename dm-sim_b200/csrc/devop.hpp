@@ -21,7 +21,16 @@ constexpr int kMaxOpsPerSweep = 112;
 // 0..2 (the 8 lanes of one LDS.128 / STS.128 phase) such positions.  Linear (thread-order) access is conflict free
 // for any swizzle of this form.  GF(2)-linear: swz(a ^ b) == swz(a) ^ swz(b) -- the encoder pre-swizzles every
 // index contribution.
-inline unsigned swz_host(unsigned e) { return e ^ ((e >> 3) & 7u) ^ ((e >> 6) & 7u) ^ ((e >> 9) & 7u); }
+//
+// Mode 1 (kSwzTma) is the hardware's 128-byte swizzle of a TMA tile (CU_TENSOR_MAP_SWIZZLE_128B on a 1024-byte aligned
+// buffer: the 16-byte chunk index of a 128-byte row is XORed with the low 3 bits of the row index): only tile bits 3..5
+// move the bank group.  Sweeps whose tile is loaded / stored by TMA use it; the encoder then picks lane bits 0..2 from
+// three different residues among tile bits 0..5.
+constexpr int kSwzXor3 = 0, kSwzTma = 1;
+inline unsigned swz_host(unsigned e, int mode = kSwzXor3)
+{
+    return mode == kSwzTma ? e ^ ((e >> 3) & 7u) : e ^ ((e >> 3) & 7u) ^ ((e >> 6) & 7u) ^ ((e >> 9) & 7u);
+}
 
 // Register-level op codes (what the device switches on).  Two-bit ops are canonicalised by the encoder so that
 // the matrix MSB sits on the HIGHER register bit; `pos` then selects one of the pairs (1,0) (2,0) (2,1).
@@ -168,6 +177,23 @@ struct alignas(16) DevGroup
 };
 static_assert(sizeof(DevGroup) == 48, "DevGroup layout");
 
+// A tile as TMA boxes.  The shard is a dense 5-D tensor of FP64 pairs: dimension d covers the physical bits
+// [start[d], start[d] + span[d]) of the element index, its low box_log2[d] bits are tile bits (the box), the bits above them
+// are not (they are part of the box's start coordinate).  Dimension 0 is always the 128-byte run (physical bits 0..2).
+// The tile bits that do not fit the box (at most 5 dimensions, <= 256 elements each, <= max box size) are enumerated by
+// n_copies = 2^n_enum separate copies; copy j lands at byte offset j * box_bytes of the tile (ascending tile-local order).
+struct TmaGeom
+{
+    int32_t n_copies, box_bytes;
+    unsigned char start[5], span[5], box_log2[5];
+    unsigned char n_enum;
+    unsigned long long enum_off[32]; // element offset of copy j (its enumerated tile bits deposited at their positions)
+};
+struct alignas(64) TmaDesc // CUtensorMap (opaque, 128 bytes, filled by cuTensorMapEncodeTiled)
+{
+    unsigned long long opaque[16];
+};
+
 // Kernel parameter block of one sweep (by value -> constant bank; the per-iteration tables become immediate
 // constant operands of the unrolled load / store loops).
 struct SweepArgs
@@ -197,5 +223,10 @@ struct SweepArgs
     unsigned char sout[12];      // tile-local bit of loop bit i (< kThreadBits) when storing
     unsigned char cin[40];       // physical bits enumerated by the tile id when loading (ascending)
     unsigned char cout[40];      // ... when storing
+    // TMA tile I/O (full-size tiles): swz_mode = kSwzTma, the tile is loaded (tma_load) / stored (tma_store: in-place
+    // sweeps that do not permute bits) as boxes of ONE tensor map over the shard buffer
+    int swz_mode, tma_load, tma_store, tma_pad;
+    TmaGeom tma;
+    TmaDesc tmap_in, tmap_out;
 };
 } // namespace dmb

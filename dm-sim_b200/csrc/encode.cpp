@@ -10,6 +10,9 @@
 
 namespace dmb
 {
+static int g_tma_box_bits = 10;
+void set_sweep_tma_box_bits(int bits) { g_tma_box_bits = bits < 3 ? 3 : (bits > kMaxTileBits ? kMaxTileBits : bits); }
+int sweep_tma_box_bits() { return g_tma_box_bits; }
 namespace
 {
 unsigned deposit(unsigned v, const std::vector<int>& pos)
@@ -389,6 +392,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
     out.stars.clear();
     out.op_mask = 0;
     const int k = sw.k;
+    const int mode = sw.swz_mode;
     const int nwb = k >= kWarpBits + kRegBits ? kWarpBits : 0;
     const int R = std::min(kRegBits, k - nwb);
     const std::vector<RoundPlan> plan = plan_rounds(sw, R);
@@ -416,7 +420,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
         std::sort(wpos.begin(), wpos.end());
         unsigned wmask = 0;
         for (int p : wpos) wmask |= 1u << p;
-        for (int w = 0; w < (1 << kWarpBits); w++) g.wtab[w] = (uint16_t)swz_host(deposit((unsigned)w, wpos));
+        for (int w = 0; w < (1 << kWarpBits); w++) g.wtab[w] = (uint16_t)swz_host(deposit((unsigned)w, wpos), mode);
 
         for (size_t ri = first; ri < end; ri++)
         {
@@ -435,7 +439,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
             memset(&rd, 0, sizeof(rd));
             rd.first = (int32_t)out.ops.size(); // op INDEX for now; rewritten to the stream offset below
             const int rd_first = rd.first;
-            for (int c = 0; c < kRegElems; c++) rd.roff[c] = (uint16_t)swz_host(deposit((unsigned)c & ((1u << R) - 1u), rb));
+            for (int c = 0; c < kRegElems; c++) rd.roff[c] = (uint16_t)swz_host(deposit((unsigned)c & ((1u << R) - 1u), rb), mode);
             std::vector<int> freep;
             for (int p = 0; p < k; p++)
                 if (!(((wmask | rmask) >> p) & 1u)) freep.push_back(p);
@@ -444,9 +448,10 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
             // classes (p mod 3, see swz_host) whenever one is free, so that the phase is bank-conflict free
             std::vector<int> lanep;
             std::vector<char> taken(k, 0);
+            // (kSwzTma: only tile bits 0..5 move the bank group)
             for (int cls = 0; cls < 3 && (int)lanep.size() < nl; cls++)
                 for (int p : freep)
-                    if (p % 3 == cls && !taken[p])
+                    if (p % 3 == cls && !taken[p] && (mode != kSwzTma || p < 6))
                     {
                         lanep.push_back(p);
                         taken[p] = 1;
@@ -459,9 +464,9 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                 if (!taken[p]) iterp.push_back(p);
             rd.n_iter = 1 << (int)iterp.size();
             rd.n_active = 1 << nl;
-            for (int l = 0; l < 32; l++) rd.lane_tab[l] = (uint16_t)swz_host(deposit((unsigned)l & ((1u << nl) - 1u), lanep));
+            for (int l = 0; l < 32; l++) rd.lane_tab[l] = (uint16_t)swz_host(deposit((unsigned)l & ((1u << nl) - 1u), lanep), mode);
             for (int it = 0; it < 8; it++)
-                rd.iter_tab[it] = (uint16_t)swz_host(deposit((unsigned)it & ((unsigned)rd.n_iter - 1u), iterp));
+                rd.iter_tab[it] = (uint16_t)swz_host(deposit((unsigned)it & ((unsigned)rd.n_iter - 1u), iterp), mode);
             out.rounds.push_back(rd);
 
             auto reg_pos = [&](int j) { // position of tile bit j among the round's register bits, -1 if none
@@ -748,7 +753,47 @@ void fill_sweep_tables(const Sweep& sw, int M, SweepArgs& a)
         }
         a.hin[it] = hi << 4; // BYTE offsets (16 B per element)
         a.hout[it] = ho << 4;
-        a.hs[it] = (unsigned short)swz_host(hs);
+        a.hs[it] = (unsigned short)swz_host(hs, sw.swz_mode);
+    }
+    a.swz_mode = sw.swz_mode;
+    a.tma_load = a.tma_store = 0;
+    if (sw.swz_mode == kSwzTma && k == kMaxTileBits && sw.in_pos[0] == 0 && sw.in_pos[1] == 1 && sw.in_pos[2] == 2)
+    {
+        // the box: the lowest tile bits, as runs of consecutive physical bits (dimension 0 = the 128-byte run, <= 8 bits
+        // per dimension, <= 5 dimensions, <= tma_box_bits bits); every other tile bit is enumerated by separate copies
+        TmaGeom& t = a.tma;
+        int nd = 0, nbox = 0;
+        int len[5] = {0, 0, 0, 0, 0};
+        for (int i = 0; i < k && nbox < sweep_tma_box_bits(); i++)
+        {
+            const int p = sw.in_pos[i];
+            const bool extend = nd > 0 && p == t.start[nd - 1] + len[nd - 1] && len[nd - 1] < (nd == 1 ? 3 : 8);
+            if (!extend)
+            {
+                if (nd == 5) break;
+                t.start[nd] = (unsigned char)p;
+                len[nd++] = 0;
+            }
+            len[nd - 1]++;
+            nbox++;
+        }
+        for (int d = 0; d < 5; d++)
+        {
+            if (d >= nd) t.start[d] = (unsigned char)M; // unit dimensions pad the rank to 5
+            t.box_log2[d] = (unsigned char)(d < nd ? len[d] : 0);
+        }
+        for (int d = 0; d < 5; d++) t.span[d] = (unsigned char)((d + 1 < 5 ? t.start[d + 1] : M) - t.start[d]);
+        t.n_enum = (unsigned char)(k - nbox);
+        t.n_copies = 1 << t.n_enum;
+        t.box_bytes = 16 << nbox;
+        for (int j = 0; j < t.n_copies; j++)
+        {
+            unsigned long long off = 0;
+            for (int b = 0; b < t.n_enum; b++) off |= (unsigned long long)((j >> b) & 1) << sw.in_pos[nbox + b];
+            t.enum_off[j] = off;
+        }
+        a.tma_load = 1;
+        a.tma_store = (sw.in_pos == sw.out_pos && !sw.out_of_place) ? 1 : 0;
     }
     std::vector<char> used_in(M, 0), used_out(M, 0);
     for (int i = 0; i < k; i++) { used_in[sw.in_pos[i]] = 1; used_out[sw.out_pos[i]] = 1; }
@@ -768,7 +813,17 @@ std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a)
         for (int i = 0; i < n; i++) o << (i ? "," : "") << (unsigned long long)v[i];
         o << "]";
     };
-    o << "{\"k\":" << a.k << ",\"n_comp\":" << a.n_comp << ",";
+    o << "{\"k\":" << a.k << ",\"n_comp\":" << a.n_comp << ",\"swz\":" << a.swz_mode << ",\"tma_load\":" << a.tma_load
+      << ",\"tma_store\":" << a.tma_store << ",";
+    if (a.tma_load)
+    {
+        o << "\"tma\":{\"n_copies\":" << a.tma.n_copies << ",\"box_bytes\":" << a.tma.box_bytes << ",";
+        arr("start", a.tma.start, 5); o << ",";
+        arr("span", a.tma.span, 5); o << ",";
+        arr("box_log2", a.tma.box_log2, 5); o << ",";
+        arr("enum_off", a.tma.enum_off, a.tma.n_copies);
+        o << "},";
+    }
     unsigned long long hin_e[kMaxIter], hout_e[kMaxIter]; // element offsets for the emulator
     for (int it = 0; it < kMaxIter; it++) { hin_e[it] = a.hin[it] >> 4; hout_e[it] = a.hout[it] >> 4; }
     arr("hin", hin_e, kMaxIter); o << ",";

@@ -20,6 +20,9 @@ struct EncodedSweep
 void encode_sweep(const Sweep& sw, EncodedSweep& out);
 // fills k, n_comp, n_tiles and every address table of `a` (pointers / counts are the caller's job)
 void fill_sweep_tables(const Sweep& sw, int M, SweepArgs& a);
+// largest TMA box in tile bits (2^bits elements of 16 bytes; default 10 = 16 KiB)
+void set_sweep_tma_box_bits(int bits);
+int sweep_tma_box_bits();
 // JSON text of the device tables of one sweep (for the CPU test-suite's kernel-indexing emulator)
 std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a);
 } // namespace dmb

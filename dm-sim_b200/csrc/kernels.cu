@@ -19,7 +19,7 @@ __global__ void init_state_kernel(double2* buf, size_t n, bool owns_origin)
 }
 void launch_init_state(double2* buf, size_t n, bool owns_origin, cudaStream_t s)
 {
-    const int grid = (int)min((size_t)148 * 16, (n + 255) / 256);
+    const int grid = (int)min((size_t)device_num_sms() * 16, (n + 255) / 256);
     init_state_kernel<<<grid, 256, 0, s>>>(buf, n, owns_origin);
 }
 
@@ -83,7 +83,7 @@ __global__ void trace_kernel(const double2* __restrict__ buf, const __grid_const
 void launch_trace(const double2* buf, const LayoutArgs& L, double* out, cudaStream_t s)
 {
     const unsigned long long dim = 1ull << L.n;
-    const unsigned grid = (unsigned)min((unsigned long long)148, (dim + 255) / 256);
+    const unsigned grid = (unsigned)min((unsigned long long)device_num_sms(), (dim + 255) / 256);
     trace_kernel<<<grid, 256, 0, s>>>(buf, L, out);
 }
 
@@ -101,7 +101,7 @@ __global__ void purity_kernel(const double2* __restrict__ buf, size_t n, double*
 }
 void launch_purity(const double2* buf, size_t n, double* out, cudaStream_t s)
 {
-    const unsigned grid = (unsigned)min((size_t)148 * 8, (n + 255) / 256);
+    const unsigned grid = (unsigned)min((size_t)device_num_sms() * 8, (n + 255) / 256);
     purity_kernel<<<grid, 256, 0, s>>>(buf, n, out);
 }
 
@@ -186,7 +186,7 @@ __global__ void gather_split_kernel(const double2* __restrict__ buf, const __gri
 void launch_gather_split(const double2* buf, const LayoutArgs& L, unsigned long long first, unsigned long long count,
                          double* re, double* im, cudaStream_t s)
 {
-    const unsigned grid = (unsigned)min((unsigned long long)148 * 16, (count + 255) / 256);
+    const unsigned grid = (unsigned)min((unsigned long long)device_num_sms() * 16, (count + 255) / 256);
     gather_split_kernel<<<grid, 256, 0, s>>>(buf, L, first, count, re, im);
 }
 
@@ -209,7 +209,7 @@ __global__ void gather_elements_kernel(const double2* __restrict__ buf, const __
 void launch_gather_elements(const double2* buf, const LayoutArgs& L, const unsigned long long* idx, unsigned long long count,
                             double* re, double* im, cudaStream_t s)
 {
-    const unsigned grid = (unsigned)min((unsigned long long)148 * 16, (count + 255) / 256);
+    const unsigned grid = (unsigned)min((unsigned long long)device_num_sms() * 16, (count + 255) / 256);
     gather_elements_kernel<<<grid, 256, 0, s>>>(buf, L, idx, count, re, im);
 }
 
@@ -228,7 +228,7 @@ __global__ void scatter_split_kernel(double2* __restrict__ buf, const __grid_con
 void launch_scatter_split(double2* buf, const LayoutArgs& L, unsigned long long first, unsigned long long count,
                           const double* re, const double* im, cudaStream_t s)
 {
-    const unsigned grid = (unsigned)min((unsigned long long)148 * 16, (count + 255) / 256);
+    const unsigned grid = (unsigned)min((unsigned long long)device_num_sms() * 16, (count + 255) / 256);
     scatter_split_kernel<<<grid, 256, 0, s>>>(buf, L, first, count, re, im);
 }
 } // namespace dmb

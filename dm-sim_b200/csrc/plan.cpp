@@ -841,6 +841,7 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
         }
         for (auto& mv : moves) phys[mv.first] = mv.second;
         for (int j = 0; j < sw.k; j++) sw.out_pos.push_back(phys[order[j]]);
+        sw.swz_mode = (opt.tma && sw.k == 12 && lowb >= 3) ? 1 : 0;
         sw.out_of_place = !moves.empty() && !in_place; // a permutation INSIDE the tile may run in place: every tile is read
                                                        // completely before it is written, to the same set of addresses
         plan.steps.push_back(st);
@@ -1112,7 +1113,7 @@ std::string plan_to_json(const Plan& p, const std::vector<std::string>* extra)
         if (st.kind == 1) { o << "{\"kind\":\"exchange\"}"; continue; }
         const Sweep& sw = st.sweep;
         o << "{\"kind\":\"sweep\",\"k\":" << sw.k << ",\"in_pos\":" << ivec(sw.in_pos) << ",\"out_pos\":" << ivec(sw.out_pos)
-          << ",\"out_of_place\":" << (sw.out_of_place ? "true" : "false") << ",\"weight\":" << sw.weight;
+          << ",\"out_of_place\":" << (sw.out_of_place ? "true" : "false") << ",\"swz\":" << sw.swz_mode << ",\"weight\":" << sw.weight;
         if (extra && s < extra->size() && !(*extra)[s].empty()) o << ",\"dev\":" << (*extra)[s];
         o << ",\"ops\":[";
         for (size_t i = 0; i < sw.ops.size(); i++)

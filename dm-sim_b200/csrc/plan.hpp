@@ -63,6 +63,8 @@ struct Sweep
     std::vector<int> in_pos;    // physical bit of tile-local bit j when loading (ascending)
     std::vector<int> out_pos;   // physical bit tile-local bit j is stored to (== in_pos unless permuting)
     bool out_of_place = false;  // reads buffer A, writes buffer B (then the buffers swap roles)
+    int swz_mode = 0;           // shared-memory swizzle of the tile (devop.hpp: kSwzXor3 / kSwzTma); kSwzTma <=> the tile
+                                // is moved by TMA (full-size tiles when PlanOptions::tma is on)
     std::vector<TileOp> ops;
     int weight = 0;
 };
@@ -84,6 +86,8 @@ struct PlanOptions
     int scan_window = 1536;  // pending ops a tile-selection scan looks at
     int max_cphase = 160;    // controlled phases per sweep (<= kMaxStarsPerSweep: each may need its own star slot)
     bool cphase = true;      // schedule controlled phases with only one bit in the tile (CLS_CPHASE)
+    bool tma = true;         // full-size tiles (k == 12) are loaded / stored by TMA (128-byte hardware swizzle)
+    int tma_box_bits = 10;   // largest TMA box: 2^10 elements = 16 KiB (the rest of the tile bits: separate copies)
 };
 
 struct Plan

@@ -20,7 +20,10 @@
 
 namespace dmb
 {
-__device__ __forceinline__ unsigned swz(unsigned e) { return e ^ ((e >> 3) & 7u) ^ ((e >> 6) & 7u) ^ ((e >> 9) & 7u); }
+__device__ __forceinline__ unsigned swz(unsigned e, int mode)
+{
+    return mode == kSwzTma ? e ^ ((e >> 3) & 7u) : e ^ ((e >> 3) & 7u) ^ ((e >> 6) & 7u) ^ ((e >> 9) & 7u);
+}
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b)
 {
@@ -71,6 +74,54 @@ __device__ __forceinline__ void cp_async16_u32(unsigned smem_dst, const void* gm
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// ---- TMA tile I/O (cp.async.bulk.tensor + mbarrier; SASS: UTMALDG / UTMASTG / SYNCS) ----
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    do
+    {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_5d(unsigned dst, const TmaDesc* map, unsigned bar, int c0, int c1, int c2, int c3, int c4)
+{
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const TmaDesc* map, unsigned src, int c0, int c1, int c2, int c3, int c4)
+{
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];\n"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_read()
+{
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// start coordinates of the box that holds element `full` (its box bits are zero): dimension d takes the index bits
+// [start[d], start[d] + span[d]); dimension 0 counts doubles (two per element)
+__device__ __forceinline__ void tma_coords(const TmaGeom& g, unsigned long long full, int (&c)[5])
+{
+#pragma unroll
+    for (int d = 0; d < 5; d++) c[d] = (int)((full >> g.start[d]) & ((1ull << g.span[d]) - 1ull));
+    c[0] <<= 1;
+}
 
 __device__ __forceinline__ void st_stream(double2* p, double2 v)
 {
@@ -393,11 +444,12 @@ __device__ __forceinline__ void apply_reg_op(double2 (&v)[E], const unsigned cha
 template <unsigned MASK>
 __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_constant__ SweepArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int k = a.k;
     const unsigned tile_elems = 1u << k;
     double2* tile = reinterpret_cast<double2*>(smem_raw);
-    unsigned char* s_ops = smem_raw + (size_t)16 * tile_elems;
+    // [tile | mbarrier (16 bytes) | op stream | rounds | groups | star tables]
+    unsigned char* s_ops = smem_raw + (size_t)16 * tile_elems + 16;
     DevRound* s_rounds = reinterpret_cast<DevRound*>(s_ops + a.ops_bytes);
     DevGroup* s_groups = reinterpret_cast<DevGroup*>(s_rounds + a.n_rounds);
     double2* s_star = reinterpret_cast<double2*>(s_groups + a.n_groups); // [n_stars][WO[8] | la[8] | lb[4]]
@@ -437,9 +489,17 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
         g_out_lo |= bit << a.gout[i];
         s_out_lo |= (unsigned)bit << a.sout[i];
     }
-    s_out_lo = swz(s_out_lo);
-    const unsigned s_in = swz((unsigned)t);
+    const int mode = a.swz_mode;
+    s_out_lo = swz(s_out_lo, mode);
+    const unsigned s_in = swz((unsigned)t, mode);
     const unsigned tile_u32 = (unsigned)__cvta_generic_to_shared(tile);
+    const unsigned bar_u32 = tile_u32 + 16u * tile_elems;
+    unsigned tma_phase = 0;
+    if (a.tma_load)
+    {
+        if (tile_u32 & 1023u) __trap(); // the hardware swizzle pattern is a function of the shared-memory ADDRESS
+        if (t == 0) mbar_init(bar_u32, 1);
+    }
     const double2* __restrict__ gin = reinterpret_cast<const double2*>(a.in);
     double2* __restrict__ gout = reinterpret_cast<double2*>(a.out);
     __syncthreads(); // program tables visible
@@ -453,8 +513,24 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
             base_in |= bit << a.cin[i];
             base_out |= bit << a.cout[i];
         }
-        // ---- load: 128-bit async copies straight into the swizzled tile; runs of >= 2^low_bits * 16 B ----
-        if (t_active)
+        // ---- load ----
+        if (a.tma_load)
+        {
+            // TMA: one thread issues the tile's boxes (128-byte rows, hardware 128-byte swizzle); everybody waits on the
+            // mbarrier after the star prologue below
+            if (t == 0)
+            {
+                mbar_expect_tx(bar_u32, 16u * tile_elems);
+                for (int j = 0; j < a.tma.n_copies; j++)
+                {
+                    int c[5];
+                    tma_coords(a.tma, base_in | a.tma.enum_off[j], c);
+                    tma_load_5d(tile_u32 + (unsigned)j * (unsigned)a.tma.box_bytes, &a.tmap_in, bar_u32, c[0], c[1], c[2], c[3], c[4]);
+                }
+            }
+        }
+        // legacy: 128-bit async copies straight into the swizzled tile; runs of >= 2^low_bits * 16 B
+        else if (t_active)
         {
             const char* src = reinterpret_cast<const char*>(gin + (base_in | g_in_lo));
             if (n_it == kMaxIter)
@@ -464,14 +540,14 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
 #pragma unroll
                 for (int it = 0; it < kMaxIter; it++)
                 {
-                    const unsigned l3 = (((unsigned)it << 1) ^ ((unsigned)it >> 2)) & 7u;
+                    const unsigned l3 = mode == kSwzTma ? 0u : ((((unsigned)it << 1) ^ ((unsigned)it >> 2)) & 7u);
                     cp_async16_u32(tile_u32 + ((s_in ^ l3) << 4) + ((unsigned)it << 11), src + a.hin[it]);
                 }
             }
             else
             {
 #pragma unroll 1 // (small tiles: a rolled loop keeps the kernel's instruction footprint down)
-                for (int it = 0; it < n_it; it++) cp_async16(&tile[swz((unsigned)(it << kThreadBits)) ^ s_in], src + a.hin[it]);
+                for (int it = 0; it < n_it; it++) cp_async16(&tile[swz((unsigned)(it << kThreadBits), mode) ^ s_in], src + a.hin[it]);
             }
         }
         cp_async_commit();
@@ -513,8 +589,17 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                 if (on) s_star[(i >> 3) * kStarEntries + (i & 7)] = cmul(acc, __ldg(reinterpret_cast<const double2*>(st->w) + (i & 7)));
             }
         }
-        cp_async_wait<0>();
-        __syncthreads();
+        if (a.tma_load)
+        {
+            if (DMB_HAS(RC_STAR)) __syncthreads(); // the star tables (written above) before anybody reads them
+            mbar_wait(bar_u32, tma_phase);
+            tma_phase ^= 1u;
+        }
+        else
+        {
+            cp_async_wait<0>();
+            __syncthreads();
+        }
 
         // ---- apply the sweep's ops: warp-local groups (CTA barrier only between groups) of register rounds
         //      (one shared-memory round trip per round, all its ops applied in registers) ----
@@ -576,8 +661,26 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
             __syncthreads();
         }
 
-        // ---- store (streaming, evict-first) ----
-        if (t_active)
+        // ---- store ----
+        if (a.tma_store)
+        {
+            // TMA: the generic-proxy writes of the rounds are fenced for the async proxy, then one thread issues the boxes
+            // and waits until they have been READ out of shared memory (the tile buffer is free again)
+            fence_proxy_async();
+            __syncthreads();
+            if (t == 0)
+            {
+                for (int j = 0; j < a.tma.n_copies; j++)
+                {
+                    int c[5];
+                    tma_coords(a.tma, base_out | a.tma.enum_off[j], c);
+                    tma_store_5d(&a.tmap_out, tile_u32 + (unsigned)j * (unsigned)a.tma.box_bytes, c[0], c[1], c[2], c[3], c[4]);
+                }
+                tma_store_commit_and_wait_read();
+            }
+        }
+        // legacy (streaming, evict-first)
+        else if (t_active)
         {
             if (a.peer_shift < 0)
             {
@@ -620,7 +723,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
     }
 }
 
-static int g_num_sms = 0;
+constexpr int kMaxDevices = 64;
+static int g_num_sms[kMaxDevices] = {0}; // per device: cudaFuncSetAttribute and the SM count are per-device state
 
 // instantiations, smallest first: a sweep runs on the first one that covers its op codes
 #define BIT(c) (1u << (c))
@@ -661,22 +765,36 @@ static int pick_variant(unsigned mask)
     return kNumVariants - 1;
 }
 
-void sweep_setup()
+static int current_device()
 {
-    if (g_num_sms) return;
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    return dev < 0 || dev >= kMaxDevices ? 0 : dev;
+}
+
+void sweep_setup()
+{
+    const int dev = current_device();
+    if (g_num_sms[dev]) return;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     VariantTable<kNumVariants - 1>::fill(g_variants);
-    const int max_smem = (16 << kMaxTileBits) + kMaxOpsPerSweep * (int)(sizeof(DevOp) + sizeof(DevRound) + sizeof(DevGroup)) +
+    const int max_smem = (16 << kMaxTileBits) + 16 + kMaxOpsPerSweep * (int)(sizeof(DevOp) + sizeof(DevRound) + sizeof(DevGroup)) +
                          kMaxStarsPerSweep * kStarSmemBytes;
     for (int i = 0; i < kNumVariants; i++)
         cudaFuncSetAttribute(g_variants[i], cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    g_num_sms[dev] = sms > 0 ? sms : 1;
+}
+
+int device_num_sms()
+{
+    sweep_setup();
+    return g_num_sms[current_device()];
 }
 
 size_t sweep_smem_bytes(const SweepArgs& a)
 {
-    return ((size_t)16 << a.k) + (size_t)a.ops_bytes + (size_t)a.n_rounds * sizeof(DevRound) +
+    return ((size_t)16 << a.k) + 16 + (size_t)a.ops_bytes + (size_t)a.n_rounds * sizeof(DevRound) +
            (size_t)a.n_groups * sizeof(DevGroup) + (size_t)a.n_stars * kStarSmemBytes;
 }
 
@@ -686,13 +804,13 @@ int sweep_max_grid(const SweepArgs& a)
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, g_variants[pick_variant(a.op_mask)], kTileThreads, sweep_smem_bytes(a));
     if (occ < 1) occ = 1;
-    return g_num_sms * occ;
+    return g_num_sms[current_device()] * occ;
 }
 
-void launch_sweep(const SweepArgs& a, int grid, cudaStream_t s)
+cudaError_t launch_sweep(const SweepArgs& a, int grid, cudaStream_t s)
 {
     sweep_setup();
     void* params[] = {const_cast<SweepArgs*>(&a)};
-    cudaLaunchKernel((const void*)g_variants[pick_variant(a.op_mask)], dim3(grid), dim3(kTileThreads), params, sweep_smem_bytes(a), s);
+    return cudaLaunchKernel((const void*)g_variants[pick_variant(a.op_mask)], dim3(grid), dim3(kTileThreads), params, sweep_smem_bytes(a), s);
 }
 } // namespace dmb

@@ -17,8 +17,33 @@ E = 16  # elements a lane keeps in registers per round (2^kRegBits)
 WB = 2  # log2(warps per CTA)
 
 
-def swz(e):
+def swz(e, mode=0):
+    """mode 0: the 3-term XOR swizzle; mode 1 (TMA tiles): the hardware's 128-byte swizzle (devop.hpp swz_host)."""
+    if mode == 1:
+        return e ^ ((e >> 3) & 7)
     return e ^ ((e >> 3) & 7) ^ ((e >> 6) & 7) ^ ((e >> 9) & 7)
+
+
+def _tma_load(dev, shard_in, base_in):
+    """The tile as the TMA path fills it: copy j = one box at byte offset j * box_bytes; inside a box the dimensions are
+    laid out dimension 0 fastest; the 16-byte chunk of every 128-byte row is XORed with (row & 7)."""
+    g = dev["tma"]
+    k = dev["k"]
+    tiles = np.full((base_in.size, 1 << k), np.nan + 0j, dtype=np.complex128)
+    box_elems = g["box_bytes"] // 16
+    e = np.arange(box_elems, dtype=np.int64)
+    off = np.zeros_like(e)  # element offset of box-local index e in the shard
+    bit = 0
+    for d in range(5):
+        for b in range(g["box_log2"][d]):
+            off |= ((e >> bit) & 1) << (g["start"][d] + b)
+            bit += 1
+    assert (1 << bit) == box_elems
+    for j in range(g["n_copies"]):
+        src = (base_in[:, None] | int(g["enum_off"][j])) + off[None, :]
+        local = j * box_elems + e
+        tiles[:, swz(local, 1)] = shard_in[src]
+    return tiles
 
 
 def _dep(v, pos):
@@ -40,16 +65,20 @@ def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = No
     act = t < tile_elems
     g_in_lo = _dep(t, dev["gin"][:klo])
     g_out_lo = _dep(t, dev["gout"][:klo])
-    s_out_lo = swz(_dep(t, dev["sout"][:klo]))
-    s_in = swz(t)
+    mode = dev.get("swz", 0)
+    s_out_lo = swz(_dep(t, dev["sout"][:klo]), mode)
+    s_in = swz(t, mode)
     tid = np.arange(n_tiles, dtype=np.int64)
     base_in = _dep(tid, dev["cin"])
     base_out = _dep(tid, dev["cout"])
 
-    tiles = np.full((n_tiles, tile_elems), np.nan + 0j, dtype=np.complex128)
-    for it in range(n_it):
-        src = (base_in[:, None] | g_in_lo[None, act]) + int(dev["hin"][it])
-        tiles[:, swz(it << TB) ^ s_in[act]] = shard_in[src]
+    if dev.get("tma_load"):
+        tiles = _tma_load(dev, shard_in, base_in)
+    else:
+        tiles = np.full((n_tiles, tile_elems), np.nan + 0j, dtype=np.complex128)
+        for it in range(n_it):
+            src = (base_in[:, None] | g_in_lo[None, act]) + int(dev["hin"][it])
+            tiles[:, swz(it << TB, mode) ^ s_in[act]] = shard_in[src]
     assert not np.isnan(tiles.real).any(), "load did not fill the tile"
 
     full = base_in | (rank << (k + n_comp))  # the full physical index of the tile's first element (rank bits on top)

@@ -61,6 +61,35 @@ def test_random_circuits_every_geometry(dm, oracle_mod, opts, n, world, o):
         assert plan["n_exchanges"] >= 1
 
 
+@pytest.mark.parametrize("n,world,o", [
+    (7, 1, dict(min_tiles_log2=2)), (7, 2, dict(min_tiles_log2=1)), (7, 1, dict(min_tiles_log2=2, tma_box_bits=12)),
+    (7, 1, dict(min_tiles_log2=2, tma_box_bits=7)), (7, 1, dict(min_tiles_log2=2, tma=0)),
+])
+def test_full_size_tiles_tma_addressing(dm, oracle_mod, opts, n, world, o):
+    """k = 12 tiles: TMA boxes (5-D tensor view of the shard, enumerated copies), the hardware 128-byte swizzle and the
+    lane-bit choice that goes with it -- walked by the kernel emulator exactly as the device does."""
+    opts(**o)
+    try:
+        rng = np.random.default_rng(77 + world)
+        gates = random_gates(n, 60, rng, exclude=("SRN",))
+        re, im = oracle_mod.Oracle(n).sim(gates).dm()
+        plan = dm.plan_json(n, world, gates)
+        sweeps = [st for st in plan["steps"] if st["kind"] == "sweep"]
+        assert any(st["k"] == 12 for st in sweeps)
+        want_tma = o.get("tma", 1)
+        for st in sweeps:
+            if st["k"] == 12:
+                assert st["dev"]["tma_load"] == want_tma and st["dev"]["swz"] == want_tma
+                if want_tma:
+                    g = st["dev"]["tma"]
+                    assert g["n_copies"] * g["box_bytes"] == 16 << 12 and g["start"][0] == 0 and g["box_log2"][0] == 3
+                    assert all(b <= 8 for b in g["box_log2"])
+                    assert st["dev"]["tma_store"] == int(st["in_pos"] == st["out_pos"] and not st["out_of_place"])
+        assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - to_complex(re, im)).max() < TOL
+    finally:
+        dm.set_option("tma", 1); dm.set_option("tma_box_bits", 10)
+
+
 def test_each_op_alone(dm, oracle_mod):
     rng = np.random.default_rng(3)
     n = 5
