@@ -32,6 +32,7 @@ OP_NAMES = [
 ]
 OP = {name: i for i, name in enumerate(OP_NAMES)}
 OP_C1, OP_C2 = 100, 101
+ALL_RANKS = -1  # DMB_ALL_RANKS: one handle drives all n_gpus devices of this process
 
 GATE_DTYPE = np.dtype(
     [("op", "<i4"), ("qb", "<i4", (5,)), ("theta", "<f8"), ("phi", "<f8"), ("lam", "<f8"), ("mat", "<i8")],
@@ -173,8 +174,10 @@ class Simulation:
     """Drop-in for DMSim::Simulation (reference src/dmsim_nvgpu_omp.cuh:193-814) as seen from Python.
 
     ``Simulation(n_qubits, n_gpus)``: with n_gpus == 1 everything runs on the current CUDA device.  With
-    n_gpus > 1 the object is ONE RANK of a one-process-per-GPU job (rank / world size come from
-    ``torch.distributed``, which must be initialised; see ``attach_communicator``).
+    n_gpus > 1 and no ``rank`` the object drives devices 0 .. n_gpus-1 from THIS process, like the reference
+    (src/py_nvgpu_omp_wrapper.cu:36-37) -- unless a ``torch.distributed`` job with world_size == n_gpus is
+    running (torchrun, one process per GPU): then, or when ``rank`` is given, the object is ONE RANK of that job
+    (see ``attach_communicator``) and its result calls are collective.
     """
 
     def __init__(self, n_qubits, n_gpus=1, rank=None, device=-1):
@@ -183,19 +186,20 @@ class Simulation:
         self.circuit = []
         self._uploaded = False
         self.last_stats = None
+        self.group = False
         if rank is None:
             rank = 0
             if self.n_gpus > 1:
-                import torch.distributed as dist
-                if not dist.is_initialized() or dist.get_world_size() != self.n_gpus:
-                    raise DMSimError("n_gpus > 1 needs torch.distributed initialised with world_size == n_gpus "
-                                     "(one process per GPU)")
-                rank = dist.get_rank()
+                dist = getattr(sys.modules.get("torch"), "distributed", None)
+                if dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() == self.n_gpus:
+                    rank = dist.get_rank()
+                else:
+                    rank, self.group = ALL_RANKS, True
         self.rank = rank
         h = ctypes.c_void_p()
         _check(lib().dmb_create(self.n_qubits, self.n_gpus, self.rank, device, ctypes.byref(h)))
         self._h = h
-        if self.n_gpus > 1:
+        if self.n_gpus > 1 and not self.group:
             self.attach_communicator()
 
     def attach_communicator(self):
@@ -334,8 +338,9 @@ class Simulation:
         return v.value
 
     def shard(self):
-        """(interleaved complex shard in PHYSICAL order, phys_of_logical[2n])."""
-        elems = (self.dim * self.dim) // self.n_gpus
+        """(interleaved complex shard in PHYSICAL order, phys_of_logical[2n]); a single-process group returns all its
+        shards back to back (the whole state in physical order)."""
+        elems = (self.dim * self.dim) // (1 if self.group else self.n_gpus)
         data = np.empty(elems, dtype=np.complex128)
         lay = np.zeros(2 * self.n_qubits, dtype=np.int32)
         _check(lib().dmb_get_shard(self._h, data.ctypes.data, lay.ctypes.data))

@@ -57,6 +57,7 @@ static void init_options()
     if (const char* e = getenv("DMB_SPARSE")) g_sparse_start = atoi(e);
     if (const char* e = getenv("DMB_TMA")) g_opt.tma = atoi(e) != 0;
     if (const char* e = getenv("DMB_TMA_BOX_BITS")) set_sweep_tma_box_bits(atoi(e));
+    if (const char* e = getenv("DMB_DENSE2_LU")) set_sweep_dense2_lu(atoi(e) != 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -220,6 +221,20 @@ struct dmb_sim
     bool p2p = false;
     double2* peer[2][8] = {{nullptr}};
     double* d_barrier = nullptr; // 2 doubles: all-reduce source / sink used as the cross-GPU barrier
+
+    // host copies of the device tables of the current plan (a group shares ONE plan between its shards)
+    std::vector<unsigned char> host_ops;
+    std::vector<DevStar> host_stars;
+    std::vector<DevRound> host_rounds;
+    std::vector<DevGroup> host_groups;
+
+    // Single-process multi-GPU (reference Simulation(n_qubits, n_gpus), :196-271: one host process drives all devices):
+    // a GROUP handle (rank == DMB_ALL_RANKS) owns one shard object per device and no buffers of its own.  The shards
+    // see each other's buffers through cudaDeviceEnablePeerAccess (no IPC), the cross-GPU barrier of the remap is a
+    // pair of CUDA events per shard (no NCCL).
+    std::vector<dmb_sim*> shards;
+    bool in_group = false;
+    cudaEvent_t ev_pre = nullptr, ev_post = nullptr;
 };
 
 static LayoutArgs layout_args(const dmb_sim* s)
@@ -255,48 +270,24 @@ static void drop_graph(dmb_sim* s)
     s->graph_cur = -1;
 }
 
-extern "C" {
 
-const char* dmb_last_error(void) { return g_err.c_str(); }
-const char* dmb_version(void) { return "dmsim-b200 0.1 (sm_100a)"; }
+// ------------------------------------------------------------------------------------------------
+// helpers shared by the single-shard and the group forms
+// ------------------------------------------------------------------------------------------------
+static bool is_group(const dmb_sim* s) { return !s->shards.empty(); }
 
-int dmb_set_option(const char* name, int64_t value)
+// cross-rank sum of `count` doubles in place on s->stream (one-process-per-GPU form, communicator attached)
+static int all_reduce_sum(dmb_sim* s, double* d_buf, size_t count)
 {
-    init_options();
-    if (!name) return fail(DMB_EINVAL, "null option name");
-    if (!strcmp(name, "tile_bits")) g_opt.tile_bits = (int)value;
-    else if (!strcmp(name, "low_bits")) g_opt.low_bits = (int)value;
-    else if (!strcmp(name, "min_tiles_log2")) g_opt.min_tiles_log2 = (int)value;
-    else if (!strcmp(name, "graph")) g_use_graph = (int)value;
-    else if (!strcmp(name, "cphase")) g_opt.cphase = value != 0;
-    else if (!strcmp(name, "sparse")) g_sparse_start = (int)value;
-    else if (!strcmp(name, "move_h")) g_opt.move_h = value != 0;
-    else if (!strcmp(name, "hot_low")) g_opt.hot_low = value != 0;
-    else if (!strcmp(name, "tma")) g_opt.tma = value != 0;
-    else if (!strcmp(name, "tma_box_bits")) set_sweep_tma_box_bits((int)value);
-    else return fail(DMB_EINVAL, std::string("unknown option ") + name);
+    const int nr = g_nccl.AllReduce(d_buf, d_buf, count, kNcclDouble, 0 /* ncclSum */, s->comm, s->stream);
+    if (nr != 0) return fail(DMB_ECOMM, std::string("NCCL all-reduce failed: ") + g_nccl.GetErrorString(nr));
     return DMB_OK;
 }
+// results of a sharded state are GLOBAL (every rank gets the full answer) when the ranks can talk to each other
+static bool collective(const dmb_sim* s) { return s->world > 1 && !s->in_group && s->comm != nullptr; }
 
-int dmb_create(int n_qubits, int world_size, int rank, int device, dmb_handle* out)
+static int create_shard(int n_qubits, int world_size, int g, int rank, int device, dmb_sim** out)
 {
-    init_options();
-    if (!out) return fail(DMB_EINVAL, "null out handle");
-    *out = nullptr;
-    if (n_qubits < 1 || n_qubits > 20) return fail(DMB_EINVAL, "n_qubits must be in [1, 20]");
-    int g = 0;
-    while ((1 << g) < world_size) g++;
-    // reference ctor (:218-229): n_gpus must be a power of two and divide 2^n
-    if (world_size < 1 || (1 << g) != world_size) return fail(DMB_EINVAL, "world_size must be a power of two");
-    if (g > n_qubits) return fail(DMB_EINVAL, "world_size must divide 2^n_qubits");
-    if (rank < 0 || rank >= world_size) return fail(DMB_EINVAL, "rank out of range");
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0)
-        return fail(DMB_ECUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(e) +
-                                   " (this engine has no CPU fallback)");
-    if (device < 0) CU(cudaGetDevice(&device));
-    if (device >= ndev) return fail(DMB_EINVAL, "device index out of range");
     CU(cudaSetDevice(device));
     dmb_sim* s = new dmb_sim;
     s->n = n_qubits; s->g = g; s->world = world_size; s->rank = rank; s->device = device;
@@ -313,16 +304,15 @@ int dmb_create(int n_qubits, int world_size, int rank, int device, dmb_handle* o
     CU(cudaEventCreate(&s->ev_end));
     s->layout.resize(s->N);
     *out = s;
-    return dmb_reset_dm(s);
+    return DMB_OK;
 }
 
-int dmb_destroy(dmb_handle s)
+static int destroy_shard(dmb_sim* s)
 {
-    if (!s) return DMB_OK;
     cudaSetDevice(s->device);
     drop_graph(s);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
-    if (s->p2p)
+    if (s->p2p && !s->in_group)
         for (int b = 0; b < 2; b++)
             for (int r = 0; r < s->world; r++)
                 if (r != s->rank && s->peer[b][r]) cudaIpcCloseMemHandle(s->peer[b][r]);
@@ -330,6 +320,8 @@ int dmb_destroy(dmb_handle s)
     for (auto ev : s->ev_comm) cudaEventDestroy(ev);
     if (s->ev_begin) cudaEventDestroy(s->ev_begin);
     if (s->ev_end) cudaEventDestroy(s->ev_end);
+    if (s->ev_pre) cudaEventDestroy(s->ev_pre);
+    if (s->ev_post) cudaEventDestroy(s->ev_post);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->buf[0]) cudaFree(s->buf[0]);
     if (s->buf[1]) cudaFree(s->buf[1]);
@@ -342,51 +334,210 @@ int dmb_destroy(dmb_handle s)
     return DMB_OK;
 }
 
-int dmb_reset_dm(dmb_handle s)
+static int reset_shard(dmb_sim* s)
 {
-    if (!s) return fail(DMB_EINVAL, "null handle");
     CU(cudaSetDevice(s->device));
     for (int l = 0; l < s->N; l++) s->layout[l] = l;
     s->conj_flag = false;
     s->non_hermitian = false;
-    s->cur = 0;
+    // (the current buffer index is kept: with peer-memory remaps every rank must agree on it, and a rank that has not
+    // reached this reset yet may still be read or written through the other buffer)
     s->support = (s->world == 1 && g_sparse_start) ? 0ull : ~0ull;
-    launch_init_state(s->buf[0], s->shard_elems, s->rank == 0, s->stream);
+    launch_init_state(s->buf[s->cur], s->shard_elems, s->rank == 0, s->stream);
     CU(cudaGetLastError());
     // no synchronisation: everything that touches the state is ordered on s->stream, so the 16 B/element clear overlaps
     // the host-side planning of the next dmb_set_circuit
     return DMB_OK;
 }
 
+template <typename T>
+static int grow_device(T*& ptr, size_t& cap, size_t need)
+{
+    if (need <= cap) return DMB_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    CU(cudaMalloc(&ptr, need * sizeof(T)));
+    cap = need;
+    return DMB_OK;
+}
+
+extern "C" {
+
+const char* dmb_last_error(void) { return g_err.c_str(); }
+const char* dmb_version(void) { return "dmsim-b200 0.2 (sm_100a)"; }
+
+int dmb_set_option(const char* name, int64_t value)
+{
+    init_options();
+    if (!name) return fail(DMB_EINVAL, "null option name");
+    if (!strcmp(name, "tile_bits")) g_opt.tile_bits = (int)value;
+    else if (!strcmp(name, "low_bits")) g_opt.low_bits = (int)value;
+    else if (!strcmp(name, "min_tiles_log2")) g_opt.min_tiles_log2 = (int)value;
+    else if (!strcmp(name, "graph")) g_use_graph = (int)value;
+    else if (!strcmp(name, "cphase")) g_opt.cphase = value != 0;
+    else if (!strcmp(name, "sparse")) g_sparse_start = (int)value;
+    else if (!strcmp(name, "move_h")) g_opt.move_h = value != 0;
+    else if (!strcmp(name, "hot_low")) g_opt.hot_low = value != 0;
+    else if (!strcmp(name, "tma")) g_opt.tma = value != 0;
+    else if (!strcmp(name, "tma_box_bits")) set_sweep_tma_box_bits((int)value);
+    else if (!strcmp(name, "dense2_lu")) set_sweep_dense2_lu(value != 0);
+    else return fail(DMB_EINVAL, std::string("unknown option ") + name);
+    return DMB_OK;
+}
+
+int dmb_create(int n_qubits, int world_size, int rank, int device, dmb_handle* out)
+{
+    init_options();
+    if (!out) return fail(DMB_EINVAL, "null out handle");
+    *out = nullptr;
+    if (n_qubits < 1 || n_qubits > 20) return fail(DMB_EINVAL, "n_qubits must be in [1, 20]");
+    int g = 0;
+    while ((1 << g) < world_size) g++;
+    // reference ctor (:218-229): n_gpus must be a power of two and divide 2^n
+    if (world_size < 1 || (1 << g) != world_size) return fail(DMB_EINVAL, "world_size must be a power of two");
+    if (g > n_qubits) return fail(DMB_EINVAL, "world_size must divide 2^n_qubits");
+    const bool group = rank == DMB_ALL_RANKS && world_size > 1;
+    if (rank == DMB_ALL_RANKS && world_size == 1) rank = 0;
+    if (!group && (rank < 0 || rank >= world_size)) return fail(DMB_EINVAL, "rank out of range");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(DMB_ECUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(e) +
+                                   " (this engine has no CPU fallback)");
+    if (!group)
+    {
+        if (device < 0) CU(cudaGetDevice(&device));
+        if (device >= ndev) return fail(DMB_EINVAL, "device index out of range");
+        dmb_sim* s = nullptr;
+        int rc = create_shard(n_qubits, world_size, g, rank, device, &s);
+        if (rc) return rc;
+        *out = s;
+        return dmb_reset_dm(s);
+    }
+    // ---- group: all world_size shards in this process, devices [first, first + world_size) ----
+    if (world_size > 8) return fail(DMB_EINVAL, "a single-process group supports up to 8 GPUs (one NVSwitch node)");
+    const int first = device < 0 ? 0 : device;
+    if (first + world_size > ndev)
+        return fail(DMB_EINVAL, "n_gpus = " + std::to_string(world_size) + " but only " + std::to_string(ndev) +
+                                    " CUDA devices are visible");
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
+    dmb_sim* grp = new dmb_sim;
+    grp->n = n_qubits; grp->g = g; grp->world = world_size; grp->rank = DMB_ALL_RANKS; grp->device = first;
+    grp->N = 2 * n_qubits; grp->M = grp->N - g;
+    grp->shard_elems = (size_t)1 << grp->M;
+    auto bail = [&](int rc) {
+        for (dmb_sim* c : grp->shards) destroy_shard(c);
+        delete grp;
+        cudaSetDevice(prev_dev);
+        return rc;
+    };
+    // every pair must be able to map each other's memory (reference :266-269 requires the same full P2P mesh)
+    for (int a = 0; a < world_size; a++)
+    {
+        if (cudaSetDevice(first + a) != cudaSuccess) return bail(fail(DMB_ECUDA, "cudaSetDevice failed"));
+        for (int b = 0; b < world_size; b++)
+        {
+            if (a == b) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, first + a, first + b);
+            if (!can)
+                return bail(fail(DMB_ECOMM, "device " + std::to_string(first + a) + " cannot access device " +
+                                                std::to_string(first + b) + " (peer access is required for n_gpus > 1)"));
+            cudaError_t pe = cudaDeviceEnablePeerAccess(first + b, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+                return bail(fail(DMB_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe)));
+            cudaGetLastError();
+        }
+    }
+    for (int r = 0; r < world_size; r++)
+    {
+        dmb_sim* c = nullptr;
+        int rc = create_shard(n_qubits, world_size, g, r, first + r, &c);
+        if (rc) return bail(rc);
+        c->in_group = true;
+        grp->shards.push_back(c);
+        rc = ensure_second_buffer(c);
+        if (rc) return bail(rc);
+        if (cudaEventCreateWithFlags(&c->ev_pre, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_post, cudaEventDisableTiming) != cudaSuccess)
+            return bail(fail(DMB_ECUDA, "cudaEventCreate failed"));
+    }
+    for (dmb_sim* c : grp->shards)
+    {
+        for (int r = 0; r < world_size; r++)
+            for (int b = 0; b < 2; b++) c->peer[b][r] = grp->shards[r]->buf[b];
+        c->p2p = true;
+    }
+    grp->layout.resize(grp->N);
+    *out = grp;
+    int rc = dmb_reset_dm(grp);
+    cudaSetDevice(prev_dev);
+    return rc;
+}
+
+int dmb_destroy(dmb_handle s)
+{
+    if (!s) return DMB_OK;
+    if (is_group(s))
+    {
+        for (dmb_sim* c : s->shards) destroy_shard(c);
+        delete s;
+        return DMB_OK;
+    }
+    return destroy_shard(s);
+}
+
+int dmb_reset_dm(dmb_handle s)
+{
+    if (!s) return fail(DMB_EINVAL, "null handle");
+    if (is_group(s))
+    {
+        for (dmb_sim* c : s->shards)
+        {
+            int rc = reset_shard(c);
+            if (rc) return rc;
+        }
+        return DMB_OK;
+    }
+    return reset_shard(s);
+}
+
+// Load an arbitrary state.  Every shard scatters the elements it owns out of the staged host chunk.
 int dmb_set_dm(dmb_handle s, const double* real, const double* imag)
 {
     if (!s || !real || !imag) return fail(DMB_EINVAL, "null argument");
-    if (s->world != 1) return fail(DMB_ESTATE, "dmb_set_dm needs world_size == 1");
-    CU(cudaSetDevice(s->device));
-    for (int l = 0; l < s->N; l++) s->layout[l] = l;
-    s->conj_flag = false;
-    s->non_hermitian = true; // arbitrary input: keep the reference's exact frame semantics from here on
-    s->support = ~0ull;
+    std::vector<dmb_sim*> mem = is_group(s) ? s->shards : std::vector<dmb_sim*>{s};
     const unsigned long long total = 1ull << s->N;
     const unsigned long long chunk = std::min<unsigned long long>(total, 1ull << 24);
-    int rc = ensure_scratch(s, chunk * 2 * sizeof(double));
-    if (rc) return rc;
-    const LayoutArgs L = layout_args(s);
-    double* d_re = s->d_scratch;
-    double* d_im = s->d_scratch + chunk;
-    for (unsigned long long first = 0; first < total; first += chunk)
+    for (dmb_sim* c : mem)
     {
-        CU(cudaMemcpyAsync(d_re, real + first, chunk * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-        CU(cudaMemcpyAsync(d_im, imag + first, chunk * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-        launch_scatter_split(s->buf[s->cur], L, first, chunk, d_re, d_im, s->stream);
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaSetDevice(c->device));
+        for (int l = 0; l < c->N; l++) c->layout[l] = l;
+        c->conj_flag = false;
+        c->non_hermitian = true; // arbitrary input: keep the reference's exact frame semantics from here on
+        c->support = ~0ull;
+        int rc = ensure_scratch(c, chunk * 2 * sizeof(double));
+        if (rc) return rc;
+        const LayoutArgs L = layout_args(c);
+        double* d_re = c->d_scratch;
+        double* d_im = c->d_scratch + chunk;
+        for (unsigned long long first = 0; first < total; first += chunk)
+        {
+            CU(cudaMemcpyAsync(d_re, real + first, chunk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(d_im, imag + first, chunk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            launch_scatter_split(c->buf[c->cur], L, first, chunk, d_re, d_im, c->stream);
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(c->stream));
+        }
     }
     return DMB_OK;
 }
 
 // ---- circuit ----------------------------------------------------------------------------------
-static int build_plan(dmb_sim* s)
+// host part: plan + encode into s->host_* (no CUDA calls)
+static int plan_and_encode(dmb_sim* s)
 {
     try
     {
@@ -404,12 +555,8 @@ static int build_plan(dmb_sim* s)
     s->plan_layout = s->layout;
     s->plan_conj = s->conj_flag;
     s->plan_nonherm = s->non_hermitian;
-    drop_graph(s);
     // device op / group tables: one contiguous upload each (the reference does 3 CUDA calls per gate per GPU, :112-163)
-    std::vector<unsigned char> host_ops;
-    std::vector<DevStar> host_stars;
-    std::vector<DevRound> host_rounds;
-    std::vector<DevGroup> host_groups;
+    s->host_ops.clear(); s->host_stars.clear(); s->host_rounds.clear(); s->host_groups.clear();
     const size_t nsteps = s->plan.steps.size();
     s->op_offset.assign(nsteps, 0);
     s->round_offset.assign(nsteps, 0);
@@ -423,10 +570,10 @@ static int build_plan(dmb_sim* s)
     EncodedSweep enc;
     for (size_t i = 0; i < nsteps; i++)
     {
-        s->op_offset[i] = host_ops.size();
-        s->round_offset[i] = host_rounds.size();
-        s->group_offset[i] = host_groups.size();
-        s->star_offset[i] = host_stars.size();
+        s->op_offset[i] = s->host_ops.size();
+        s->round_offset[i] = s->host_rounds.size();
+        s->group_offset[i] = s->host_groups.size();
+        s->star_offset[i] = s->host_stars.size();
         if (s->plan.steps[i].kind != 0) continue;
         try
         {
@@ -439,69 +586,81 @@ static int build_plan(dmb_sim* s)
         s->n_dev_ops[i] = (int)enc.stream.size(); // bytes
         s->n_dev_stars[i] = (int)enc.stars.size();
         s->op_masks[i] = enc.op_mask;
-        host_stars.insert(host_stars.end(), enc.stars.begin(), enc.stars.end());
+        s->host_stars.insert(s->host_stars.end(), enc.stars.begin(), enc.stars.end());
         s->n_dev_rounds[i] = (int)enc.rounds.size();
         s->n_dev_groups[i] = (int)enc.groups.size();
-        host_ops.insert(host_ops.end(), enc.stream.begin(), enc.stream.end());
-        host_rounds.insert(host_rounds.end(), enc.rounds.begin(), enc.rounds.end());
-        host_groups.insert(host_groups.end(), enc.groups.begin(), enc.groups.end());
+        s->host_ops.insert(s->host_ops.end(), enc.stream.begin(), enc.stream.end());
+        s->host_rounds.insert(s->host_rounds.end(), enc.rounds.begin(), enc.rounds.end());
+        s->host_groups.insert(s->host_groups.end(), enc.groups.begin(), enc.groups.end());
     }
+    return DMB_OK;
+}
+
+// shard `s` takes over the plan (and host tables) of `src` (another shard of the same group, same layout)
+static void adopt_plan(dmb_sim* s, const dmb_sim* src)
+{
+    s->plan = src->plan;
+    s->plan_layout = src->plan_layout; s->plan_conj = src->plan_conj; s->plan_nonherm = src->plan_nonherm;
+    s->op_offset = src->op_offset; s->round_offset = src->round_offset; s->group_offset = src->group_offset;
+    s->star_offset = src->star_offset; s->n_dev_ops = src->n_dev_ops; s->n_dev_rounds = src->n_dev_rounds;
+    s->n_dev_groups = src->n_dev_groups; s->n_dev_stars = src->n_dev_stars; s->op_masks = src->op_masks;
+    s->host_ops = src->host_ops; s->host_stars = src->host_stars; s->host_rounds = src->host_rounds;
+    s->host_groups = src->host_groups;
+}
+
+// device part: the single H2D of the step (stream-ordered; the copies are flushed before returning because the host
+// vectors may be rebuilt by the next dmb_set_circuit)
+static int upload_tables(dmb_sim* s)
+{
+    drop_graph(s);
     CU(cudaSetDevice(s->device));
-    if (host_ops.size() > s->d_ops_cap)
+    int rc;
+    if ((rc = grow_device(s->d_ops, s->d_ops_cap, s->host_ops.size()))) return rc;
+    if ((rc = grow_device(s->d_stars, s->d_stars_cap, s->host_stars.size()))) return rc;
+    if ((rc = grow_device(s->d_rounds, s->d_rounds_cap, s->host_rounds.size()))) return rc;
+    if ((rc = grow_device(s->d_groups, s->d_groups_cap, s->host_groups.size()))) return rc;
+    s->h2d_bytes = s->host_ops.size() + s->host_stars.size() * sizeof(DevStar) + s->host_rounds.size() * sizeof(DevRound) +
+                   s->host_groups.size() * sizeof(DevGroup);
+    if (!s->host_ops.empty())
     {
-        if (s->d_ops) cudaFree(s->d_ops);
-        s->d_ops = nullptr;
-        s->d_ops_cap = 0;
-        CU(cudaMalloc(&s->d_ops, host_ops.size()));
-        s->d_ops_cap = host_ops.size();
-    }
-    if (host_stars.size() > s->d_stars_cap)
-    {
-        if (s->d_stars) cudaFree(s->d_stars);
-        s->d_stars = nullptr;
-        s->d_stars_cap = 0;
-        CU(cudaMalloc(&s->d_stars, host_stars.size() * sizeof(DevStar)));
-        s->d_stars_cap = host_stars.size();
-    }
-    if (host_rounds.size() > s->d_rounds_cap)
-    {
-        if (s->d_rounds) cudaFree(s->d_rounds);
-        s->d_rounds = nullptr;
-        s->d_rounds_cap = 0;
-        CU(cudaMalloc(&s->d_rounds, host_rounds.size() * sizeof(DevRound)));
-        s->d_rounds_cap = host_rounds.size();
-    }
-    if (host_groups.size() > s->d_groups_cap)
-    {
-        if (s->d_groups) cudaFree(s->d_groups);
-        s->d_groups = nullptr;
-        s->d_groups_cap = 0;
-        CU(cudaMalloc(&s->d_groups, host_groups.size() * sizeof(DevGroup)));
-        s->d_groups_cap = host_groups.size();
-    }
-    s->h2d_bytes = host_ops.size() + host_stars.size() * sizeof(DevStar) + host_rounds.size() * sizeof(DevRound) +
-                   host_groups.size() * sizeof(DevGroup);
-    if (!host_ops.empty())
-    {
-        CU(cudaMemcpyAsync(s->d_ops, host_ops.data(), host_ops.size(), cudaMemcpyHostToDevice, s->stream));
-        if (!host_stars.empty())
-            CU(cudaMemcpyAsync(s->d_stars, host_stars.data(), host_stars.size() * sizeof(DevStar), cudaMemcpyHostToDevice,
+        CU(cudaMemcpyAsync(s->d_ops, s->host_ops.data(), s->host_ops.size(), cudaMemcpyHostToDevice, s->stream));
+        if (!s->host_stars.empty())
+            CU(cudaMemcpyAsync(s->d_stars, s->host_stars.data(), s->host_stars.size() * sizeof(DevStar), cudaMemcpyHostToDevice,
                                s->stream));
-        CU(cudaMemcpyAsync(s->d_rounds, host_rounds.data(), host_rounds.size() * sizeof(DevRound), cudaMemcpyHostToDevice,
+        CU(cudaMemcpyAsync(s->d_rounds, s->host_rounds.data(), s->host_rounds.size() * sizeof(DevRound), cudaMemcpyHostToDevice,
                            s->stream));
-        CU(cudaMemcpyAsync(s->d_groups, host_groups.data(), host_groups.size() * sizeof(DevGroup), cudaMemcpyHostToDevice,
+        CU(cudaMemcpyAsync(s->d_groups, s->host_groups.data(), s->host_groups.size() * sizeof(DevGroup), cudaMemcpyHostToDevice,
                            s->stream));
         CU(cudaStreamSynchronize(s->stream));
     }
     return DMB_OK;
 }
 
+static int build_plan(dmb_sim* s)
+{
+    if (is_group(s))
+    {
+        dmb_sim* lead = s->shards[0];
+        int rc = plan_and_encode(lead); // ONE plan: it depends on (world, layout), not on the rank
+        if (rc) return rc;
+        for (dmb_sim* c : s->shards)
+        {
+            if (c != lead) adopt_plan(c, lead);
+            if ((rc = upload_tables(c))) return rc;
+        }
+        return DMB_OK;
+    }
+    int rc = plan_and_encode(s);
+    return rc ? rc : upload_tables(s);
+}
+
 int dmb_set_circuit(dmb_handle s, const dmb_gate* gates, size_t n_gates, const double* mats, size_t n_mats)
 {
     if (!s) return fail(DMB_EINVAL, "null handle");
     if (n_gates && !gates) return fail(DMB_EINVAL, "null gate list");
-    s->gates.assign(gates, gates + n_gates);
-    s->mats.assign(mats ? mats : nullptr, mats ? mats + 32 * n_mats : nullptr);
+    dmb_sim* owner = is_group(s) ? s->shards[0] : s;
+    owner->gates.assign(gates, gates + n_gates);
+    owner->mats.assign(mats ? mats : nullptr, mats ? mats + 32 * n_mats : nullptr);
     s->have_circuit = false;
     int rc = build_plan(s);
     if (rc) return rc;
@@ -512,9 +671,11 @@ int dmb_set_circuit(dmb_handle s, const dmb_gate* gates, size_t n_gates, const d
 int dmb_clear_circuit(dmb_handle s)
 {
     if (!s) return fail(DMB_EINVAL, "null handle");
-    s->gates.clear();
-    s->mats.clear();
+    dmb_sim* owner = is_group(s) ? s->shards[0] : s;
+    owner->gates.clear();
+    owner->mats.clear();
     s->have_circuit = false;
+    for (dmb_sim* c : s->shards) drop_graph(c);
     drop_graph(s);
     return DMB_OK;
 }
@@ -563,7 +724,72 @@ static int fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, dou
     return DMB_OK;
 }
 
-// enqueue every step of the plan on s->stream; cur is updated as buffers flip
+static int comm_events(dmb_sim* s, size_t comm_idx)
+{
+    while (s->ev_comm.size() < 2 * (comm_idx + 1))
+    {
+        cudaEvent_t a_;
+        CU(cudaEventCreate(&a_));
+        s->ev_comm.push_back(a_);
+    }
+    return DMB_OK;
+}
+
+static int nccl_barrier(dmb_sim* s)
+{
+    const int nr = g_nccl.AllReduce(s->d_barrier, s->d_barrier + 1, 1, kNcclDouble, 0 /* ncclSum */, s->comm, s->stream);
+    if (nr != 0) return fail(DMB_ECOMM, std::string("NCCL barrier failed: ") + g_nccl.GetErrorString(nr));
+    return DMB_OK;
+}
+
+// the permuting sweep of a remap whose stores go straight into the destination ranks' shards (peer memory)
+static int launch_fused_remap(dmb_sim* s, size_t i, int cur)
+{
+    SweepArgs a;
+    int rc = fill_sweep_args(s, i, s->buf[cur], s->buf[cur ^ 1], a);
+    if (rc) return rc;
+    a.tma_store = 0;
+    a.peer_shift = s->M - s->g;
+    a.peer_rank = s->rank;
+    for (int r = 0; r < s->world; r++) a.peer_out[r] = (unsigned long long)s->peer[cur ^ 1][r];
+    const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)sweep_max_grid(a));
+    CU(launch_sweep(a, grid, s->stream));
+    CU(cudaGetLastError());
+    return DMB_OK;
+}
+
+static bool is_fused_remap(const dmb_sim* s, size_t i)
+{
+    const Step& st = s->plan.steps[i];
+    return st.kind == 0 && st.sweep.out_of_place && s->p2p && i + 1 < s->plan.steps.size() && s->plan.steps[i + 1].kind == 1;
+}
+
+// one local sweep of shard s (step i) on its stream
+static int enqueue_sweep(dmb_sim* s, size_t i, int& cur, uint64_t& launches, unsigned long long& support)
+{
+    const Sweep& sw = s->plan.steps[i].sweep;
+    double2* in = s->buf[cur];
+    double2* out = in;
+    if (sw.out_of_place)
+    {
+        int rc = ensure_second_buffer(s);
+        if (rc) return rc;
+        out = s->buf[cur ^ 1];
+    }
+    SweepArgs a;
+    if (sw.out_of_place) support = ~0ull; // (only multi-GPU remaps permute; kept general)
+    int rca = fill_sweep_args(s, i, in, out, a, support);
+    if (rca) return rca;
+    for (int j = 0; j < sw.k; j++) support |= 1ull << sw.in_pos[j];
+    const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)sweep_max_grid(a));
+    CU(launch_sweep(a, grid, s->stream));
+    CU(cudaGetLastError());
+    launches++;
+    if (sw.out_of_place) cur ^= 1;
+    return DMB_OK;
+}
+
+// enqueue every step of the plan on s->stream (one shard per process); cur is updated as buffers flip
 static int enqueue_steps(dmb_sim* s, int& cur, uint64_t& launches, bool allow_exchange, unsigned long long& support)
 {
     size_t comm_idx = 0;
@@ -572,59 +798,28 @@ static int enqueue_steps(dmb_sim* s, int& cur, uint64_t& launches, bool allow_ex
     {
         const Step& st = s->plan.steps[i];
         // qubit remap with peer memory: the permuting sweep stores straight into the destination ranks' shards (one
-        // kernel = pack + all-to-all over NVLink), followed by a one-element all-reduce as the cross-GPU barrier
-        const bool fused = st.kind == 0 && st.sweep.out_of_place && s->p2p && allow_exchange && i + 1 < s->plan.steps.size() &&
-                           s->plan.steps[i + 1].kind == 1;
-        if (fused)
+        // kernel = pack + all-to-all over NVLink) between two one-element all-reduces: the first makes sure every peer
+        // is done with the buffer that is about to be overwritten (its earlier sweeps, readouts or resets may still be
+        // running), the second that every peer's stores have landed
+        if (allow_exchange && is_fused_remap(s, i))
         {
-            if (s->ev_comm.size() < 2 * (comm_idx + 1))
-            {
-                cudaEvent_t a_, b_;
-                CU(cudaEventCreate(&a_));
-                CU(cudaEventCreate(&b_));
-                s->ev_comm.push_back(a_);
-                s->ev_comm.push_back(b_);
-            }
+            int rc = comm_events(s, comm_idx);
+            if (rc) return rc;
             CU(cudaEventRecord(s->ev_comm[2 * comm_idx], s->stream));
-            SweepArgs a;
-            int rca = fill_sweep_args(s, i, s->buf[cur], s->buf[cur ^ 1], a);
-            if (rca) return rca;
-            a.peer_shift = s->M - s->g;
-            a.peer_rank = s->rank;
-            for (int r = 0; r < s->world; r++) a.peer_out[r] = (unsigned long long)s->peer[cur ^ 1][r];
-            const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)sweep_max_grid(a));
-            CU(launch_sweep(a, grid, s->stream));
-            CU(cudaGetLastError());
-            const int nr = g_nccl.AllReduce(s->d_barrier, s->d_barrier + 1, 1, kNcclDouble, 0 /* ncclSum */, s->comm, s->stream);
-            if (nr != 0) return fail(DMB_ECOMM, std::string("NCCL barrier failed: ") + g_nccl.GetErrorString(nr));
+            if ((rc = nccl_barrier(s))) return rc;
+            if ((rc = launch_fused_remap(s, i, cur))) return rc;
+            if ((rc = nccl_barrier(s))) return rc;
             CU(cudaEventRecord(s->ev_comm[2 * comm_idx + 1], s->stream));
             comm_idx++;
-            launches += 2;
+            launches += 3;
             cur ^= 1;
             i++; // the exchange step is done
             continue;
         }
         if (st.kind == 0)
         {
-            const Sweep& sw = st.sweep;
-            double2* in = s->buf[cur];
-            double2* out = in;
-            if (sw.out_of_place)
-            {
-                int rc = ensure_second_buffer(s);
-                if (rc) return rc;
-                out = s->buf[cur ^ 1];
-            }
-            SweepArgs a;
-            if (sw.out_of_place) support = ~0ull; // (only multi-GPU remaps permute; kept general)
-            int rca = fill_sweep_args(s, i, in, out, a, support);
-            if (rca) return rca;
-            for (int j = 0; j < sw.k; j++) support |= 1ull << sw.in_pos[j];
-            const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)sweep_max_grid(a));
-            CU(launch_sweep(a, grid, s->stream));
-            CU(cudaGetLastError());
-            launches++;
-            if (sw.out_of_place) cur ^= 1;
+            int rc = enqueue_sweep(s, i, cur, launches, support);
+            if (rc) return rc;
         }
         else
         {
@@ -635,14 +830,7 @@ static int enqueue_steps(dmb_sim* s, int& cur, uint64_t& launches, bool allow_ex
             const size_t chunk = s->shard_elems / P; // complex elements per peer
             const double2* src = s->buf[cur];
             double2* dst = s->buf[cur ^ 1];
-            if (s->ev_comm.size() < 2 * (comm_idx + 1))
-            {
-                cudaEvent_t a_, b_;
-                CU(cudaEventCreate(&a_));
-                CU(cudaEventCreate(&b_));
-                s->ev_comm.push_back(a_);
-                s->ev_comm.push_back(b_);
-            }
+            if ((rc = comm_events(s, comm_idx))) return rc;
             CU(cudaEventRecord(s->ev_comm[2 * comm_idx], s->stream));
             CU(cudaMemcpyAsync(dst + (size_t)s->rank * chunk, src + (size_t)s->rank * chunk, chunk * sizeof(double2),
                                cudaMemcpyDeviceToDevice, s->stream));
@@ -665,10 +853,145 @@ static int enqueue_steps(dmb_sim* s, int& cur, uint64_t& launches, bool allow_ex
     return DMB_OK;
 }
 
+// every shard's stream waits until all the OTHER shards have reached the event `which` (0 = ev_pre, 1 = ev_post)
+static int group_barrier(dmb_sim* grp, int which)
+{
+    for (dmb_sim* c : grp->shards)
+    {
+        CU(cudaSetDevice(c->device));
+        CU(cudaEventRecord(which ? c->ev_post : c->ev_pre, c->stream));
+    }
+    for (dmb_sim* c : grp->shards)
+    {
+        CU(cudaSetDevice(c->device));
+        for (dmb_sim* o : grp->shards)
+            if (o != c) CU(cudaStreamWaitEvent(c->stream, which ? o->ev_post : o->ev_pre, 0));
+    }
+    return DMB_OK;
+}
+
+// single-process group: the host walks the plan step by step and feeds every shard's stream (the launches are
+// asynchronous, so the devices run concurrently like the reference's one-OpenMP-thread-per-GPU loop, :397-451)
+static int group_run(dmb_sim* grp, dmb_stats* stats)
+{
+    dmb_sim* lead = grp->shards[0];
+    const size_t nsteps = lead->plan.steps.size();
+    for (dmb_sim* c : grp->shards)
+    {
+        CU(cudaSetDevice(c->device));
+        sweep_setup();
+        CU(cudaEventRecord(c->ev_begin, c->stream));
+    }
+    uint64_t launches = 0;
+    size_t comm_idx = 0;
+    for (size_t i = 0; i < nsteps; i++)
+    {
+        const Step& st = lead->plan.steps[i];
+        const bool fused = is_fused_remap(lead, i);
+        if (fused || st.kind == 1)
+        {
+            int rc = comm_events(lead, comm_idx);
+            if (rc) return rc;
+            CU(cudaSetDevice(lead->device));
+            CU(cudaEventRecord(lead->ev_comm[2 * comm_idx], lead->stream));
+            if ((rc = group_barrier(grp, 0))) return rc; // every shard is done with the buffer the peers will write
+            for (dmb_sim* c : grp->shards)
+            {
+                CU(cudaSetDevice(c->device));
+                if (fused)
+                {
+                    if ((rc = launch_fused_remap(c, i, c->cur))) return rc;
+                    launches++;
+                }
+                else
+                {
+                    // plain exchange (no permuting sweep in front): chunk p of rank r becomes chunk r of rank p
+                    const size_t chunk = c->shard_elems / c->world;
+                    for (int p = 0; p < c->world; p++)
+                        CU(cudaMemcpyPeerAsync(c->peer[c->cur ^ 1][p] + (size_t)c->rank * chunk, grp->shards[p]->device,
+                                               c->buf[c->cur] + (size_t)p * chunk, c->device, chunk * sizeof(double2), c->stream));
+                    launches += c->world;
+                }
+                c->cur ^= 1;
+            }
+            if ((rc = group_barrier(grp, 1))) return rc; // every peer's stores have landed
+            CU(cudaSetDevice(lead->device));
+            CU(cudaEventRecord(lead->ev_comm[2 * comm_idx + 1], lead->stream));
+            comm_idx++;
+            if (fused) i++;
+            continue;
+        }
+        for (dmb_sim* c : grp->shards)
+        {
+            CU(cudaSetDevice(c->device));
+            unsigned long long support = ~0ull;
+            int rc = enqueue_sweep(c, i, c->cur, launches, support);
+            if (rc) return rc;
+        }
+    }
+    for (dmb_sim* c : grp->shards)
+    {
+        CU(cudaSetDevice(c->device));
+        CU(cudaEventRecord(c->ev_end, c->stream));
+    }
+    double sim_ms = 0;
+    for (dmb_sim* c : grp->shards)
+    {
+        CU(cudaSetDevice(c->device));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        c->layout = lead->plan.end_layout;
+        c->conj_flag = lead->plan.conj_end;
+        if (lead->plan.has_srn) c->non_hermitian = true;
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end));
+        sim_ms = std::max(sim_ms, (double)ms);
+    }
+    if (stats)
+    {
+        memset(stats, 0, sizeof(*stats));
+        stats->sim_ms = sim_ms;
+        double comm = 0;
+        CU(cudaSetDevice(lead->device));
+        for (size_t i = 0; i < comm_idx; i++)
+        {
+            float c = 0;
+            CU(cudaEventElapsedTime(&c, lead->ev_comm[2 * i], lead->ev_comm[2 * i + 1]));
+            comm += c;
+        }
+        stats->comm_ms = comm;
+        stats->comp_ms = sim_ms - comm;
+        stats->n_gates = lead->plan.n_gates;
+        stats->n_primitives = lead->plan.n_primitives;
+        stats->n_blocks = lead->plan.n_blocks;
+        stats->n_sweeps = lead->plan.n_sweeps;
+        stats->n_exchanges = lead->plan.n_exchanges;
+        stats->n_launches = launches;
+        stats->sweep_bytes = 32ull * lead->shard_elems;
+        stats->exchange_bytes = lead->plan.n_exchanges * (uint64_t)(lead->world - 1) * (lead->shard_elems / lead->world) * 16ull;
+        stats->h2d_bytes = lead->h2d_bytes * grp->shards.size();
+    }
+    return DMB_OK;
+}
+
 int dmb_run(dmb_handle s, dmb_stats* stats)
 {
     if (!s) return fail(DMB_EINVAL, "null handle");
     if (!s->have_circuit) return fail(DMB_ESTATE, "dmb_run before dmb_set_circuit");
+    if (is_group(s))
+    {
+        dmb_sim* lead = s->shards[0];
+        if (lead->plan_layout != lead->layout || lead->plan_conj != lead->conj_flag || lead->plan_nonherm != lead->non_hermitian)
+        {
+            int rc = build_plan(s);
+            if (rc) return rc;
+        }
+        int prev = 0;
+        cudaGetDevice(&prev);
+        int rc = group_run(s, stats);
+        cudaSetDevice(prev);
+        return rc;
+    }
     CU(cudaSetDevice(s->device));
     if (s->plan_layout != s->layout || s->plan_conj != s->conj_flag || s->plan_nonherm != s->non_hermitian)
     {
@@ -717,6 +1040,7 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
     }
     else
     {
+        sweep_setup();
         CU(cudaEventRecord(s->ev_begin, s->stream));
         int rc = enqueue_steps(s, cur, launches, true, s->support);
         if (rc) return rc;
@@ -757,26 +1081,70 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
 }
 
 // ---- results ----------------------------------------------------------------------------------
+// A sharded state answers GLOBALLY: a group handle gathers over its shards; a rank of a one-process-per-GPU job with
+// a communicator attached all-reduces (every rank must make the call, every rank gets the full answer -- the
+// reference's distributed measure() does the same with MPI_Gather / MPI_Bcast, src/dmsim_nvgpu_mpi.cuh:472-520).
 int dmb_get_dm(dmb_handle s, double* real, double* imag)
 {
     if (!s || !real || !imag) return fail(DMB_EINVAL, "null argument");
-    if (s->world != 1) return fail(DMB_ESTATE, "dmb_get_dm needs world_size == 1 (use dmb_get_shard)");
-    CU(cudaSetDevice(s->device));
+    if (s->world != 1 && !is_group(s) && !collective(s))
+        return fail(DMB_ESTATE, "dmb_get_dm on one rank of a sharded state needs a communicator (dmb_comm_init)");
     const unsigned long long total = 1ull << s->N;
     const unsigned long long chunk = std::min<unsigned long long>(total, 1ull << 24);
-    int rc = ensure_scratch(s, chunk * 2 * sizeof(double));
+    dmb_sim* lead = is_group(s) ? s->shards[0] : s;
+    CU(cudaSetDevice(lead->device));
+    int rc = ensure_scratch(lead, chunk * 2 * sizeof(double));
     if (rc) return rc;
-    const LayoutArgs L = layout_args(s);
-    double* d_re = s->d_scratch;
-    double* d_im = s->d_scratch + chunk;
+    double* d_re = lead->d_scratch;
+    double* d_im = lead->d_scratch + chunk;
     for (unsigned long long first = 0; first < total; first += chunk)
     {
-        launch_gather_split(s->buf[s->cur], L, first, chunk, d_re, d_im, s->stream);
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(real + first, d_re, chunk * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaMemcpyAsync(imag + first, d_im, chunk * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
+        if (is_group(s))
+        {
+            // every shard writes the elements it owns straight into the lead device's staging buffers (peer memory)
+            for (dmb_sim* c : s->shards)
+            {
+                CU(cudaSetDevice(c->device));
+                launch_gather_split(c->buf[c->cur], layout_args(c), first, chunk, d_re, d_im, 1 /* owned only */, c->stream);
+                CU(cudaGetLastError());
+            }
+            for (dmb_sim* c : s->shards)
+            {
+                CU(cudaSetDevice(c->device));
+                CU(cudaStreamSynchronize(c->stream));
+            }
+            CU(cudaSetDevice(lead->device));
+        }
+        else
+        {
+            launch_gather_split(s->buf[s->cur], layout_args(s), first, chunk, d_re, d_im, s->world > 1 ? 2 /* zero the rest */ : 0,
+                                s->stream);
+            CU(cudaGetLastError());
+            if (collective(s) && (rc = all_reduce_sum(s, d_re, 2 * chunk))) return rc;
+        }
+        CU(cudaMemcpyAsync(real + first, d_re, chunk * sizeof(double), cudaMemcpyDeviceToHost, lead->stream));
+        CU(cudaMemcpyAsync(imag + first, d_im, chunk * sizeof(double), cudaMemcpyDeviceToHost, lead->stream));
+        CU(cudaStreamSynchronize(lead->stream));
     }
+    return DMB_OK;
+}
+
+// one shard's part of n arbitrary elements (zero where another rank owns the element) into host arrays
+static int shard_elements(dmb_sim* s, const uint64_t* flat_index, size_t n, double* real, double* imag, bool reduce)
+{
+    CU(cudaSetDevice(s->device));
+    int rc = ensure_scratch(s, n * (sizeof(unsigned long long) + 2 * sizeof(double)));
+    if (rc) return rc;
+    double* d_re = s->d_scratch;
+    double* d_im = d_re + n;
+    unsigned long long* d_idx = reinterpret_cast<unsigned long long*>(d_im + n);
+    CU(cudaMemcpyAsync(d_idx, flat_index, n * sizeof(unsigned long long), cudaMemcpyHostToDevice, s->stream));
+    launch_gather_elements(s->buf[s->cur], layout_args(s), d_idx, n, d_re, d_im, s->stream);
+    CU(cudaGetLastError());
+    if (reduce && (rc = all_reduce_sum(s, d_re, 2 * n))) return rc;
+    CU(cudaMemcpyAsync(real, d_re, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(imag, d_im, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
     return DMB_OK;
 }
 
@@ -787,30 +1155,64 @@ int dmb_get_elements(dmb_handle s, const uint64_t* flat_index, size_t n, double*
     const uint64_t total = 1ull << s->N;
     for (size_t i = 0; i < n; i++)
         if (flat_index[i] >= total) return fail(DMB_EINVAL, "element index out of range");
+    if (!is_group(s)) return shard_elements(s, flat_index, n, real, imag, collective(s));
+    std::vector<double> re(n), im(n);
+    std::fill(real, real + n, 0.0);
+    std::fill(imag, imag + n, 0.0);
+    for (dmb_sim* c : s->shards)
+    {
+        int rc = shard_elements(c, flat_index, n, re.data(), im.data(), false);
+        if (rc) return rc;
+        for (size_t i = 0; i < n; i++) { real[i] += re[i]; imag[i] += im[i]; }
+    }
+    return DMB_OK;
+}
+
+// diagonal of one shard (zero where another rank owns the entry): real parts or their absolute values, left on the
+// device in s->d_scratch[0 .. dim) (all-reduced when `reduce`)
+static int shard_diag_device(dmb_sim* s, bool abs_values, bool reduce, size_t extra_bytes = 0)
+{
     CU(cudaSetDevice(s->device));
-    int rc = ensure_scratch(s, n * (sizeof(unsigned long long) + 2 * sizeof(double)));
+    const size_t dim = (size_t)1 << s->n;
+    int rc = ensure_scratch(s, dim * sizeof(double) + extra_bytes);
     if (rc) return rc;
-    double* d_re = s->d_scratch;
-    double* d_im = d_re + n;
-    unsigned long long* d_idx = reinterpret_cast<unsigned long long*>(d_im + n);
-    CU(cudaMemcpyAsync(d_idx, flat_index, n * sizeof(unsigned long long), cudaMemcpyHostToDevice, s->stream));
-    launch_gather_elements(s->buf[s->cur], layout_args(s), d_idx, n, d_re, d_im, s->stream);
+    launch_diag(s->buf[s->cur], layout_args(s), abs_values ? nullptr : s->d_scratch, abs_values ? s->d_scratch : nullptr, s->stream);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(real, d_re, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(imag, d_im, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    if (reduce && (rc = all_reduce_sum(s, s->d_scratch, dim))) return rc;
+    return DMB_OK;
+}
+
+// the full diagonal (or |diagonal|) of a group on the host
+static int group_diag_host(dmb_sim* grp, bool abs_values, std::vector<double>& acc)
+{
+    const size_t dim = (size_t)1 << grp->n;
+    acc.assign(dim, 0.0);
+    std::vector<double> part(dim);
+    for (dmb_sim* c : grp->shards)
+    {
+        int rc = shard_diag_device(c, abs_values, false);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(part.data(), c->d_scratch, dim * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < dim; i++) acc[i] += part[i];
+    }
     return DMB_OK;
 }
 
 int dmb_get_diag(dmb_handle s, double* diag)
 {
     if (!s || !diag) return fail(DMB_EINVAL, "null argument");
-    CU(cudaSetDevice(s->device));
     const size_t dim = (size_t)1 << s->n;
-    int rc = ensure_scratch(s, dim * sizeof(double));
+    if (is_group(s))
+    {
+        std::vector<double> acc;
+        int rc = group_diag_host(s, false, acc);
+        if (rc) return rc;
+        memcpy(diag, acc.data(), dim * sizeof(double));
+        return DMB_OK;
+    }
+    int rc = shard_diag_device(s, false, collective(s));
     if (rc) return rc;
-    launch_diag(s->buf[s->cur], layout_args(s), s->d_scratch, nullptr, s->stream);
-    CU(cudaGetLastError());
     CU(cudaMemcpyAsync(diag, s->d_scratch, dim * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return DMB_OK;
@@ -819,6 +1221,19 @@ int dmb_get_diag(dmb_handle s, double* diag)
 static int reduce_scalar(dmb_sim* s, bool purity, double* out)
 {
     if (!s || !out) return fail(DMB_EINVAL, "null argument");
+    if (is_group(s))
+    {
+        double acc = 0.0;
+        for (dmb_sim* c : s->shards)
+        {
+            double v = 0.0;
+            int rc = reduce_scalar(c, purity, &v);
+            if (rc) return rc;
+            acc += v;
+        }
+        *out = acc;
+        return DMB_OK;
+    }
     CU(cudaSetDevice(s->device));
     int rc = ensure_scratch(s, sizeof(double));
     if (rc) return rc;
@@ -826,6 +1241,7 @@ static int reduce_scalar(dmb_sim* s, bool purity, double* out)
     if (purity) launch_purity(s->buf[s->cur], s->shard_elems, s->d_scratch, s->stream);
     else launch_trace(s->buf[s->cur], layout_args(s), s->d_scratch, s->stream);
     CU(cudaGetLastError());
+    if (collective(s) && (rc = all_reduce_sum(s, s->d_scratch, 1))) return rc;
     CU(cudaMemcpyAsync(out, s->d_scratch, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return DMB_OK;
@@ -836,28 +1252,38 @@ int dmb_purity(dmb_handle s, double* purity) { return reduce_scalar(s, true, pur
 int dmb_sample(dmb_handle s, const double* r, size_t n, uint64_t* out, double* total)
 {
     if (!s || (n && (!r || !out))) return fail(DMB_EINVAL, "null argument");
-    if (s->world != 1) return fail(DMB_ESTATE, "dmb_sample needs world_size == 1");
-    CU(cudaSetDevice(s->device));
+    if (s->world != 1 && !is_group(s) && !collective(s))
+        return fail(DMB_ESTATE, "dmb_sample on one rank of a sharded state needs a communicator (dmb_comm_init)");
     const size_t dim = (size_t)1 << s->n;
-    // scratch: p[dim] | scan[dim+1] | r[n] | out[n]
+    // scratch of the sampling device: p[dim] | scan[dim+1] | r[n] | out[n]
     const size_t bytes = (2 * dim + 1 + n) * sizeof(double) + n * sizeof(unsigned long long);
-    int rc = ensure_scratch(s, bytes);
-    if (rc) return rc;
-    double* d_p = s->d_scratch;
+    dmb_sim* lead = is_group(s) ? s->shards[0] : s;
+    int rc;
+    if (is_group(s))
+    {
+        std::vector<double> p;
+        if ((rc = group_diag_host(s, true, p))) return rc; // |Re rho_ii| of every shard, summed (one owner per entry)
+        CU(cudaSetDevice(lead->device));
+        if ((rc = ensure_scratch(lead, bytes))) return rc;
+        CU(cudaMemcpyAsync(lead->d_scratch, p.data(), dim * sizeof(double), cudaMemcpyHostToDevice, lead->stream));
+        CU(cudaStreamSynchronize(lead->stream)); // p is a local vector
+    }
+    else if ((rc = shard_diag_device(s, true, collective(s), bytes - dim * sizeof(double))))
+        return rc;
+    double* d_p = lead->d_scratch;
     double* d_scan = d_p + dim;
     double* d_r = d_scan + dim + 1;
     unsigned long long* d_out = reinterpret_cast<unsigned long long*>(d_r + n);
-    launch_diag(s->buf[s->cur], layout_args(s), nullptr, d_p, s->stream);
-    launch_scan(d_p, d_scan, dim, s->stream);
+    launch_scan(d_p, d_scan, dim, lead->stream);
     if (n)
     {
-        CU(cudaMemcpyAsync(d_r, r, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-        launch_sample(d_scan, dim, d_r, n, d_out, s->stream);
+        CU(cudaMemcpyAsync(d_r, r, n * sizeof(double), cudaMemcpyHostToDevice, lead->stream));
+        launch_sample(d_scan, dim, d_r, n, d_out, lead->stream);
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(out, d_out, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(out, d_out, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, lead->stream));
     }
-    if (total) CU(cudaMemcpyAsync(total, d_scan + dim, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    if (total) CU(cudaMemcpyAsync(total, d_scan + dim, sizeof(double), cudaMemcpyDeviceToHost, lead->stream));
+    CU(cudaStreamSynchronize(lead->stream));
     CU(cudaGetLastError());
     return DMB_OK;
 }
@@ -874,6 +1300,16 @@ int dmb_measure(dmb_handle s, unsigned seed, size_t repetition, uint64_t* out, d
 int dmb_get_shard(dmb_handle s, double* interleaved, int32_t* phys_of_logical)
 {
     if (!s) return fail(DMB_EINVAL, "null handle");
+    if (is_group(s))
+    {
+        // group: the shards back to back in rank order (2 * 4^n doubles), i.e. the whole state in PHYSICAL order
+        for (dmb_sim* c : s->shards)
+        {
+            int rc = dmb_get_shard(c, interleaved ? interleaved + 2 * c->shard_elems * (size_t)c->rank : nullptr, phys_of_logical);
+            if (rc) return rc;
+        }
+        return DMB_OK;
+    }
     CU(cudaSetDevice(s->device));
     if (interleaved)
     {

@@ -60,6 +60,10 @@ enum RegOpCode : int32_t
                       // by m[0]; `pos` as for the other two-bit ops
     RC_QFT2 = 14,     // butterfly on the LOWER register bit of the pair, controlled phase m[0] between the two, butterfly on
                       // the HIGHER bit: the radix-4 step of a QFT round as ONE dispatch (`pos` as for the two-bit ops)
+    RC_DENSE2_LU = 15, // dense 4x4 as M = L U (unit lower, upper; no pivoting -- the encoder only emits it when the factors
+                       // stay small): U is applied top-down and L bottom-up IN PLACE, the same 16 complex multiply-adds as
+                       // the direct form but no copies of the inputs (the direct form spent 11 % of its instructions on register
+                       // moves).  m[0..9] = U row by row (u00 u01 u02 u03 u11 u12 u13 u22 u23 u33), m[10..15] = l10 l20 l21 l30 l31 l32
     RC_STAR = 10      // controlled-phase star: for every register bit p in aux bits 0..3, the elements with that bit set
                       // are multiplied by  L_p[lane] * WO_p[warp, iteration]  (DevStar slot star[p]): the product of the
                       // phases of all controlled-phase ops between register bit p and the partner bits that are set in
@@ -95,7 +99,8 @@ struct alignas(16) DevOpHdr
 // The kernel's jump-table index of an op: dense over (code, position) -- and over the register-bit MASK for RC_HAD and
 // RC_STAR, so that those two need no header read at all.
 constexpr int kVidDense2 = 0, kVidPerm2 = 6, kVidCp2 = 12, kVidDense1 = 18, kVidRR = 22, kVidRI = 26, kVidMono1 = 30,
-              kVidSrn1 = 34, kVidDiagP = 38, kVidDiagR = 42, kVidQft2 = 43, kVidHad = 49, kVidStar = 64, kNumVids = 79;
+              kVidSrn1 = 34, kVidDiagP = 38, kVidDiagR = 42, kVidQft2 = 43, kVidLu2 = 49, kVidHad = 55, kVidStar = 70,
+              kNumVids = 85;
 constexpr int dev_vid(int code, int pos, int aux)
 {
     switch (code)
@@ -111,6 +116,7 @@ constexpr int dev_vid(int code, int pos, int aux)
     case RC_DIAGP: return kVidDiagP + pos;
     case RC_DIAGR: return kVidDiagR;
     case RC_QFT2: return kVidQft2 + pos;
+    case RC_DENSE2_LU: return kVidLu2 + pos;
     case RC_HAD: return kVidHad + (aux & 15) - 1;
     case RC_STAR: return kVidStar + (aux & 15) - 1;
     default: return kNumVids;
@@ -123,6 +129,7 @@ constexpr int dev_op_payload_bytes(int code)
     case RC_DENSE1: return 64;
     case RC_MONO1: return 32;
     case RC_DENSE2: return 256;
+    case RC_DENSE2_LU: return 256;
     case RC_PERM2: return 64;
     case RC_DIAGR: return 256;
     case RC_DIAGP: return 128;

@@ -11,6 +11,9 @@
 namespace dmb
 {
 static int g_tma_box_bits = 10;
+static bool g_dense2_lu = true;
+void set_sweep_dense2_lu(bool on) { g_dense2_lu = on; }
+bool sweep_dense2_lu() { return g_dense2_lu; }
 void set_sweep_tma_box_bits(int bits) { g_tma_box_bits = bits < 3 ? 3 : (bits > kMaxTileBits ? kMaxTileBits : bits); }
 int sweep_tma_box_bits() { return g_tma_box_bits; }
 namespace
@@ -135,6 +138,36 @@ DevOp make_reg_op(const TileOp& t, int p0, int p1)
                 d.aux = w | ((unit ? 1 : 0) << 12);
                 return d;
             }
+    }
+    // M = L U without pivoting: applied in place (no copies of the inputs) when the factors stay small
+    if (sweep_dense2_lu())
+    {
+        cplx a[16], l[16];
+        memcpy(a, m, sizeof(a));
+        for (auto& x : l) x = 0;
+        double big = 0;
+        bool ok = true;
+        for (int k = 0; k < 4 && ok; k++)
+        {
+            if (std::abs(a[k * 5]) < 1e-3) { ok = false; break; }
+            for (int i = k + 1; i < 4; i++)
+            {
+                l[i * 4 + k] = a[i * 4 + k] / a[k * 5];
+                for (int c = k; c < 4; c++) a[i * 4 + c] -= l[i * 4 + k] * a[k * 4 + c];
+                a[i * 4 + k] = 0;
+            }
+        }
+        for (int i = 0; ok && i < 16; i++) big = std::max(big, std::max(std::abs(a[i]), std::abs(l[i])));
+        if (ok && big <= 64.0)
+        {
+            d.code = RC_DENSE2_LU;
+            int at = 0;
+            for (int i = 0; i < 4; i++)
+                for (int j = i; j < 4; j++) put(d, at++, a[i * 4 + j]);
+            for (int i = 1; i < 4; i++)
+                for (int j = 0; j < i; j++) put(d, at++, l[i * 4 + j]);
+            return d;
+        }
     }
     d.code = RC_DENSE2;
     for (int i = 0; i < 16; i++) put(d, i, m[i]);
@@ -283,7 +316,7 @@ void fold_hadamard_scales(std::vector<DevOp>& ops)
     for (int i = (int)ops.size() - 1; i >= 0 && carrier < 0; i--)
     {
         const int c = ops[i].code;
-        if ((c == RC_DENSE1 || c == RC_DENSE2 || c == RC_DENSE1_RI || c == RC_DENSE1_RR) && !is_had(ops[i])) carrier = i;
+        if ((c == RC_DENSE1 || c == RC_DENSE2 || c == RC_DENSE2_LU || c == RC_DENSE1_RI || c == RC_DENSE1_RR) && !is_had(ops[i])) carrier = i;
     }
     if (carrier < 0)
         for (int i = (int)ops.size() - 1; i >= 0 && carrier < 0; i--)
@@ -305,6 +338,7 @@ void fold_hadamard_scales(std::vector<DevOp>& ops)
     {
     case RC_DENSE1: for (int i = 0; i < 8; i++) d.m[i] *= f; break;
     case RC_DENSE2: for (int i = 0; i < 32; i++) d.m[i] *= f; break;
+    case RC_DENSE2_LU: for (int i = 0; i < 20; i++) d.m[i] *= f; break; // (f L U = L (f U))
     default: d.m[0] *= f; d.m[1] *= f; d.m[3] *= f; break; // pivoted forms: d2/d0 is scale free
     }
 }
@@ -315,7 +349,7 @@ unsigned reg_support(const DevOp& d)
     static const int hi[6] = {1, 2, 2, 3, 3, 3}, lo[6] = {0, 0, 1, 0, 1, 2};
     switch (d.code)
     {
-    case RC_DENSE2: case RC_PERM2: case RC_CP2: case RC_QFT2: return (1u << hi[d.pos]) | (1u << lo[d.pos]);
+    case RC_DENSE2: case RC_DENSE2_LU: case RC_PERM2: case RC_CP2: case RC_QFT2: return (1u << hi[d.pos]) | (1u << lo[d.pos]);
     case RC_HAD: case RC_STAR: return (unsigned)d.aux & 15u;
     case RC_DIAGR: case RC_DIAGP: return 15u;
     default: return 1u << d.pos;
@@ -403,10 +437,14 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
         // ---- group: consecutive rounds that leave kWarpBits tile bits untouched ----
         unsigned used = 0;
         size_t end = first;
+        // (kSwzTma: only tile bits 0..5 move the bank group, and lane bits 0..2 need three of them with different
+        // residues mod 3 -- a group ends early rather than let its warp bits eat into them)
+        const unsigned high_mask = k > 6 ? ((1u << k) - 1u) & ~63u : 0u;
         while (end < nr)
         {
             const unsigned u = used | plan[end].touched;
             if (k - __builtin_popcount(u) < nwb) break;
+            if (mode == kSwzTma && end > first && __builtin_popcount(~u & high_mask) < nwb) break;
             used = u;
             end++;
         }
@@ -428,9 +466,12 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
             std::vector<int> rb;
             for (int p = 0; p < k; p++)
                 if ((rp.touched >> p) & 1u) rb.push_back(p);
-            // pad the register bits with free tile bits (lowest first)
-            for (int p = 0; p < k && (int)rb.size() < R; p++)
+            // pad the register bits with free tile bits (lowest first; kSwzTma: highest first, the low ones are lane bits)
+            for (int q = 0; q < k && (int)rb.size() < R; q++)
+            {
+                const int p = mode == kSwzTma ? k - 1 - q : q;
                 if (!((wmask >> p) & 1u) && std::find(rb.begin(), rb.end(), p) == rb.end()) rb.push_back(p);
+            }
             std::sort(rb.begin(), rb.end());
             unsigned rmask = 0;
             for (int p : rb) rmask |= 1u << p;

@@ -23,6 +23,9 @@ void fill_sweep_tables(const Sweep& sw, int M, SweepArgs& a);
 // largest TMA box in tile bits (2^bits elements of 16 bytes; default 10 = 16 KiB)
 void set_sweep_tma_box_bits(int bits);
 int sweep_tma_box_bits();
+// dense 4x4 ops as in-place L U (RC_DENSE2_LU) where the factors stay small (default on)
+void set_sweep_dense2_lu(bool on);
+bool sweep_dense2_lu();
 // JSON text of the device tables of one sweep (for the CPU test-suite's kernel-indexing emulator)
 std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a);
 } // namespace dmb

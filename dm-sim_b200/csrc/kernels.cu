@@ -169,25 +169,29 @@ void launch_sample(const double* scan, size_t dim, const double* r, size_t n, un
     sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(scan, dim, r, n, out);
 }
 
+// owner: 0 = the shard is the whole state; 1 = write only the elements this rank owns (several ranks fill ONE staging
+// buffer, possibly in a peer's memory); 2 = write zeros for the elements another rank owns (the ranks' buffers are summed)
 __global__ void gather_split_kernel(const double2* __restrict__ buf, const __grid_constant__ LayoutArgs L,
                                     unsigned long long first, unsigned long long count, double* __restrict__ re,
-                                    double* __restrict__ im)
+                                    double* __restrict__ im, int owner)
 {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     const unsigned long long mask = (L.M >= 64) ? ~0ull : ((1ull << L.M) - 1ull);
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
     {
         const unsigned long long p = to_phys(first + i, L);
-        const double2 v = buf[p & mask];
+        const bool mine = owner == 0 || (p >> L.M) == (unsigned long long)L.rank;
+        if (!mine && owner == 1) continue;
+        const double2 v = mine ? buf[p & mask] : make_double2(0.0, 0.0);
         re[i] = v.x;
         im[i] = L.conj ? -v.y : v.y;
     }
 }
 void launch_gather_split(const double2* buf, const LayoutArgs& L, unsigned long long first, unsigned long long count,
-                         double* re, double* im, cudaStream_t s)
+                         double* re, double* im, int owner, cudaStream_t s)
 {
     const unsigned grid = (unsigned)min((unsigned long long)device_num_sms() * 16, (count + 255) / 256);
-    gather_split_kernel<<<grid, 256, 0, s>>>(buf, L, first, count, re, im);
+    gather_split_kernel<<<grid, 256, 0, s>>>(buf, L, first, count, re, im, owner);
 }
 
 // arbitrary logical flat indices (col*dim + row) -> values; elements another rank owns come back as zero
@@ -222,6 +226,7 @@ __global__ void scatter_split_kernel(double2* __restrict__ buf, const __grid_con
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
     {
         const unsigned long long p = to_phys(first + i, L);
+        if ((p >> L.M) != (unsigned long long)L.rank) continue; // another rank owns this element
         buf[p & mask] = make_double2(re[i], L.conj ? -im[i] : im[i]);
     }
 }

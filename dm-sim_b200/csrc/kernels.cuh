@@ -29,8 +29,9 @@ void launch_purity(const double2* buf, size_t n_elems, double* out, cudaStream_t
 void launch_scan(const double* p, double* scan /* dim+1 */, size_t dim, cudaStream_t s);
 void launch_sample(const double* scan, size_t dim, const double* r, size_t n, unsigned long long* out, cudaStream_t s);
 // logical [first, first+count) of the flat col*dim+row index -> split real / imag staging
+// owner: 0 whole state in this shard, 1 write owned elements only, 2 zero the elements of other ranks
 void launch_gather_split(const double2* buf, const LayoutArgs& L, unsigned long long first, unsigned long long count,
-                         double* re, double* im, cudaStream_t s);
+                         double* re, double* im, int owner, cudaStream_t s);
 void launch_gather_elements(const double2* buf, const LayoutArgs& L, const unsigned long long* idx, unsigned long long count,
                             double* re, double* im, cudaStream_t s);
 void launch_scatter_split(double2* buf, const LayoutArgs& L, unsigned long long first, unsigned long long count,

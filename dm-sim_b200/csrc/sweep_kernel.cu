@@ -108,11 +108,15 @@ __device__ __forceinline__ void tma_store_5d(const TmaDesc* map, unsigned src, i
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                  : "memory");
 }
-__device__ __forceinline__ void tma_store_commit_and_wait_read()
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
 {
-    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+// until the committed stores have been READ out of shared memory (the tile buffer may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+// until the committed stores are complete (before the CTA exits)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 // start coordinates of the box that holds element `full` (its box bits are zero): dimension d takes the index bits
 // [start[d], start[d] + span[d]); dimension 0 counts doubles (two per element)
@@ -269,6 +273,49 @@ __device__ __forceinline__ void r_dense2(double2 (&v)[E], Op op)
             v[qb | o] = cfma(m3, b3, cfma(m2, b2, cfma(m1, b1, cmul(m0, b0))));
         }
     }
+}
+// 4x4 dense as L U, in place (RC_DENSE2_LU): every matrix entry is loaded once (broadcast LDS.128) and applied to the four
+// quads of the lane -- 16 loads per 256 FP64 instructions, four independent chains per entry, no temporaries
+__device__ __forceinline__ void cfma_ip(double2& c, const double2 a, const double2 b) // c += a * b
+{
+    c.x = fma(a.x, b.x, fma(-a.y, b.y, c.x));
+    c.y = fma(a.x, b.y, fma(a.y, b.x, c.y));
+}
+template <int PH, int PL>
+__device__ __forceinline__ void r_dense2_lu(double2 (&v)[E], Op op)
+{
+    constexpr int bh = 1 << PH, bl = 1 << PL;
+    constexpr int rest = (E - 1) & ~(bh | bl); // the two register bits the op does not touch
+    constexpr int r0 = rest & -rest, r1 = rest & ~r0;
+    const double2* m = op_m(op);
+#define DMB_QUAD(qi) (((qi) & 1 ? r0 : 0) | ((qi) & 2 ? r1 : 0))
+#define DMB_ELEM(i) (((i) & 1 ? bl : 0) | ((i) & 2 ? bh : 0))
+    int at = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) // x_i = u_ii x_i + sum_{j > i} u_ij x_j   (x_j for j > i still hold the inputs)
+    {
+        const double2 d = m[at++];
+#pragma unroll
+        for (int q = 0; q < 4; q++) cmul_ip(v[DMB_QUAD(q) | DMB_ELEM(i)], d);
+#pragma unroll
+        for (int j = i + 1; j < 4; j++)
+        {
+            const double2 e = m[at++];
+#pragma unroll
+            for (int q = 0; q < 4; q++) cfma_ip(v[DMB_QUAD(q) | DMB_ELEM(i)], e, v[DMB_QUAD(q) | DMB_ELEM(j)]);
+        }
+    }
+#pragma unroll
+    for (int i = 3; i >= 1; i--) // x_i += sum_{j < i} l_ij x_j, bottom-up (x_j for j < i still hold U x)
+#pragma unroll
+        for (int j = 0; j < i; j++)
+        {
+            const double2 e = m[10 + (i * (i - 1)) / 2 + j];
+#pragma unroll
+            for (int q = 0; q < 4; q++) cfma_ip(v[DMB_QUAD(q) | DMB_ELEM(i)], e, v[DMB_QUAD(q) | DMB_ELEM(j)]);
+        }
+#undef DMB_QUAD
+#undef DMB_ELEM
 }
 // monomial ops with one of three row permutations: W = 0: CX (MSB control): rows 2<->3; 1: CX (LSB control): rows
 // 1<->3; 2: SWAP: rows 1<->2.  out[r] = ph[r] * in[src[r]].  With unit phases the op is a pure register renaming.
@@ -427,6 +474,7 @@ __device__ __forceinline__ void apply_reg_op(double2 (&v)[E], const unsigned cha
         DMB_CASE2(kVidPerm2, RC_PERM2, r_perm2, v, op)
         DMB_CASE2(kVidCp2, RC_CP2, r_cp2, v, op)
         DMB_CASE2(kVidQft2, RC_QFT2, r_qft2, v, op)
+        DMB_CASE2(kVidLu2, RC_DENSE2_LU, r_dense2_lu, v, op)
         DMB_CASE1(kVidDense1, RC_DENSE1, r_dense1, v, op)
         DMB_CASE1(kVidRR, RC_DENSE1_RR, r_dense1_rr, v, op)
         DMB_CASE1(kVidRI, RC_DENSE1_RI, r_dense1_ri, v, op)
@@ -476,29 +524,39 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
             }
     }
 
-    // per-thread part of the address maps (the low kThreadBits loop bits come from the thread index)
+    // per-thread part of the address maps (the low kThreadBits loop bits come from the thread index): recomputed per
+    // tile by the legacy load / store paths (a handful of instructions next to 32 copies) instead of living in registers
+    // across the compute phase, where the 16 resident elements need every register
     const int klo = k < kThreadBits ? k : kThreadBits;
     const int n_it = k <= kThreadBits ? 1 : (1 << (k - kThreadBits));
     const bool t_active = (unsigned)t < tile_elems;
-    unsigned long long g_in_lo = 0, g_out_lo = 0;
-    unsigned s_out_lo = 0;
-    for (int i = 0; i < klo; i++)
-    {
-        const unsigned long long bit = (t >> i) & 1;
-        g_in_lo |= bit << a.gin[i];
-        g_out_lo |= bit << a.gout[i];
-        s_out_lo |= (unsigned)bit << a.sout[i];
-    }
     const int mode = a.swz_mode;
-    s_out_lo = swz(s_out_lo, mode);
-    const unsigned s_in = swz((unsigned)t, mode);
+    auto thread_in = [&]() {
+        unsigned long long g = 0;
+        for (int i = 0; i < klo; i++) g |= (unsigned long long)((t >> i) & 1) << a.gin[i];
+        return g;
+    };
+    auto thread_out = [&](unsigned& s_lo) {
+        unsigned long long g = 0;
+        unsigned sl = 0;
+        for (int i = 0; i < klo; i++)
+        {
+            const unsigned long long bit = (t >> i) & 1;
+            g |= bit << a.gout[i];
+            sl |= (unsigned)bit << a.sout[i];
+        }
+        s_lo = swz(sl, mode);
+        return g;
+    };
     const unsigned tile_u32 = (unsigned)__cvta_generic_to_shared(tile);
     const unsigned bar_u32 = tile_u32 + 16u * tile_elems;
     unsigned tma_phase = 0;
     if (a.tma_load)
     {
         if (tile_u32 & 1023u) __trap(); // the hardware swizzle pattern is a function of the shared-memory ADDRESS
-        if (t == 0) mbar_init(bar_u32, 1);
+        // arrivals per tile: thread 0 (with the byte count of the TMA loads) + one per warp once its share of the star
+        // prologue is in shared memory
+        if (t == 0) mbar_init(bar_u32, 1 + NT / 32);
     }
     const double2* __restrict__ gin = reinterpret_cast<const double2*>(a.in);
     double2* __restrict__ gout = reinterpret_cast<double2*>(a.out);
@@ -520,6 +578,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
             // mbarrier after the star prologue below
             if (t == 0)
             {
+                if (a.tma_store) tma_store_wait_read(); // the previous tile has left the buffer (nobody else waits for it)
                 mbar_expect_tx(bar_u32, 16u * tile_elems);
                 for (int j = 0; j < a.tma.n_copies; j++)
                 {
@@ -532,7 +591,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
         // legacy: 128-bit async copies straight into the swizzled tile; runs of >= 2^low_bits * 16 B
         else if (t_active)
         {
-            const char* src = reinterpret_cast<const char*>(gin + (base_in | g_in_lo));
+            const char* src = reinterpret_cast<const char*>(gin + (base_in | thread_in()));
+            const unsigned s_in = swz((unsigned)t, mode);
             if (n_it == kMaxIter)
             {
                 // full-size tile: no per-iteration predicates.  swz(it << 7) = (it << 7) | l3(it) with a 3-bit l3, and
@@ -565,6 +625,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                 const DevStar* st = a.stars + (on ? (i >> 3) : 0);
                 // (bit[] is padded with 63 and phi[] with 1 up to kMaxStarOut: every load below is independent)
                 double2 acc = make_double2(1.0, 0.0);
+                const double2 wv = on ? __ldg(reinterpret_cast<const double2*>(st->w) + (i & 7)) : acc; // (in flight with the rest)
                 if (on)
                 {
                     int bj[(kMaxStarOut + 7) / 8];
@@ -586,12 +647,14 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                     const double ox = __shfl_xor_sync(0xffffffffu, acc.x, m), oy = __shfl_xor_sync(0xffffffffu, acc.y, m);
                     acc = cmul(acc, make_double2(ox, oy));
                 }
-                if (on) s_star[(i >> 3) * kStarEntries + (i & 7)] = cmul(acc, __ldg(reinterpret_cast<const double2*>(st->w) + (i & 7)));
+                if (on) s_star[(i >> 3) * kStarEntries + (i & 7)] = cmul(acc, wv);
             }
         }
         if (a.tma_load)
         {
-            if (DMB_HAS(RC_STAR)) __syncthreads(); // the star tables (written above) before anybody reads them
+            // the mbarrier completes when the tile has landed AND every warp has published its star tables
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_u32);
             mbar_wait(bar_u32, tma_phase);
             tma_phase ^= 1u;
         }
@@ -658,16 +721,17 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                     __syncwarp();
                 }
             }
+            // (TMA store: the generic-proxy writes of the rounds are fenced for the async proxy before the last barrier)
+            if (a.tma_store && gi + 1 == a.n_groups) fence_proxy_async();
             __syncthreads();
         }
 
         // ---- store ----
         if (a.tma_store)
         {
-            // TMA: the generic-proxy writes of the rounds are fenced for the async proxy, then one thread issues the boxes
-            // and waits until they have been READ out of shared memory (the tile buffer is free again)
-            fence_proxy_async();
-            __syncthreads();
+            // TMA: one thread issues the boxes.  Nobody waits here: thread 0 waits for the boxes to be READ out of
+            // shared memory just before it issues the next tile's load, the other threads go on to the next tile's star
+            // prologue (which does not touch the tile) and then block on the load's mbarrier
             if (t == 0)
             {
                 for (int j = 0; j < a.tma.n_copies; j++)
@@ -676,12 +740,15 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                     tma_coords(a.tma, base_out | a.tma.enum_off[j], c);
                     tma_store_5d(&a.tmap_out, tile_u32 + (unsigned)j * (unsigned)a.tma.box_bytes, c[0], c[1], c[2], c[3], c[4]);
                 }
-                tma_store_commit_and_wait_read();
+                tma_store_commit();
             }
+            continue;
         }
         // legacy (streaming, evict-first)
         else if (t_active)
         {
+            unsigned s_out_lo;
+            const unsigned long long g_out_lo = thread_out(s_out_lo);
             if (a.peer_shift < 0)
             {
                 char* dst = reinterpret_cast<char*>(gout + (base_out | g_out_lo));
@@ -721,6 +788,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
         }
         __syncthreads(); // every thread is done with the tile before the next load overwrites it
     }
+    if (a.tma_store && t == 0) tma_store_wait_all();
 }
 
 constexpr int kMaxDevices = 64;
@@ -730,15 +798,19 @@ static int g_num_sms[kMaxDevices] = {0}; // per device: cudaFuncSetAttribute and
 #define BIT(c) (1u << (c))
 constexpr unsigned kVariantMasks[] = {
     0u,                                                                              // pure data movement (remap pack)
-    BIT(RC_DENSE2),                                                                  // random C2 blocks
+    BIT(RC_DENSE2_LU),                                                               // random C2 blocks (in-place L U form)
+    BIT(RC_DENSE2) | BIT(RC_DENSE2_LU),                                              // ... with badly conditioned factors too
     BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_QFT2) | BIT(RC_DENSE1_RR) | BIT(RC_HAD),                                               // H + diagonal
     BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_QFT2) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_STAR),                                // QFT-like
     BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_PERM2),                                               // H / CX
-    BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI),         // dense 1- and 2-qubit blocks
+    BIT(RC_DENSE2_LU) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI),      // dense 1- and 2-qubit blocks
+    BIT(RC_DENSE2) | BIT(RC_DENSE2_LU) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI),
     BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_QFT2) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1),               // Clifford+T style
     BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_QFT2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) | BIT(RC_STAR), // no dense 4x4
-    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_QFT2) | BIT(RC_DENSE2) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) | BIT(RC_MONO1) |
-        BIT(RC_SRN1) | BIT(RC_STAR),                                                 // everything
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_QFT2) | BIT(RC_DENSE2_LU) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) | BIT(RC_PERM2) |
+        BIT(RC_MONO1) | BIT(RC_STAR),                                                // everything but SRN and the direct 4x4
+    BIT(RC_DIAGR) | BIT(RC_DIAGP) | BIT(RC_CP2) | BIT(RC_QFT2) | BIT(RC_DENSE2) | BIT(RC_DENSE2_LU) | BIT(RC_DENSE1) | BIT(RC_DENSE1_RR) | BIT(RC_HAD) | BIT(RC_DENSE1_RI) |
+        BIT(RC_PERM2) | BIT(RC_MONO1) | BIT(RC_SRN1) | BIT(RC_STAR),                 // everything
 };
 constexpr int kNumVariants = sizeof(kVariantMasks) / sizeof(kVariantMasks[0]);
 typedef void (*SweepFn)(const SweepArgs);

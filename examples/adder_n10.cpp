@@ -27,9 +27,9 @@ static void unmaj(Simulation& sim, const IdxType a, const IdxType b, const IdxTy
 int main(int argc, char** argv)
 {
     const int n_qubits = 10;
-    const int n_gpus = 1;
+    // the reference example hard-codes n_gpus = 4 (example/adder_n10_nvgpu_omp.cu:45); here: ./adder_n10 [n_gpus], default 1
+    const int n_gpus = argc > 1 ? atoi(argv[1]) : 1;
     const IdxType cin = 0, a[4] = {1, 2, 3, 4}, b[4] = {5, 6, 7, 8}, cout = 9;
-    (void)argc; (void)argv;
     srand(time(0));
     Simulation sim(n_qubits, n_gpus);
     Gate* g;

@@ -42,19 +42,13 @@ public:
     virtual ~DmSimBackend() {}
 };
 
-// The B200 engine behind the plugin ABI.  One backend object drives ONE GPU of this process (the reference's n_gpus
-// argument spawned one OpenMP thread per device; here n_gpus > 1 is the one-process-per-GPU Simulation overload and
-// is not reachable through this 4-call ABI, so init() rejects it).
+// The B200 engine behind the plugin ABI.  init(n_qubits, n_gpus) drives n_gpus devices of this process, like the
+// reference runner (xacc/nvidia_omp/NvidiaOmpRunner.cu: one Simulation(n_qubits, n_gpus) behind the 4 calls).
 class B200Backend : public DmSimBackend
 {
 public:
     void init(int n_qubits, int n_gpus = 1) override
     {
-        if (n_gpus != 1)
-        {
-            fprintf(stderr, "Error: DmSimBackend on dmsim_b200 drives one GPU per process (n_gpus=%d)\n", n_gpus);
-            exit(1);
-        }
         m_sim = std::make_shared<::DMSim::Simulation>((::DMSim::IdxType)n_qubits, (::DMSim::IdxType)n_gpus);
     }
     void addGate(OP op, const std::vector<int>& qubits, const std::vector<double>& params = {}) override

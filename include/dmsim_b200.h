@@ -8,10 +8,16 @@
  *
  * Conventions
  *  - All functions return DMB_OK (0) or a negative DMB_E* code; dmb_last_error() gives the text.
- *  - A handle owns ONE shard of the state on ONE GPU.  world_size == 1 is the single-GPU engine;
- *    for world_size P = 2^g (one process per GPU) rank r holds the flat indices whose top g bits of
- *    the 2n-bit PHYSICAL index equal r.  The only cross-rank step is the qubit-remap exchange
- *    (dmb_comm_* below).
+ *  - The state is sharded on the top g = log2(world_size) bits of the 2n-bit PHYSICAL index: rank r
+ *    holds the flat indices whose top g bits equal r.  world_size == 1 is the single-GPU engine.
+ *    Two ways to drive P = 2^g GPUs of one node:
+ *      (a) ONE process, ONE handle (the reference's Simulation(n_qubits, n_gpus), :196-271):
+ *          dmb_create(n, P, DMB_ALL_RANKS, first_device, &h) owns all P shards on devices
+ *          [first_device, first_device + P); the shards reach each other through peer access
+ *          (cudaDeviceEnablePeerAccess, no IPC, no NCCL), every call below works on the whole state.
+ *      (b) one process per GPU (torchrun / MPI style): dmb_create(n, P, rank, device, &h) owns ONE
+ *          shard; dmb_comm_* below attach the NCCL communicator (and optionally the peers' buffers).
+ *    The only cross-rank step of a run is the qubit-remap exchange.
  *  - State layout in HBM: interleaved complex FP64 (re,im), flat logical index = col*dim + row with
  *    qubit q = bit q of row (reference :989-998), i.e. a 2n-bit vector on which a gate U on qubit q
  *    acts as U on bit q and conj(U) on bit q+n.  What is stored is rho^T, as in the reference.
@@ -33,6 +39,8 @@ extern "C" {
 #define DMB_ESTATE (-3)   /* call sequence error (run before set_circuit, ...) */
 #define DMB_ENOMEM (-4)
 #define DMB_ECOMM (-5)    /* multi-GPU exchange needed but no communicator attached */
+
+#define DMB_ALL_RANKS (-1) /* rank argument of dmb_create: this handle drives all world_size GPUs from one process */
 
 /* enum OP, reference :42-48 (order matters: xacc/DmSimApi.hpp:6-45 mirrors it).
  * DMB_OP_C1 / DMB_OP_C2 expose the reference's C1_GATE (:1004-1025) and C2_GATE (:1028-1122), which
@@ -78,13 +86,15 @@ typedef struct dmb_sim* dmb_handle;
 
 /* ---- life cycle: replaces Simulation::Simulation / ~Simulation (:196-301) ---- */
 /* device < 0: current CUDA device.  Allocates the shard (16 * 4^n / world_size bytes; a second buffer
- * of the same size is allocated lazily the first time an out-of-place step needs one). */
+ * of the same size is allocated lazily the first time an out-of-place step needs one).
+ * rank == DMB_ALL_RANKS with world_size > 1: a single-process group on devices [max(device, 0), +world_size)
+ * (needs peer access between every pair, as the reference does, :266-269; both buffers are allocated up front). */
 int dmb_create(int n_qubits, int world_size, int rank, int device, dmb_handle* out);
 int dmb_destroy(dmb_handle h);
 /* reset_dm (:308-329): rho[0][0] = 1, identity bit layout. */
 int dmb_reset_dm(dmb_handle h);
-/* Load an arbitrary state (split real/imag host arrays of 4^n doubles, [col][row] like dm_real_res).
- * world_size == 1 only.  Not in the reference (its state is only reachable by running gates). */
+/* Load an arbitrary state (split real/imag host arrays of 4^n doubles, [col][row] like dm_real_res): every shard
+ * keeps the elements it owns.  Not in the reference (its state is only reachable by running gates). */
 int dmb_set_dm(dmb_handle h, const double* real, const double* imag);
 
 /* ---- circuit: replaces append/upload/clear_circuit (:331-377, :496-520) ----
@@ -99,21 +109,25 @@ int dmb_clear_circuit(dmb_handle h);
  * Blocking.  State continues from the previous run (GPU-backend semantics). stats may be NULL. */
 int dmb_run(dmb_handle h, dmb_stats* stats);
 
-/* ---- results: replaces the D2H of dm_real_res / dm_imag_res (:458-466) and measure (:521-549) ---- */
-/* Full matrix into split host arrays (4^n doubles each, [col][row], holds rho^T).  world_size == 1. */
+/* ---- results: replaces the D2H of dm_real_res / dm_imag_res (:458-466) and measure (:521-549) ----
+ * Results of a sharded state are GLOBAL: a group handle gathers over its shards; one rank of a one-process-per-GPU
+ * job answers through the communicator (dmb_comm_init): the call is then COLLECTIVE -- every rank makes it and every
+ * rank receives the full answer (the reference's MPI flavour does the same, src/dmsim_nvgpu_mpi.cuh:472-520).
+ * Without a communicator a rank reports its own part (zeros for what other ranks own; the sum over ranks is the
+ * answer) where that makes sense (dmb_get_elements, dmb_get_diag, dmb_trace, dmb_purity) and fails otherwise. */
+/* Full matrix into split host arrays (4^n doubles each, [col][row], holds rho^T). */
 int dmb_get_dm(dmb_handle h, double* real, double* imag);
 /* n arbitrary elements dm_real_res[f] / dm_imag_res[f], f = col*dim + row (spot checks of states too large to copy
- * back).  With world_size > 1 elements owned by another rank come back as zero (sum over ranks = the values). */
+ * back). */
 int dmb_get_elements(dmb_handle h, const uint64_t* flat_index, size_t n, double* real, double* imag);
-/* Real part of the diagonal (2^n doubles), dm_real_res[i*dim+i].  With world_size > 1 a rank fills the
- * entries it owns and zeroes the others (sum over ranks = full diagonal). */
+/* Real part of the diagonal (2^n doubles), dm_real_res[i*dim+i]. */
 int dmb_get_diag(dmb_handle h, double* diag);
-/* sum_i Re rho_ii and sum_ij |rho_ij|^2 of the local shard (sum over ranks for world_size > 1). */
+/* sum_i Re rho_ii and sum_ij |rho_ij|^2. */
 int dmb_trace(dmb_handle h, double* trace);
 int dmb_purity(dmb_handle h, double* purity);
 /* measure(): p_i = |Re rho_ii|, prefix sum, one basis index per uniform number r[i] in [0,1]
  * (index j with scan[j] <= r < scan[j+1], else 0 -- exactly the reference's rule :536-543).
- * total (may be NULL) receives scan[dim]. world_size == 1. */
+ * total (may be NULL) receives scan[dim]. */
 int dmb_sample(dmb_handle h, const double* r, size_t n, uint64_t* out, double* total);
 /* measure() with the reference's generator: srand(seed); r = rand()/RAND_MAX per shot (:534-539). */
 int dmb_measure(dmb_handle h, unsigned seed, size_t repetition, uint64_t* out, double* total);
@@ -135,7 +149,8 @@ int dmb_comm_import(dmb_handle h, const uint8_t* all_handles);
  * the same form: a host that could not import the handles on some rank calls dmb_comm_p2p(h, 0) on all of them. */
 int dmb_comm_p2p(dmb_handle h, int enable);
 /* Raw shard + layout, for tests and host-side gathers: copies the local shard (interleaved complex,
- * 2 * 4^n / world_size doubles, PHYSICAL order) and the logical->physical bit map (2n ints). */
+ * 2 * 4^n / world_size doubles, PHYSICAL order; a group handle: all shards back to back, 2 * 4^n doubles) and the
+ * logical->physical bit map (2n ints). */
 int dmb_get_shard(dmb_handle h, double* interleaved, int32_t* phys_of_logical);
 
 /* ---- planner introspection (host only, needs no GPU): used by the CPU test-suite ----

@@ -13,7 +13,8 @@
 //   * The full-matrix D2H the reference does after every sim() (:458-466) is lazy: dm_real_res / dm_imag_res are
 //     accessor calls res_real() / res_imag() that fetch on first use after a run (print_res_* and the public
 //     pointers dm_real_res / dm_imag_res are refreshed by sync_results()).  measure() runs on the device.
-//   * n_gpus > 1 means ONE PROCESS PER GPU: construct Simulation(n, world_size, rank, nccl_id) (extra overload).
+//   * Simulation(n_qubits, n_gpus) drives all n_gpus devices from this one process like the reference (:196-271,
+//     :397-399); the extra overload Simulation(n, world_size, rank, nccl_id) is the one-process-per-GPU form.
 //   * Extra factories C1 / C2 expose the reference's unreachable generic gates (C1_GATE :1004, C2_GATE :1028).
 //   * Errors: fatal like the reference (message on stderr + exit(1)); no exceptions cross the API.
 #ifndef DMSIM_B200_HPP
@@ -148,9 +149,10 @@ public:
 class Simulation
 {
 public:
-    Simulation(IdxType _n_qubits, IdxType _n_gpus) { init(_n_qubits, _n_gpus, 0, NULL); }
+    // n_gpus > 1: ONE process, devices 0 .. n_gpus-1 with peer access between every pair (reference :259-269)
+    Simulation(IdxType _n_qubits, IdxType _n_gpus) { init(_n_qubits, _n_gpus, _n_gpus > 1 ? (long long)DMB_ALL_RANKS : 0, NULL); }
     // one process per GPU: rank r of world size _n_gpus; nccl_id = the 128 bytes from dmb_comm_unique_id on rank 0
-    Simulation(IdxType _n_qubits, IdxType _n_gpus, IdxType rank, const uint8_t* nccl_id) { init(_n_qubits, _n_gpus, rank, nccl_id); }
+    Simulation(IdxType _n_qubits, IdxType _n_gpus, IdxType rank, const uint8_t* nccl_id) { init(_n_qubits, _n_gpus, (long long)rank, nccl_id); }
     ~Simulation()
     {
         clear_circuit();
@@ -382,7 +384,7 @@ public:
     dmb_stats last_stats;
 
 private:
-    void init(IdxType _n_qubits, IdxType _n_gpus, IdxType rank, const uint8_t* nccl_id)
+    void init(IdxType _n_qubits, IdxType _n_gpus, long long rank, const uint8_t* nccl_id)
     {
         n_qubits = _n_qubits;
         n_gpus = _n_gpus;
@@ -403,11 +405,11 @@ private:
             exit(1);
         }
         DMSIM_CHECK(dmb_create((int)n_qubits, (int)n_gpus, (int)rank, -1, &h));
-        if (n_gpus > 1)
+        if (n_gpus > 1 && rank != (long long)DMB_ALL_RANKS)
         {
             if (!nccl_id)
             {
-                std::cerr << "Error: n_gpus > 1 needs the one-process-per-GPU constructor (rank, nccl_id)." << std::endl;
+                std::cerr << "Error: the one-process-per-GPU constructor needs the NCCL unique id of rank 0." << std::endl;
                 exit(1);
             }
             DMSIM_CHECK(dmb_comm_init(h, nccl_id));

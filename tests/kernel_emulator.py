@@ -99,7 +99,7 @@ def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = No
 
 
 (RC_DENSE1, RC_DIAG1, RC_MONO1, RC_SRN1, RC_DENSE2, RC_DIAG2, RC_PERM2, RC_DIAGR, RC_DENSE1_RR, RC_DENSE1_RI, RC_STAR,
- RC_HAD, RC_DIAGP, RC_CP2, RC_QFT2) = range(15)
+ RC_HAD, RC_DIAGP, RC_CP2, RC_QFT2, RC_DENSE2_LU) = range(16)
 _POS2 = {0: (1, 0), 1: (2, 0), 2: (2, 1), 3: (3, 0), 4: (3, 1), 5: (3, 2)}
 _PERMS = {0: [0, 1, 3, 2], 1: [0, 3, 2, 1], 2: [0, 2, 1, 3]}
 
@@ -238,6 +238,17 @@ def _apply_reg_op(op, v):
         if code == RC_DENSE2:
             for r in range(4):
                 v[ids[r]] = sum(m[4 * r + c] * a[c] for c in range(4))
+        elif code == RC_DENSE2_LU:  # in place: U top-down (m[0..9], row by row), then L bottom-up (m[10..15])
+            at = 0
+            for i in range(4):
+                v[ids[i]] = m[at] * v[ids[i]]
+                at += 1
+                for j in range(i + 1, 4):
+                    v[ids[i]] = v[ids[i]] + m[at] * v[ids[j]]
+                    at += 1
+            for i in (3, 2, 1):
+                for j in range(i):
+                    v[ids[i]] = v[ids[i]] + m[10 + i * (i - 1) // 2 + j] * v[ids[j]]
         elif code == RC_DIAG2:
             for r in range(4):
                 if not (skip >> r) & 1:
