@@ -5,11 +5,15 @@
 
 A "step" is ONE sim() of the workload circuit on the resident density matrix (dmb_run through the C-ABI).
 N = 1 : workload qft_n15 (benchmark/qft_n15.qasm gate-for-gate, 15 qubits, 16 GiB state) -- the configuration
-        BASELINE.json's metric (gates/s, ms/gate at 15 q on one GPU) is quoted on.
-N > 1 : one process per GPU under torchrun; workload random_c1c2_n16 (N = 2, 4) / random_c1c2_n17 (N = 8),
-        state sharded on the top log2(N) index bits, NCCL qubit-remap exchange inside the timed region.
-Prints ONE JSON line (rank 0).  `--impl reference` times the reference CPU backend (oracle/_ref, the
-unmodified dmsim_cpu_omp.hpp compiled in place) on the host cores on a bounded sample of the same workload.
+        BASELINE.json's metric (gates/s, ms/gate at 15 q on one GPU) is quoted on; the line also carries
+        `extra_workloads` (the other single-GPU configs of BASELINE.json, each measured outside the timed region).
+N > 1 : one process per GPU under torchrun; workload random_c1c2_n16 (N = 2, 4) / random_c1c2_n17 (N = 8), state
+        sharded on the top log2(N) index bits, qubit-remap exchange inside the timed region.  Every N > 1 line carries
+        `parity` (an 11-qubit all-op circuit against the oracle on the N ranks, and the TIMED workload itself against a
+        2^n state-vector run: all diagonal probabilities, 2^16 elements, purity) and `strong_scaling` (random_c1c2_n16
+        on ONE GPU, measured by rank 0 in the same run, against the same circuit on N GPUs).
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference CPU backend (oracle/_ref, the unmodified
+dmsim_cpu_omp.hpp compiled in place) on the host cores on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -24,6 +28,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+# FP64 pipe of one B200 as probed by tools/fp64probe.cu (profiles/r1_fp64probe.txt): 62.7 DFMA per clock per SM x 148 SMs
+# x 1.965 GHz = 18.2e12 FP64 instructions/s = 36.5 TFLOP/s counting an FMA as two
+FP64_TFLOPS, FP64_SRC = 36.5, "profiles/r1_fp64probe.txt (DFMA 62.7 per clock per SM, 148 SMs, 1965 MHz)"
+PARITY_TOL = 1e-12
 
 
 def _peaks():
@@ -91,14 +100,12 @@ def workload(name):
         return n, circuits.bv(n)
     if fam == "adder":
         return 10, circuits.adder_n10()
-    if fam == "vqe_uccsd":  # benchmark/vqe_uccsd_n8.qasm (10808 gates): the gate list travels inside the golden fixture
-        import numpy as np
-        z = np.load(os.path.join(ROOT, "tests", "golden", "vqe_uccsd_n8.npz"))
-        names = importlib.import_module("dm-sim_b200").OP_NAMES
-        return int(z["n"]), [(names[int(g["op"])], [int(q) for q in g["qb"][:2]], float(g["theta"]), float(g["phi"]),
-                              float(g["lam"])) for g in z["gates"]]
+    if fam == "vqe_uccsd":  # benchmark/vqe_uccsd_n8.qasm (10808 gates)
+        return 8, circuits.vqe_uccsd_n8()
     if fam == "random_c1c2":
         return n, circuits.random_c1c2(n, 256)
+    if fam == "allops":   # every op of enum OP + raw C1 / C2 on random qubits (the parity circuit of the N > 1 lines)
+        return n, circuits.random_allops(n, 60)
     if fam == "single":   # one gate = one sweep with 2 ops: the memory pipeline of the sweep kernel
         return n, [("H", [5], 0.0, 0.0, 0.0)]
     if fam == "hlayer":   # one dense 1-qubit gate per qubit
@@ -117,9 +124,9 @@ def reference_arm(args, name):
     while n_cpus * 2 <= cores:
         n_cpus *= 2
     # bounded sample: the same circuit family at a size the CPU finishes in seconds; cost scales 4x per qubit
-    n_s = min(n, args.cpu_sample_qubits)
+    n_s = n if args.cpu_full_size else min(n, args.cpu_sample_qubits)
     fam = name.rpartition("_n")[0]
-    _, g_s = workload(f"{fam}_n{n_s}") if fam != "adder" else (n, gates)
+    _, g_s = workload(f"{fam}_n{n_s}") if fam not in ("adder", "vqe_uccsd") else (n, gates)
     n_cpus = min(n_cpus, 1 << n_s)
     os.environ.setdefault("OMP_PROC_BIND", "close")
     os.environ.setdefault("OMP_PLACES", "cores")
@@ -138,16 +145,228 @@ def reference_arm(args, name):
     scale = 4.0 ** (n - n_s)
     ms_full = ms_sample * scale * (len(gates) / len(g_s))
     value = len(gates) / (ms_full * 1e-3)
-    sample = (f"{fam}_n{n_s} ({len(g_s)} gates) via dmsim_cpu_omp n_cpus={n_cpus}: {ms_sample:.1f} ms/sim; scaled x4^{n - n_s}"
-              f" and x{len(gates)}/{len(g_s)} gates to {name}")
+    extrapolated = n_s != n or len(g_s) != len(gates)
+    sample = (f"{fam}_n{n_s} ({len(g_s)} gates) via dmsim_cpu_omp n_cpus={n_cpus}: {ms_sample:.1f} ms/sim"
+              + (f"; EXTRAPOLATED x4^{n - n_s} and x{len(gates)}/{len(g_s)} gates to {name} (the full size needs "
+                 f"{8 * 8 * 4 ** n / 2 ** 30:.0f} GiB of host memory and minutes per sim)" if extrapolated else "; measured at full size"))
     line = {"metric": "gates/sec", "value": value, "unit": "gates/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_full, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": {"workload": name, "n_qubits": n, "n_gates": len(gates)},
-            "cpu_baseline": {"value": value, "unit": "gates/s", "cores": n_cpus, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "gates/s", "cores": n_cpus, "kind": kind, "sample": sample,
+                             "same_config": not extrapolated, "extrapolated": extrapolated,
+                             "measured_at_full_size": not extrapolated},
             "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     return line
+
+
+class Job:
+    """Process-group plumbing of one bench run (torch.distributed only for the barrier / max-over-ranks)."""
+
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+
+    def init(self):
+        import torch
+        self.torch = torch
+        if self.world > 1:
+            import torch.distributed as dist
+            torch.cuda.set_device(self.local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            dist.barrier()
+            self.dist = dist
+        else:
+            torch.cuda.set_device(0)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max(self, values):
+        if self.dist is None:
+            return [float(v) for v in values]
+        t = self.torch.tensor(list(values), device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def measure(job, dm, name, steps, warmup, world=None, sampler=None, e2e=True, keep=False):
+    """Device time of `steps` runs of workload `name` on the DENSE resident state (+ the end-to-end legs).
+    world = None: the job's ranks (one shard per process); world = 1 inside a multi-rank job: this process alone."""
+    import numpy as np
+    L = dm.lib()
+    n, gates = workload(name)
+    rec, mats = dm.pack_gates(gates)
+    solo = world == 1 and job.world > 1
+    world = job.world if world is None else world
+    sim = dm.Simulation(n, world, rank=job.rank, device=job.local_rank) if world > 1 else dm.Simulation(n, 1)
+    barrier = (lambda: job.torch.cuda.synchronize()) if solo or world == 1 else job.barrier
+
+    def set_circuit():
+        dm._check(L.dmb_set_circuit(sim._h, rec.ctypes.data, len(rec), mats.ctypes.data if mats.size else None, mats.size // 32))
+        sim._uploaded = True
+
+    # `value` / `roofline` are measured on the DENSE resident state: every tile of every sweep is launched (after a reset
+    # the engine would otherwise skip the tiles that are still all-zero, see the e2e leg below)
+    dm.set_option("sparse", 0)
+    sim.reset_dm()
+    set_circuit()
+    for _ in range(warmup):
+        sim.run()
+    if sampler is not None:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, comm_ms, launches, sweeps = 0.0, 0.0, 0, 0
+    for _ in range(steps):
+        sim.run()
+        st = sim.last_stats
+        dev_ms += st["sim_ms"]; comm_ms += st["comm_ms"]
+        launches += st["n_launches"]; sweeps += st["n_sweeps"]
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if sampler is not None else None
+    st = dict(sim.last_stats)
+    if not solo and world > 1:
+        dev_ms, comm_ms, wall_ms = job.max([dev_ms, comm_ms, wall_ms])
+    out = {"name": name, "n": n, "gates": gates, "n_gates": len(gates), "st": st, "ms_step": dev_ms / steps, "dev_ms": dev_ms,
+           "comm_ms": comm_ms, "wall_ms_step": wall_ms / steps, "launches": launches, "sweeps": sweeps, "clocks": clocks,
+           "steps": steps, "world": world}
+    if e2e:
+        # ---- end to end through the C-ABI with HOST buffers: reset + circuit upload (H2D) + run + diagonal (D2H)
+        diag = np.empty(1 << n)
+        dm.set_option("sparse", 1)
+        e2e_ms, parts = [], [0.0, 0.0, 0.0, 0.0]
+        for i in range(2 + min(steps, 3)):
+            barrier()
+            t1 = time.perf_counter()
+            sim.reset_dm()
+            t2 = time.perf_counter()
+            set_circuit()
+            t3 = time.perf_counter()
+            sim.run()
+            t4 = time.perf_counter()
+            dm._check(L.dmb_get_diag(sim._h, diag.ctypes.data))
+            barrier()
+            t5 = time.perf_counter()
+            if i >= 2:
+                e2e_ms.append((t5 - t1) * 1e3)
+                for j, dt in enumerate((t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+                    parts[j] += dt * 1e3
+        e2e_v = sum(e2e_ms) / len(e2e_ms)
+        parts = [x / len(e2e_ms) for x in parts]
+        # the same call sequence WITHOUT the reset: the circuit is re-uploaded and applied to the resident (dense) state,
+        # so that no tile is skipped as still-zero
+        dm.set_option("sparse", 0)
+        sim.reset_dm()
+        res_ms = []
+        for i in range(1 + min(steps, 3)):
+            barrier()
+            t1 = time.perf_counter()
+            set_circuit()
+            sim.run()
+            dm._check(L.dmb_get_diag(sim._h, diag.ctypes.data))
+            barrier()
+            if i >= 1:
+                res_ms.append((time.perf_counter() - t1) * 1e3)
+        e2e_res = sum(res_ms) / len(res_ms)
+        if not solo and world > 1:
+            e2e_v, e2e_res = job.max([e2e_v, e2e_res])
+        out.update({"e2e_ms": e2e_v, "e2e_parts": parts, "e2e_res_ms": e2e_res, "trace": float(diag.sum()),
+                    "h2d": int(sim.last_stats["h2d_bytes"])})
+    if keep:
+        out["sim"] = sim
+    else:
+        del sim
+    return out
+
+
+def roofline(m, peak, peak_src):
+    """The dominant kernel (sweep_kernel) of a measured workload against BOTH floors; `bound` = the higher floor."""
+    st = m["st"]
+    comp_s = (m["dev_ms"] - m["comm_ms"]) * 1e-3
+    sweep_bytes = st["sweep_bytes"]
+    hbm = (m["sweeps"] * sweep_bytes) / comp_s / 1e9 if comp_s > 0 else 0.0
+    fp64 = 2.0 * st["fp64_ops"] * m["steps"] / comp_s / 1e12 if comp_s > 0 else 0.0  # FMA-equivalent TFLOP/s
+    frac_hbm, frac_fp64 = hbm / peak, fp64 / FP64_TFLOPS
+    bound = "fp64" if frac_fp64 > frac_hbm else "hbm"
+    r = {"bound": bound, "kernel": "sweep_kernel",
+         "achieved": fp64 if bound == "fp64" else hbm, "peak": FP64_TFLOPS if bound == "fp64" else peak,
+         "unit": "TFLOP/s" if bound == "fp64" else "GB/s", "frac": max(frac_hbm, frac_fp64),
+         "frac_hbm": frac_hbm, "achieved_GBps": hbm, "peak_GBps": peak, "frac_of_8TBs_nominal": hbm / 8000.0, "peak_source": peak_src,
+         "frac_fp64": frac_fp64, "achieved_fp64_TFLOPs": fp64, "peak_fp64_TFLOPs": FP64_TFLOPS, "peak_fp64_source": FP64_SRC,
+         "fp64_note": "FP64 pipe slots (DFMA / DMUL / DADD of the register-level ops, dmb_stats.fp64_ops) x 2 = FMA-equivalent flop",
+         "avg_launch_ms": comp_s * 1e3 / max(1, m["sweeps"]), "bytes_per_launch": sweep_bytes,
+         "fp64_instr_per_element_per_step": st["fp64_ops"] / (sweep_bytes / 32),
+         "traffic": _ncu_traffic(m["name"])}
+    return r
+
+
+def brief(m, peak, peak_src):
+    """Compact record of an extra workload."""
+    r = roofline(m, peak, peak_src)
+    d = {"workload": m["name"], "n_qubits": m["n"], "n_gates": m["n_gates"], "n_gpus": m["world"], "steps": m["steps"],
+         "ms_per_step": m["ms_step"], "gates_per_s": m["n_gates"] / (m["ms_step"] * 1e-3), "sweeps_per_step": m["st"]["n_sweeps"],
+         "gpu_launches_per_step": m["launches"] // max(1, m["steps"]),
+         "roofline": {k: r[k] for k in ("bound", "frac", "frac_hbm", "frac_fp64", "achieved_GBps", "achieved_fp64_TFLOPs", "avg_launch_ms")}}
+    if "e2e_ms" in m:
+        d["e2e"] = {"ms_per_step": m["e2e_ms"], "gates_per_s": m["n_gates"] / (m["e2e_ms"] * 1e-3),
+                    "resident_state_ms_per_step": m["e2e_res_ms"], "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 8 * (1 << m["n"])}
+        d["trace_after_run"] = m["trace"]
+    return d
+
+
+def parity_small(job, dm):
+    """An 11-qubit circuit of every op (two runs: the second starts from the remapped layout) on the job's ranks against
+    the oracle (the C restatement, bit-identical to the reference CPU backend): full matrix, diagonal, trace."""
+    import numpy as np
+    import oracle
+    n = 11 if job.world <= 8 else 12
+    _, gates = workload(f"allops_n{n}")
+    sim = dm.Simulation(n, job.world, rank=job.rank, device=job.local_rank) if job.world > 1 else dm.Simulation(n, 1)
+    o = oracle.Oracle(n) if job.rank == 0 else None
+    rec, mats = dm.pack_gates(gates)
+    err, exch = 0.0, 0
+    for rep in range(2):
+        dm._check(dm.lib().dmb_set_circuit(sim._h, rec.ctypes.data, len(rec), mats.ctypes.data if mats.size else None, mats.size // 32))
+        sim._uploaded = True
+        sim.run()
+        exch += sim.last_stats["n_exchanges"]
+        re, im = sim.get_dm()      # collective for world > 1: every rank receives the full matrix
+        d, tr = sim.diag(), sim.trace()
+        if job.rank == 0:
+            o.sim(gates)
+            ore, oim = o.dm()
+            err = max(err, float(np.abs(re - ore).max()), float(np.abs(im - oim).max()), float(np.abs(d - o.diag()).max()), abs(tr - 1.0))
+    del sim
+    return {"world": job.world, "n": n, "circuit": f"allops_n{n} (60 random gates over all 38 ops + C1/C2, run twice)",
+            "against": "oracle/dmsim_oracle.c (bit-identical to the reference dmsim_cpu_omp, tests/test_oracle.py)",
+            "exchanges": exch, "max_abs_err": err, "tol": PARITY_TOL}
+
+
+def parity_workload(job, m):
+    """The TIMED workload itself: one run from |0..0><0..0| against a 2^n state-vector run of the same gates."""
+    from oracle.statevector import check_against_statevector
+    sim = m["sim"]
+    sim.reset_dm()
+    sim.run()
+    diag, purity = sim.diag(), sim.purity()
+    res = check_against_statevector(m["n"], m["gates"], diag, sim.elements, purity)
+    res.update({"workload": m["name"], "n": m["n"], "world": m["world"], "trace_err": abs(float(diag.sum()) - 1.0),
+                "against": "oracle/statevector.py (2^n state vector of the same gates; pinned to the oracle at n <= 7): all 2^n "
+                           "diagonal probabilities, 2^16 random elements, purity",
+                "max_abs_err": max(res["diag"], res["elements"]), "tol": PARITY_TOL})
+    return res
 
 
 def main():
@@ -158,13 +377,15 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-sample-qubits", type=int, default=13)
+    ap.add_argument("--cpu-full-size", action="store_true", help="reference arm: run the named size itself (n = 15: 64 GiB, minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra_workloads / strong_scaling / parity (quick A/B runs)")
     args = ap.parse_args()
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.workload is None:
+    job = Job()
+    rank, world = job.rank, job.world
+    default = args.workload is None
+    if default:
         args.workload = {1: "qft_n15", 2: "random_c1c2_n16", 4: "random_c1c2_n16", 8: "random_c1c2_n17"}.get(args.gpus, "random_c1c2_n16")
 
     if args.impl == "reference":
@@ -172,161 +393,105 @@ def main():
             print(json.dumps(reference_arm(args, args.workload)), flush=True)
         return
 
-    import numpy as np
-    import torch
     import __graft_entry__ as ge
-    if local_rank == 0:
+    if job.local_rank == 0:
         ge.build()
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dist.barrier()
-    else:
-        torch.cuda.set_device(0)
+    job.init()
+    if job.local_rank != 0:
+        ge.build()  # (already built: only imports the package)
     dm = importlib.import_module("dm-sim_b200")
-    n, gates = workload(args.workload)
-    rec, mats = dm.pack_gates(gates)
-    sim = dm.Simulation(n, world, rank=rank, device=local_rank) if world > 1 else dm.Simulation(n, 1)
-    if world > 1 and sim.n_gpus > 1 and not hasattr(sim, "_comm_done"):
-        pass
-    L = dm.lib()
+    peak, peak_src = _peaks()
+    extras = default and not args.no_extra
 
-    def set_circuit():
-        dm._check(L.dmb_set_circuit(sim._h, rec.ctypes.data, len(rec), mats.ctypes.data if mats.size else None, mats.size // 32))
-        sim._uploaded = True
+    parity = {}
+    if extras:
+        parity["small"] = parity_small(job, dm)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
+    sampler = ClockSampler(job.local_rank) if rank == 0 else None
+    m = measure(job, dm, args.workload, args.steps, args.warmup, sampler=sampler, keep=True)
+    if extras and world > 1:
+        parity["workload"] = parity_workload(job, m)
+    m.pop("sim", None)
 
-    # `value` / `roofline` are measured on the DENSE resident state: every tile of every sweep is launched (after a reset
-    # the engine would otherwise skip the tiles that are still all-zero, see the e2e leg below)
-    dm.set_option("sparse", 0)
-    sim.reset_dm()
-    set_circuit()
-    for _ in range(args.warmup):
-        sim.run()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    dev_ms, comm_ms, launches, sweeps, exch = 0.0, 0.0, 0, 0, 0
-    for _ in range(args.steps):
-        sim.run()
-        st = sim.last_stats
-        dev_ms += st["sim_ms"]; comm_ms += st["comm_ms"]
-        launches += st["n_launches"]; sweeps += st["n_sweeps"]; exch += st["n_exchanges"]
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop() if rank == 0 else None
-    st = sim.last_stats
-    if dist is not None:
-        t = torch.tensor([dev_ms, comm_ms, wall_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, comm_ms, wall_ms = (float(x) for x in t.tolist())
-
-    # ---- end to end through the C-ABI with HOST buffers: reset + circuit upload (H2D) + run + diagonal (D2H)
-    diag = np.empty(1 << n)
-    dm.set_option("sparse", 1)
-    e2e_ms, parts = [], [0.0, 0.0, 0.0, 0.0]
-    for i in range(2 + min(args.steps, 3)):
-        barrier()
-        t1 = time.perf_counter()
-        sim.reset_dm()
-        t2 = time.perf_counter()
-        set_circuit()
-        t3 = time.perf_counter()
-        sim.run()
-        t4 = time.perf_counter()
-        dm._check(L.dmb_get_diag(sim._h, diag.ctypes.data))
-        barrier()
-        t5 = time.perf_counter()
-        if i >= 2:
-            e2e_ms.append((t5 - t1) * 1e3)
-            for j, dt in enumerate((t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
-                parts[j] += dt * 1e3
-    e2e = sum(e2e_ms) / len(e2e_ms)
-    parts = [x / len(e2e_ms) for x in parts]
-    # the same call sequence WITHOUT the reset: the circuit is re-uploaded and applied to the resident (dense) state, so
-    # that no tile is skipped as still-zero
-    dm.set_option("sparse", 0)
-    sim.reset_dm()
-    res_ms = []
-    for i in range(1 + min(args.steps, 3)):
-        barrier()
-        t1 = time.perf_counter()
-        set_circuit()
-        sim.run()
-        dm._check(L.dmb_get_diag(sim._h, diag.ctypes.data))
-        barrier()
-        if i >= 1:
-            res_ms.append((time.perf_counter() - t1) * 1e3)
-    e2e_res = sum(res_ms) / len(res_ms)
-    if dist is not None:
-        t = torch.tensor([e2e, e2e_res], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e, e2e_res = (float(x) for x in t.tolist())
-        d = torch.from_numpy(diag).cuda()
-        dist.all_reduce(d)
-        diag = d.cpu().numpy()
-    trace = float(diag.sum())
+    extra_workloads, strong = [], None
+    if extras and world == 1:
+        # the other single-GPU configurations of BASELINE.json, each outside the timed region of the headline
+        for name, k, w in (("bv_n15", 5, 3), ("adder_n10", 20, 3), ("vqe_uccsd_n8", 5, 3), ("random_c1c2_n15", 2, 1), ("random_c1c2_n16", 2, 1)):
+            try:
+                extra_workloads.append(brief(measure(job, dm, name, k, w), peak, peak_src))
+            except Exception as e:  # noqa: BLE001  (e.g. not enough device memory for the 64 GiB state)
+                extra_workloads.append({"workload": name, "failed": repr(e)})
+    if extras and world > 1:
+        # strong scaling on ONE workload: random_c1c2_n16 (64 GiB) on one GPU (rank 0 alone) vs the same circuit on N
+        anchor = "random_c1c2_n16"
+        mn = m if args.workload == anchor else measure(job, dm, anchor, 2, 1, e2e=False)
+        job.barrier()
+        m1 = measure(job, dm, anchor, 2, 1, world=1, e2e=False) if rank == 0 else None
+        job.barrier()
+        if rank == 0:
+            strong = {"workload": anchor, "ms_per_step_1gpu": m1["ms_step"], "ms_per_step_Ngpu": mn["ms_step"], "n_gpus": world,
+                      "speedup": m1["ms_step"] / mn["ms_step"], "efficiency": m1["ms_step"] / mn["ms_step"] / world,
+                      "sweeps_1gpu": m1["st"]["n_sweeps"], "sweeps_Ngpu": mn["st"]["n_sweeps"], "exchanges_Ngpu": mn["st"]["n_exchanges"],
+                      "comm_ms_Ngpu": mn["comm_ms"] / mn["steps"],
+                      "what": "same circuit, same total work: rank 0 alone on one GPU (measured in this run) vs all N ranks"}
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        job.close()
         return
-    peak, peak_src = _peaks()
-    ms_step = dev_ms / args.steps
-    n_gates = len(gates)
-    sweep_bytes = st["sweep_bytes"]
-    comp_ms = dev_ms - comm_ms
-    achieved = (sweeps * sweep_bytes) / (comp_ms * 1e-3) / 1e9 if comp_ms > 0 else 0.0
+    st = m["st"]
+    n, n_gates, ms_step = m["n"], m["n_gates"], m["ms_step"]
     line = {
         "metric": "gates/sec", "value": n_gates / (ms_step * 1e-3), "unit": "gates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_gate": ms_step / n_gates,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if world in (2, 4) else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "n_qubits": n, "n_gates": n_gates, "n_primitives": st["n_primitives"],
                    "fused_blocks_per_side": st["n_blocks"], "sweeps_per_step": st["n_sweeps"],
                    "exchanges_per_step": st["n_exchanges"], "state_bytes": 16 * 4 ** n,
                    "state_bytes_per_gpu": 16 * 4 ** n // world,
-                   "scaling_note": "BASELINE.json configs: 15 q on 1 GPU, 16 q on 2/4 GPUs, 17 q on 8 GPUs (16-32 GiB per GPU)",
+                   "scaling_note": "BASELINE.json names a different configuration per GPU count (15 q on 1 GPU, 16 q on 2 / 4, 17 q "
+                                   "on 8): `value` of different N is NOT one scaling series.  The same-workload series is "
+                                   "`strong_scaling` (random_c1c2_n16 on 1 GPU, measured by rank 0 in this run, vs N GPUs)",
                    "l2_policy": "state per GPU (>= 16 GiB at the named sizes) is far larger than the 126 MB L2; no flush needed",
-                   "parallelism": f"shard on top {world.bit_length() - 1} index bits" if world > 1 else "single GPU"},
-        "roofline": {"bound": "hbm", "kernel": "sweep_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "frac_of_8TBs_nominal": achieved / 8000.0, "peak_source": peak_src,
-                     "avg_launch_ms": comp_ms / max(1, sweeps), "bytes_per_launch": sweep_bytes,
-                     "traffic": _ncu_traffic(args.workload)},
-        "e2e": {"value": n_gates / (e2e * 1e-3), "unit": "gates/s", "ms_per_step": e2e,
-                "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": 8 * (1 << n),
-                "host_call_ms": {"reset_dm": parts[0], "set_circuit": parts[1], "run": parts[2], "get_diag": parts[3]},
-                "resident_state": {"value": n_gates / (e2e_res * 1e-3), "ms_per_step": e2e_res,
+                   "parallelism": f"shard on top {world.bit_length() - 1} index bits, one process per GPU" if world > 1 else "single GPU"},
+        "roofline": roofline(m, peak, peak_src),
+        "e2e": {"value": n_gates / (m["e2e_ms"] * 1e-3), "unit": "gates/s", "ms_per_step": m["e2e_ms"],
+                "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 8 * (1 << n),
+                "host_call_ms": dict(zip(("reset_dm", "set_circuit", "run", "get_diag"), m["e2e_parts"])),
+                "quoted": "from |0..0><0..0| (dmb_reset_dm inside the timed region; on one GPU the leading sweeps skip the tiles "
+                          "that are still all-zero, 'sparse start')",
+                "resident_state": {"value": n_gates / (m["e2e_res_ms"] * 1e-3), "ms_per_step": m["e2e_res_ms"],
                                    "what": "same calls without dmb_reset_dm: circuit applied to the resident dense state"},
                 "what": "host gate list in, host diagonal out, one circuit from |0><0| as the reference's sim(): dmb_reset_dm + "
                         "dmb_set_circuit (plan + H2D of the device op tables) + dmb_run + dmb_get_diag (D2H of the 2^n "
-                        "probabilities), wall clock.  After a reset the leading sweeps launch only the tiles that can be "
-                        "non-zero (single GPU; DESIGN.md 'sparse start'); `value` and `resident_state` run on the dense state"},
+                        "probabilities), wall clock"},
         # size-independent rate (gates/s shrinks 4x per added qubit): gates x density-matrix elements updated per second
         "work_rate": {"value": n_gates * float(4 ** n) / (ms_step * 1e-3), "unit": "gate x element updates/s"},
-        "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
-        "trace_after_run": trace, "clocks": clocks,
+        "gpu_launches": int(m["launches"]), "wall_ms_per_step": m["wall_ms_step"],
+        "trace_after_run": m["trace"], "clocks": m["clocks"],
     }
+    if parity:
+        worst = max(p["max_abs_err"] for p in parity.values())
+        line["parity"] = dict(parity, max_abs_err=worst, tol=PARITY_TOL, ok=bool(worst < PARITY_TOL))
+    if extra_workloads:
+        line["extra_workloads"] = extra_workloads
+    if strong:
+        line["strong_scaling"] = strong
     if world > 1:
-        line["comm"] = {"ms_per_step": comm_ms / args.steps, "bytes_sent_per_rank_per_step": st["exchange_bytes"],
-                        "GBps_per_direction": (st["exchange_bytes"] / 1e9) / (comm_ms / args.steps * 1e-3) if comm_ms > 0 else None}
+        line["comm"] = {"ms_per_step": m["comm_ms"] / args.steps, "bytes_sent_per_rank_per_step": st["exchange_bytes"],
+                        "GBps_per_direction": (st["exchange_bytes"] / 1e9) / (m["comm_ms"] / args.steps * 1e-3) if m["comm_ms"] > 0 else None,
+                        "what": "device time between the CUDA events around the qubit remap (barrier + permuting sweep storing into "
+                                "the peers' shards over NVLink + barrier)"}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            ref = reference_arm(argparse.Namespace(gpus=1, steps=1, warmup=0, cpu_sample_qubits=args.cpu_sample_qubits), args.workload)
+            ref = reference_arm(argparse.Namespace(gpus=1, steps=1, warmup=0, cpu_sample_qubits=args.cpu_sample_qubits,
+                                                   cpu_full_size=False), args.workload)
             line["cpu_baseline"] = ref["cpu_baseline"]
         except Exception as e:  # the checker must never take the product's number down
             line["cpu_baseline"] = {"value": None, "unit": "gates/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    job.close()
+    if parity and not line["parity"]["ok"]:
+        sys.exit(3)
 
 
 def _ncu_traffic(workload):

@@ -45,7 +45,8 @@ class dmb_stats(ctypes.Structure):
     _fields_ = [("sim_ms", ctypes.c_double), ("comm_ms", ctypes.c_double), ("comp_ms", ctypes.c_double),
                 ("n_gates", ctypes.c_uint64), ("n_primitives", ctypes.c_uint64), ("n_blocks", ctypes.c_uint64),
                 ("n_sweeps", ctypes.c_uint64), ("n_exchanges", ctypes.c_uint64), ("n_launches", ctypes.c_uint64),
-                ("sweep_bytes", ctypes.c_uint64), ("exchange_bytes", ctypes.c_uint64), ("h2d_bytes", ctypes.c_uint64)]
+                ("sweep_bytes", ctypes.c_uint64), ("exchange_bytes", ctypes.c_uint64), ("h2d_bytes", ctypes.c_uint64),
+                ("fp64_ops", ctypes.c_uint64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -76,3 +76,45 @@ def random_c1c2(n: int, n_gates: int = 256, seed: int = 20201115):
             a, b = rng.choice(n, size=2, replace=False)
             g.append(("C2", [int(a), int(b)], 0.0, 0.0, 0.0, haar_unitary(4, rng)))
     return g
+
+
+def vqe_uccsd_n8():
+    """benchmark/vqe_uccsd_n8.qasm gate for gate (8 qubits, 10808 gates = 5488 cx + 2352 h + 2352 y + 616 rz): the gate
+    list as parsed by the OpenQASM front-end (tests/golden/make_golden.py), stored next to this file so that the GPU box
+    (which has no /root/reference) can run the configuration."""
+    import os
+
+    names = ["U3", "U2", "U1", "CX", "ID", "X", "Y", "Z", "H", "S", "SDG", "T", "TDG", "RX", "RY", "RZ"]
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "vqe_uccsd_n8_gates.npz"))
+    return [(names[int(op)], [int(a), int(b)], float(t), float(p), float(la))
+            for op, a, b, t, p, la in zip(z["op"], z["q0"], z["q1"], z["theta"], z["phi"], z["lam"])]
+
+
+_ARITY = {"CX": 2, "CZ": 2, "CY": 2, "SWAP": 2, "CH": 2, "CRX": 2, "CRY": 2, "CRZ": 2, "CU1": 2, "CU3": 2, "RXX": 2, "RZZ": 2,
+          "RYY": 2, "CCX": 3, "CSWAP": 3, "RCCX": 3, "RC3X": 4, "C3X": 4, "C3SQRTX": 4, "C4X": 5, "C2": 2}
+_ALL_OPS = ["U3", "U2", "U1", "CX", "ID", "X", "Y", "Z", "H", "S", "SDG", "T", "TDG", "RX", "RY", "RZ", "CZ", "CY", "SWAP", "CH",
+            "CCX", "CSWAP", "CRX", "CRY", "CRZ", "CU1", "CU3", "RXX", "RZZ", "RCCX", "RC3X", "C3X", "C3SQRTX", "C4X", "R", "W", "RYY",
+            "C1", "C2"]
+
+
+def random_allops(n: int, n_gates: int = 60, seed: int = 1115):
+    """n_gates random gates over every op of enum OP (except SRN, which is not a quantum gate) plus the raw C1 / C2, on
+    random distinct qubits with random angles: the parity circuit bench.py runs on the ranks of a multi-GPU job."""
+    rng = np.random.default_rng(seed)
+    g = []
+    while len(g) < n_gates:
+        nm = _ALL_OPS[int(rng.integers(len(_ALL_OPS)))]
+        a = _ARITY.get(nm, 1)
+        if a > n:
+            continue
+        q = [int(x) for x in rng.choice(n, size=a, replace=False)]
+        th, ph, la = (float(x) for x in rng.uniform(-3.2, 3.2, size=3))
+        if nm == "R":
+            th = 1.0 if rng.integers(2) else -1.0  # R multiplies by i*theta: |theta| = 1 keeps the state normalised
+        if nm == "C1":
+            g.append((nm, q, 0.0, 0.0, 0.0, haar_unitary(2, rng)))
+        elif nm == "C2":
+            g.append((nm, q, 0.0, 0.0, 0.0, haar_unitary(4, rng)))
+        else:
+            g.append((nm, q, th, ph, la))
+    return g

@@ -43,6 +43,7 @@ static int fail(int code, const std::string& msg)
 
 static PlanOptions g_opt;
 static int g_use_graph = 1;
+static int g_grid_per_sm = 0;   // experiments: resident CTAs per SM of the sweep kernel (0 = what the occupancy query says)
 static int g_sparse_start = 1; // skip the tiles that are still all-zero after dmb_reset_dm (DMB_SPARSE=0 / option "sparse")
 static bool g_opt_init = false;
 static void init_options()
@@ -58,6 +59,7 @@ static void init_options()
     if (const char* e = getenv("DMB_TMA")) g_opt.tma = atoi(e) != 0;
     if (const char* e = getenv("DMB_TMA_BOX_BITS")) set_sweep_tma_box_bits(atoi(e));
     if (const char* e = getenv("DMB_DENSE2_LU")) set_sweep_dense2_lu(atoi(e) != 0);
+    if (const char* e = getenv("DMB_GRID_PER_SM")) g_grid_per_sm = atoi(e);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -227,6 +229,7 @@ struct dmb_sim
     std::vector<DevStar> host_stars;
     std::vector<DevRound> host_rounds;
     std::vector<DevGroup> host_groups;
+    unsigned long long fp64_per_16 = 0; // FP64 instructions per 16 shard elements over all sweeps of the plan
 
     // Single-process multi-GPU (reference Simulation(n_qubits, n_gpus), :196-271: one host process drives all devices):
     // a GROUP handle (rank == DMB_ALL_RANKS) owns one shard object per device and no buffers of its own.  The shards
@@ -568,6 +571,7 @@ static int plan_and_encode(dmb_sim* s)
     s->star_offset.assign(nsteps, 0);
     s->n_dev_stars.assign(nsteps, 0);
     EncodedSweep enc;
+    s->fp64_per_16 = 0;
     for (size_t i = 0; i < nsteps; i++)
     {
         s->op_offset[i] = s->host_ops.size();
@@ -583,6 +587,7 @@ static int plan_and_encode(dmb_sim* s)
         {
             return fail(DMB_ESTATE, e.what());
         }
+        s->fp64_per_16 += enc.fp64_per_16;
         s->n_dev_ops[i] = (int)enc.stream.size(); // bytes
         s->n_dev_stars[i] = (int)enc.stars.size();
         s->op_masks[i] = enc.op_mask;
@@ -606,6 +611,7 @@ static void adopt_plan(dmb_sim* s, const dmb_sim* src)
     s->n_dev_groups = src->n_dev_groups; s->n_dev_stars = src->n_dev_stars; s->op_masks = src->op_masks;
     s->host_ops = src->host_ops; s->host_stars = src->host_stars; s->host_rounds = src->host_rounds;
     s->host_groups = src->host_groups;
+    s->fp64_per_16 = src->fp64_per_16;
 }
 
 // device part: the single H2D of the step (stream-ordered; the copies are flushed before returning because the host
@@ -781,7 +787,7 @@ static int enqueue_sweep(dmb_sim* s, size_t i, int& cur, uint64_t& launches, uns
     int rca = fill_sweep_args(s, i, in, out, a, support);
     if (rca) return rca;
     for (int j = 0; j < sw.k; j++) support |= 1ull << sw.in_pos[j];
-    const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)sweep_max_grid(a));
+    const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)(g_grid_per_sm > 0 ? g_grid_per_sm * device_num_sms() : sweep_max_grid(a)));
     CU(launch_sweep(a, grid, s->stream));
     CU(cudaGetLastError());
     launches++;
@@ -970,6 +976,7 @@ static int group_run(dmb_sim* grp, dmb_stats* stats)
         stats->sweep_bytes = 32ull * lead->shard_elems;
         stats->exchange_bytes = lead->plan.n_exchanges * (uint64_t)(lead->world - 1) * (lead->shard_elems / lead->world) * 16ull;
         stats->h2d_bytes = lead->h2d_bytes * grp->shards.size();
+        stats->fp64_ops = lead->fp64_per_16 * (lead->shard_elems / 16);
     }
     return DMB_OK;
 }
@@ -1076,6 +1083,7 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
         stats->sweep_bytes = 32ull * s->shard_elems;
         stats->exchange_bytes = s->plan.n_exchanges * (uint64_t)(s->world - 1) * (s->shard_elems / s->world) * 16ull;
         stats->h2d_bytes = s->h2d_bytes;
+        stats->fp64_ops = s->fp64_per_16 * (s->shard_elems / 16);
     }
     return DMB_OK;
 }

@@ -728,6 +728,30 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
     fold_hadamard_scales(out.ops);
     merge_butterflies(out);
 
+    // FP64 instructions per 16 elements (one lane, one iteration) of every device op: the sweep's algorithmic FP64 work
+    out.fp64_per_16 = 0;
+    for (const DevOp& d : out.ops)
+    {
+        unsigned long long c = 0;
+        switch (d.code)
+        {
+        case RC_DENSE1: c = 128; break;
+        case RC_DENSE1_RR: case RC_DENSE1_RI: c = 64; break;
+        case RC_HAD: c = 32ull * __builtin_popcount((unsigned)d.aux & 15u); break;
+        case RC_MONO1: c = ((d.aux >> 12) & 1) ? 0 : 64; break;
+        case RC_SRN1: c = 48; break;
+        case RC_DENSE2: case RC_DENSE2_LU: c = 256; break;
+        case RC_PERM2: c = ((d.aux >> 12) & 1) ? 0 : 64; break;
+        case RC_DIAGR: c = 4ull * (16 - __builtin_popcount((unsigned)d.aux & 0xffffu)); break;
+        case RC_DIAGP: c = 4ull * (8 - __builtin_popcount((unsigned)d.aux & 0xffu)); break;
+        case RC_CP2: c = 16; break;
+        case RC_QFT2: c = 80; break;
+        case RC_STAR: c = 36ull * __builtin_popcount((unsigned)d.aux & 15u); break;
+        default: break;
+        }
+        out.fp64_per_16 += c;
+    }
+
     // ---- the device op stream: 16-byte header + the used part of the payload per op, a zero header at the end ----
     std::vector<int> offset16(out.ops.size() + 1, 0);
     for (size_t i = 0; i < out.ops.size(); i++)

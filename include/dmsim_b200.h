@@ -80,6 +80,8 @@ typedef struct dmb_stats
     uint64_t sweep_bytes;  /* algorithmic bytes of one sweep of the local shard = 32 * 4^n / P */
     uint64_t exchange_bytes; /* bytes sent per rank over NVLink by this run */
     uint64_t h2d_bytes;    /* device op tables copied host -> device by the dmb_set_circuit this run executes */
+    uint64_t fp64_ops;     /* algorithmic FP64 instructions (DFMA / DMUL / DADD, one pipe slot each) per GPU of this run:
+                              what the register-level ops of all sweeps spend on the local shard */
 } dmb_stats;
 
 typedef struct dmb_sim* dmb_handle;

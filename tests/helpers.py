@@ -57,29 +57,8 @@ def to_complex(re, im):
 
 
 def statevector(n, gates):
-    """TEST INFRASTRUCTURE: 2^n state-vector run of a circuit made of H / X / U1 / RZ / CX only (the gates of
-    benchmark/qft_n15.qasm and bv_n15.qasm), with the reference's conventions (U1 = diag(1, e^{i lam}), RZ == U1,
-    src/dmsim_nvgpu_omp.cuh:1381-1397, :1485-1489).  Used for size-independent checks at n = 15: every circuit of
-    BASELINE.json starts pure, so rho = psi psi^dagger and what the engine stores is rho^T."""
-    psi = np.zeros(1 << n, dtype=np.complex128)
-    psi[0] = 1.0
-    idx = np.arange(1 << n)
-    s2i = 0.70710678118654752440
-    for g in gates:
-        name, q = g[0], g[1]
-        if name == "H":
-            b = 1 << q[0]
-            lo = idx[(idx & b) == 0]
-            a0, a1 = psi[lo].copy(), psi[lo | b].copy()
-            psi[lo], psi[lo | b] = s2i * (a0 + a1), s2i * (a0 - a1)
-        elif name == "X":
-            psi = psi[idx ^ (1 << q[0])]
-        elif name in ("U1", "RZ"):
-            lam = g[4] if name == "U1" else g[3]
-            psi[(idx >> q[0]) & 1 == 1] *= np.cos(lam) + 1j * np.sin(lam)
-        elif name == "CX":
-            c, t = q[0], q[1]
-            psi = psi[np.where((idx >> c) & 1 == 1, idx ^ (1 << t), idx)]
-        else:
-            raise ValueError(f"statevector(): unsupported gate {name}")
-    return psi
+    """TEST INFRASTRUCTURE: 2^n state-vector run with the reference's gate conventions (oracle/statevector.py: H X Y Z S
+    SDG T TDG U1 RZ RX RY U2 U3 W CX CZ and raw C1 / C2).  Used for size-independent checks at n >= 15: every circuit
+    of BASELINE.json starts pure, so rho = psi psi^dagger and what the engine stores is rho^T."""
+    from oracle.statevector import statevector as sv
+    return sv(n, gates)

@@ -27,7 +27,7 @@ def test_every_declared_symbol_is_exported(dm):
 
 def test_pod_layouts(dm):
     assert dm.GATE_DTYPE.itemsize == 56
-    assert ctypes.sizeof(dm.dmb_stats) == 3 * 8 + 9 * 8
+    assert ctypes.sizeof(dm.dmb_stats) == 3 * 8 + 10 * 8
     assert dm.lib().dmb_version().decode().startswith("dmsim-b200")
 
 
