@@ -732,6 +732,7 @@ static int fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, dou
 
 static int comm_events(dmb_sim* s, size_t comm_idx)
 {
+    CU(cudaSetDevice(s->device)); // an event belongs to the device that is current when it is created
     while (s->ev_comm.size() < 2 * (comm_idx + 1))
     {
         cudaEvent_t a_;
