@@ -43,6 +43,7 @@ static int fail(int code, const std::string& msg)
 
 static PlanOptions g_opt;
 static int g_use_graph = 1;
+static int g_tma_prefetch = 0;  // L2 prefetch of a CTA's next tile (DMB_TMA_PREFETCH=0 / option "tma_prefetch")
 static int g_grid_per_sm = 0;   // experiments: resident CTAs per SM of the sweep kernel (0 = what the occupancy query says)
 static int g_sparse_start = 1; // skip the tiles that are still all-zero after dmb_reset_dm (DMB_SPARSE=0 / option "sparse")
 static bool g_opt_init = false;
@@ -60,6 +61,8 @@ static void init_options()
     if (const char* e = getenv("DMB_TMA_BOX_BITS")) set_sweep_tma_box_bits(atoi(e));
     if (const char* e = getenv("DMB_DENSE2_LU")) set_sweep_dense2_lu(atoi(e) != 0);
     if (const char* e = getenv("DMB_GRID_PER_SM")) g_grid_per_sm = atoi(e);
+    if (const char* e = getenv("DMB_DUAL")) set_sweep_dual(atoi(e) != 0);
+    if (const char* e = getenv("DMB_TMA_PREFETCH")) g_tma_prefetch = atoi(e);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -385,6 +388,7 @@ int dmb_set_option(const char* name, int64_t value)
     else if (!strcmp(name, "tma")) g_opt.tma = value != 0;
     else if (!strcmp(name, "tma_box_bits")) set_sweep_tma_box_bits((int)value);
     else if (!strcmp(name, "dense2_lu")) set_sweep_dense2_lu(value != 0);
+    else if (!strcmp(name, "tma_prefetch")) g_tma_prefetch = (int)value;
     else return fail(DMB_EINVAL, std::string("unknown option ") + name);
     return DMB_OK;
 }
@@ -721,6 +725,9 @@ static int fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, dou
     a.n_rounds = s->n_dev_rounds[step];
     a.n_groups = s->n_dev_groups[step];
     a.op_mask = s->op_masks[step];
+    a.tma_prefetch = g_tma_prefetch;
+    if (a.n_comp > 21) return fail(DMB_EINVAL, "shard too large for the tile-base tables");
+    fill_base_tables(a);
     if (a.tma_load)
     {
         std::string why;

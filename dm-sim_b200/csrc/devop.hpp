@@ -155,7 +155,8 @@ static_assert(sizeof(DevOp) == 272, "DevOp layout");
 
 // A round: the lane loads the 2^kRegBits elements  base ^ roff[c]  (base = lane_tab[lane] ^ iter_tab[iter] ^
 // wtab[warp], everything pre-swizzled), applies ops [first, first+count) in registers and stores them back:
-// ONE shared-memory round trip for `count` ops.
+// ONE shared-memory round trip for `count` ops.  lane_tab / iter_tab / roff / DevGroup::wtab hold BYTE offsets into the
+// tile (element index * 16 <= 65520): the XOR of the four is the address, no scaling on the device.
 constexpr int kMaxOpsPerRound = 16; // the encoder splits longer rounds (same tables, one more shared-memory round trip)
 struct alignas(16) DevRound
 {
@@ -232,7 +233,11 @@ struct SweepArgs
     unsigned char cout[40];      // ... when storing
     // TMA tile I/O (full-size tiles): swz_mode = kSwzTma, the tile is loaded (tma_load) / stored (tma_store: in-place
     // sweeps that do not permute bits) as boxes of ONE tensor map over the shard buffer
-    int swz_mode, tma_load, tma_store, tma_pad;
+    int swz_mode, tma_load, tma_store;
+    int tma_prefetch; // thread 0 also prefetches the CTA's next tile into L2 when it issues a tile's loads
+    // tile id -> element offset of the tile (the deposit of the id's bits at cin[] / cout[]), as three 7-bit lookups:
+    // base = base_in[0][id & 127] | base_in[1][(id >> 7) & 127] | base_in[2][id >> 14]
+    unsigned long long base_in[3][128], base_out[3][128];
     TmaGeom tma;
     TmaDesc tmap_in, tmap_out;
 };

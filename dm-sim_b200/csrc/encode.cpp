@@ -458,7 +458,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
         std::sort(wpos.begin(), wpos.end());
         unsigned wmask = 0;
         for (int p : wpos) wmask |= 1u << p;
-        for (int w = 0; w < (1 << kWarpBits); w++) g.wtab[w] = (uint16_t)swz_host(deposit((unsigned)w, wpos), mode);
+        for (int w = 0; w < (1 << kWarpBits); w++) g.wtab[w] = (uint16_t)(16u * swz_host(deposit((unsigned)w, wpos), mode));
 
         for (size_t ri = first; ri < end; ri++)
         {
@@ -480,7 +480,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
             memset(&rd, 0, sizeof(rd));
             rd.first = (int32_t)out.ops.size(); // op INDEX for now; rewritten to the stream offset below
             const int rd_first = rd.first;
-            for (int c = 0; c < kRegElems; c++) rd.roff[c] = (uint16_t)swz_host(deposit((unsigned)c & ((1u << R) - 1u), rb), mode);
+            for (int c = 0; c < kRegElems; c++) rd.roff[c] = (uint16_t)(16u * swz_host(deposit((unsigned)c & ((1u << R) - 1u), rb), mode));
             std::vector<int> freep;
             for (int p = 0; p < k; p++)
                 if (!(((wmask | rmask) >> p) & 1u)) freep.push_back(p);
@@ -505,9 +505,9 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                 if (!taken[p]) iterp.push_back(p);
             rd.n_iter = 1 << (int)iterp.size();
             rd.n_active = 1 << nl;
-            for (int l = 0; l < 32; l++) rd.lane_tab[l] = (uint16_t)swz_host(deposit((unsigned)l & ((1u << nl) - 1u), lanep), mode);
+            for (int l = 0; l < 32; l++) rd.lane_tab[l] = (uint16_t)(16u * swz_host(deposit((unsigned)l & ((1u << nl) - 1u), lanep), mode));
             for (int it = 0; it < 8; it++)
-                rd.iter_tab[it] = (uint16_t)swz_host(deposit((unsigned)it & ((unsigned)rd.n_iter - 1u), iterp), mode);
+                rd.iter_tab[it] = (uint16_t)(16u * swz_host(deposit((unsigned)it & ((unsigned)rd.n_iter - 1u), iterp), mode));
             out.rounds.push_back(rd);
 
             auto reg_pos = [&](int j) { // position of tile bit j among the round's register bits, -1 if none
@@ -870,12 +870,30 @@ void fill_sweep_tables(const Sweep& sw, int M, SweepArgs& a)
     }
 }
 
+void fill_base_tables(SweepArgs& a)
+{
+    for (int t = 0; t < 3; t++)
+        for (int v = 0; v < 128; v++)
+        {
+            unsigned long long bi = 0, bo = 0;
+            for (int b = 0; b < 7; b++)
+            {
+                const int i = 7 * t + b;
+                if (i >= a.n_comp || !((v >> b) & 1)) continue;
+                bi |= 1ull << a.cin[i];
+                bo |= 1ull << a.cout[i];
+            }
+            a.base_in[t][v] = bi;
+            a.base_out[t][v] = bo;
+        }
+}
+
 std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a)
 {
     std::ostringstream o;
-    auto arr = [&](const char* name, auto* v, int n) {
+    auto arr = [&](const char* name, auto* v, int n, unsigned div = 1) {
         o << "\"" << name << "\":[";
-        for (int i = 0; i < n; i++) o << (i ? "," : "") << (unsigned long long)v[i];
+        for (int i = 0; i < n; i++) o << (i ? "," : "") << (unsigned long long)v[i] / div;
         o << "]";
     };
     o << "{\"k\":" << a.k << ",\"n_comp\":" << a.n_comp << ",\"swz\":" << a.swz_mode << ",\"tma_load\":" << a.tma_load
@@ -904,7 +922,7 @@ std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a)
     {
         const DevGroup& G = e.groups[g];
         o << (g ? "," : "") << "{\"first\":" << G.first << ",\"count\":" << G.count << ",\"n_warps\":" << G.n_warps << ",";
-        arr("wtab", G.wtab, 16);
+        arr("wtab", G.wtab, 16, 16); // (byte offsets on the device, element indices in the JSON)
         o << "}";
     }
     o << "],\"rounds\":[";
@@ -913,9 +931,9 @@ std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a)
         const DevRound& D = e.rounds[r];
         o << (r ? "," : "") << "{\"first\":" << D.first << ",\"count\":" << D.count << ",\"n_iter\":" << D.n_iter
           << ",\"n_active\":" << D.n_active << ",";
-        arr("lane_tab", D.lane_tab, 32); o << ",";
-        arr("iter_tab", D.iter_tab, 8); o << ",";
-        arr("roff", D.roff, kRegElems);
+        arr("lane_tab", D.lane_tab, 32, 16); o << ",";
+        arr("iter_tab", D.iter_tab, 8, 16); o << ",";
+        arr("roff", D.roff, kRegElems, 16);
         o << "}";
     }
     o << "],\"ops\":[";

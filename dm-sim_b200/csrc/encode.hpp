@@ -27,6 +27,8 @@ int sweep_tma_box_bits();
 // dense 4x4 ops as in-place L U (RC_DENSE2_LU) where the factors stay small (default on)
 void set_sweep_dense2_lu(bool on);
 bool sweep_dense2_lu();
+// the tile-id -> tile-base lookup tables of `a` from its (possibly reduced: sparse start) cin / cout / n_comp
+void fill_base_tables(SweepArgs& a);
 // JSON text of the device tables of one sweep (for the CPU test-suite's kernel-indexing emulator)
 std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a);
 } // namespace dmb

@@ -18,6 +18,7 @@ struct LayoutArgs
 
 size_t sweep_smem_bytes(const SweepArgs& a);
 cudaError_t launch_sweep(const SweepArgs& a, int grid, cudaStream_t s);
+void set_sweep_dual(bool on);           // experiments: full-size tiles on the two-iterations-resident kernel
 int device_num_sms();                   // SM count of the current device
 int sweep_max_grid(const SweepArgs& a); // resident CTAs for this sweep's shared-memory footprint (SMs * occupancy)
 void sweep_setup();                     // one-time function attributes (must not run inside a stream capture)

@@ -102,6 +102,13 @@ __device__ __forceinline__ void tma_load_5d(unsigned dst, const TmaDesc* map, un
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
                  : "memory");
 }
+// the box into L2 only (the next tile of this CTA: its real load then hits L2 instead of waiting for DRAM)
+__device__ __forceinline__ void tma_prefetch_5d(const TmaDesc* map, int c0, int c1, int c2, int c3, int c4)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];\n"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_5d(const TmaDesc* map, unsigned src, int c0, int c1, int c2, int c3, int c4)
 {
     asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];\n"
@@ -127,6 +134,19 @@ __device__ __forceinline__ void tma_coords(const TmaGeom& g, unsigned long long 
     c[0] <<= 1;
 }
 
+// explicit shared-state-space accesses with a 32-bit address: the tile's window offset folds into the instruction's
+// immediate (through generic pointers ptxas adds the shared window base to every address: one extra instruction each)
+__device__ __forceinline__ double2 lds128(unsigned addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(unsigned addr, double2 v)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+
 __device__ __forceinline__ void st_stream(double2* p, double2 v)
 {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
@@ -137,6 +157,8 @@ __device__ __forceinline__ void st_stream(double2* p, double2 v)
 // <-> round register bit r).  P / (PH, PL) are compile-time register bits, so every v[] index is static.
 // ------------------------------------------------------------------------------------------------
 constexpr int E = kRegElems;
+constexpr unsigned kDynSmemBase = 1024; // shared-window offset of the dynamic shared memory (no static shared memory in the
+                                        // kernel; the first KiB is the system's) -- checked at kernel start
 // an op in the shared-memory op stream: DevOpHdr (16 bytes) + payload
 // (the kernel never reads vid / size16 from the stream: it dispatches from DevRound::vids and every body knows its size)
 struct Op
@@ -238,7 +260,7 @@ __device__ __forceinline__ void r_mono1(double2 (&v)[E], Op op)
 }
 // reference SRN_GATE (:1253-1266): re0'=re1'=(re0+re1)/2, im0'=(im0-im1)/2, im1'=(-im0+im1)/2
 template <int P>
-__device__ __forceinline__ void r_srn1(double2 (&v)[E])
+__device__ __forceinline__ void r_srn1(double2 (&v)[E], Op)
 {
 #pragma unroll
     for (int q = 0; q < E; q++)
@@ -397,8 +419,10 @@ __device__ __forceinline__ void r_diagp(double2 (&v)[E], Op op)
 // controlled-phase star: the elements whose register bit p is set get the phase  L_p[lane] * WO_p[iw]
 struct StarCtx
 {
-    const double2* tab; // shared, per slot 40 entries: WO[8] (rebuilt per tile) | L[32] = la x lb per lane (built once)
-    int lane, iw;
+    // shared, per slot 40 entries: WO[8] (rebuilt per tile) | L[32] = la x lb per lane (built once); the two pointers
+    // address this lane's entry of slot 0 (lane: fixed for the kernel; wo: per warp and iteration)
+    const double2* lane_p;
+    const double2* wo_p;
 };
 constexpr int kStarEntries = kStarSmemBytes / 16;
 // mask = the register bits with a star; their DevStar slots are consecutive from `slot` (advanced past them)
@@ -413,8 +437,7 @@ __device__ __forceinline__ void r_star(double2 (&v)[E], int mask, int& slot, con
         for (int q = 0; q < 2; q++)
             if ((mask >> (h + q)) & 1)
             {
-                const double2* tb = sc.tab + slot * kStarEntries;
-                ph[q] = cmul(tb[8 + sc.lane], tb[sc.iw]);
+                ph[q] = cmul(sc.lane_p[slot * kStarEntries], sc.wo_p[slot * kStarEntries]);
                 slot++;
             }
 #pragma unroll
@@ -442,46 +465,58 @@ __device__ __forceinline__ void r_hadm(double2 (&v)[E], int mask)
 // vid = dev_vid(code, pos, aux) (devop.hpp): one dense jump table for op kind and register position.
 #define DMB_HAS(c) ((MASK >> (c)) & 1u)
 #define DMB_SZ(c) (16 + dev_op_payload_bytes(c))
-#define DMB_CASE1(base, c, FN, ...)                                                            \
-    case (base) + 0: if (DMB_HAS(c)) { FN<0>(__VA_ARGS__); p += DMB_SZ(c); } break;            \
-    case (base) + 1: if (DMB_HAS(c)) { FN<1>(__VA_ARGS__); p += DMB_SZ(c); } break;            \
-    case (base) + 2: if (DMB_HAS(c)) { FN<2>(__VA_ARGS__); p += DMB_SZ(c); } break;            \
-    case (base) + 3: if (DMB_HAS(c)) { FN<3>(__VA_ARGS__); p += DMB_SZ(c); } break;
-#define DMB_CASE2(base, c, FN, ...)                                                            \
-    case (base) + 0: if (DMB_HAS(c)) { FN<1, 0>(__VA_ARGS__); p += DMB_SZ(c); } break;         \
-    case (base) + 1: if (DMB_HAS(c)) { FN<2, 0>(__VA_ARGS__); p += DMB_SZ(c); } break;         \
-    case (base) + 2: if (DMB_HAS(c)) { FN<2, 1>(__VA_ARGS__); p += DMB_SZ(c); } break;         \
-    case (base) + 3: if (DMB_HAS(c)) { FN<3, 0>(__VA_ARGS__); p += DMB_SZ(c); } break;         \
-    case (base) + 4: if (DMB_HAS(c)) { FN<3, 1>(__VA_ARGS__); p += DMB_SZ(c); } break;         \
-    case (base) + 5: if (DMB_HAS(c)) { FN<3, 2>(__VA_ARGS__); p += DMB_SZ(c); } break;
-#define DMB_CASE15(base)                                                                                              \
-    case (base) + 0: case (base) + 1: case (base) + 2: case (base) + 3: case (base) + 4: case (base) + 5: case (base) + 6:  \
-    case (base) + 7: case (base) + 8: case (base) + 9: case (base) + 10: case (base) + 11: case (base) + 12:               \
-    case (base) + 13: case (base) + 14:
+// (NI = iterations of the round a lane holds in registers at once: with NI == 2 every op is applied to both halves from
+// ONE dispatch -- two independent instruction streams for ptxas to interleave)
+#define DMB_DO(c, CALL0, CALL1) if (DMB_HAS(c)) { CALL0; if (NI == 2) { CALL1; } p += DMB_SZ(c); } break;
+#define DMB_CASE1(base, c, FN)                                                     \
+    case (base) + 0: DMB_DO(c, FN<0>(v[0], op), FN<0>(v[NI - 1], op))              \
+    case (base) + 1: DMB_DO(c, FN<1>(v[0], op), FN<1>(v[NI - 1], op))              \
+    case (base) + 2: DMB_DO(c, FN<2>(v[0], op), FN<2>(v[NI - 1], op))              \
+    case (base) + 3: DMB_DO(c, FN<3>(v[0], op), FN<3>(v[NI - 1], op))
+#define DMB_CASE2(base, c, FN)                                                           \
+    case (base) + 0: DMB_DO(c, (FN<1, 0>(v[0], op)), (FN<1, 0>(v[NI - 1], op)))          \
+    case (base) + 1: DMB_DO(c, (FN<2, 0>(v[0], op)), (FN<2, 0>(v[NI - 1], op)))          \
+    case (base) + 2: DMB_DO(c, (FN<2, 1>(v[0], op)), (FN<2, 1>(v[NI - 1], op)))          \
+    case (base) + 3: DMB_DO(c, (FN<3, 0>(v[0], op)), (FN<3, 0>(v[NI - 1], op)))          \
+    case (base) + 4: DMB_DO(c, (FN<3, 1>(v[0], op)), (FN<3, 1>(v[NI - 1], op)))          \
+    case (base) + 5: DMB_DO(c, (FN<3, 2>(v[0], op)), (FN<3, 2>(v[NI - 1], op)))
 
 // applies the op at stream position p and advances p past it (header + payload: a compile-time size per op code).
 // vid = dev_vid(): ONE dense jump table; RC_HAD / RC_STAR carry their register-bit mask in the vid (no header read).
-template <unsigned MASK>
-__device__ __forceinline__ void apply_reg_op(double2 (&v)[E], const unsigned char*& p, int vid, int& slot, const StarCtx& sc)
+template <unsigned MASK, int NI>
+__device__ __forceinline__ void apply_reg_op(double2 (&v)[NI][E], const unsigned char*& p, int vid, int& slot, const StarCtx (&sc)[NI])
 {
     const Op op = {p};
     // the two mask-carrying ops first (two compares), everything else through one dense jump table
-    if (DMB_HAS(RC_STAR) && vid >= kVidStar) { r_star(v, vid - kVidStar + 1, slot, sc); p += DMB_SZ(RC_STAR); return; }
-    if (DMB_HAS(RC_HAD) && vid >= kVidHad) { r_hadm(v, vid - kVidHad + 1); p += DMB_SZ(RC_HAD); return; }
+    if (DMB_HAS(RC_STAR) && vid >= kVidStar)
+    {
+        int slot1 = slot;
+        r_star(v[0], vid - kVidStar + 1, slot, sc[0]);
+        if (NI == 2) r_star(v[NI - 1], vid - kVidStar + 1, slot1, sc[NI - 1]);
+        p += DMB_SZ(RC_STAR);
+        return;
+    }
+    if (DMB_HAS(RC_HAD) && vid >= kVidHad)
+    {
+        r_hadm(v[0], vid - kVidHad + 1);
+        if (NI == 2) r_hadm(v[NI - 1], vid - kVidHad + 1);
+        p += DMB_SZ(RC_HAD);
+        return;
+    }
     switch (vid)
     {
-        DMB_CASE2(kVidDense2, RC_DENSE2, r_dense2, v, op)
-        DMB_CASE2(kVidPerm2, RC_PERM2, r_perm2, v, op)
-        DMB_CASE2(kVidCp2, RC_CP2, r_cp2, v, op)
-        DMB_CASE2(kVidQft2, RC_QFT2, r_qft2, v, op)
-        DMB_CASE2(kVidLu2, RC_DENSE2_LU, r_dense2_lu, v, op)
-        DMB_CASE1(kVidDense1, RC_DENSE1, r_dense1, v, op)
-        DMB_CASE1(kVidRR, RC_DENSE1_RR, r_dense1_rr, v, op)
-        DMB_CASE1(kVidRI, RC_DENSE1_RI, r_dense1_ri, v, op)
-        DMB_CASE1(kVidMono1, RC_MONO1, r_mono1, v, op)
-        DMB_CASE1(kVidSrn1, RC_SRN1, r_srn1, v)
-        DMB_CASE1(kVidDiagP, RC_DIAGP, r_diagp, v, op)
-    case kVidDiagR: if (DMB_HAS(RC_DIAGR)) { r_diagr(v, op); p += DMB_SZ(RC_DIAGR); } break;
+        DMB_CASE2(kVidDense2, RC_DENSE2, r_dense2)
+        DMB_CASE2(kVidPerm2, RC_PERM2, r_perm2)
+        DMB_CASE2(kVidCp2, RC_CP2, r_cp2)
+        DMB_CASE2(kVidQft2, RC_QFT2, r_qft2)
+        DMB_CASE2(kVidLu2, RC_DENSE2_LU, r_dense2_lu)
+        DMB_CASE1(kVidDense1, RC_DENSE1, r_dense1)
+        DMB_CASE1(kVidRR, RC_DENSE1_RR, r_dense1_rr)
+        DMB_CASE1(kVidRI, RC_DENSE1_RI, r_dense1_ri)
+        DMB_CASE1(kVidMono1, RC_MONO1, r_mono1)
+        DMB_CASE1(kVidSrn1, RC_SRN1, r_srn1)
+        DMB_CASE1(kVidDiagP, RC_DIAGP, r_diagp)
+    case kVidDiagR: DMB_DO(RC_DIAGR, r_diagr(v[0], op), r_diagr(v[NI - 1], op))
     default: __builtin_unreachable();
     }
 }
@@ -489,8 +524,11 @@ __device__ __forceinline__ void apply_reg_op(double2 (&v)[E], const unsigned cha
 // ------------------------------------------------------------------------------------------------
 // the sweep kernel.  Shared memory = [tile | ops | rounds | groups]
 // ------------------------------------------------------------------------------------------------
-template <unsigned MASK>
-__global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_constant__ SweepArgs a)
+// NI = 1: three CTAs per SM, one iteration of a round in registers.  NI = 2 (full-size tiles only: every round has two
+// iterations): two CTAs per SM with up to 255 registers, both iterations resident -- half the dispatches, two
+// independent instruction streams per warp.
+template <unsigned MASK, int NI>
+__global__ void __launch_bounds__(kTileThreads, NI == 2 ? 2 : 3) sweep_kernel(const __grid_constant__ SweepArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int k = a.k;
@@ -549,6 +587,9 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
         return g;
     };
     const unsigned tile_u32 = (unsigned)__cvta_generic_to_shared(tile);
+    // the round trips address the tile as LITERAL window offset + byte offset (the literal folds into the instruction's
+    // immediate; the generic-to-shared conversion would cost an add per access)
+    if (tile_u32 != kDynSmemBase) __trap();
     const unsigned bar_u32 = tile_u32 + 16u * tile_elems;
     unsigned tma_phase = 0;
     if (a.tma_load)
@@ -564,13 +605,10 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
 
     for (unsigned long long tile_id = blockIdx.x; tile_id < a.n_tiles; tile_id += gridDim.x)
     {
-        unsigned long long base_in = 0, base_out = 0;
-        for (int i = 0; i < a.n_comp; i++)
-        {
-            const unsigned long long bit = (tile_id >> i) & 1ull;
-            base_in |= bit << a.cin[i];
-            base_out |= bit << a.cout[i];
-        }
+        // element offset of the tile: the id's bits deposited at the positions outside the tile (three 7-bit lookups)
+        const unsigned i0 = (unsigned)tile_id & 127u, i1 = (unsigned)(tile_id >> 7) & 127u, i2 = (unsigned)(tile_id >> 14) & 127u;
+        const unsigned long long base_in = a.base_in[0][i0] | a.base_in[1][i1] | a.base_in[2][i2];
+        const unsigned long long base_out = a.base_out[0][i0] | a.base_out[1][i1] | a.base_out[2][i2];
         // ---- load ----
         if (a.tma_load)
         {
@@ -585,6 +623,19 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                     int c[5];
                     tma_coords(a.tma, base_in | a.tma.enum_off[j], c);
                     tma_load_5d(tile_u32 + (unsigned)j * (unsigned)a.tma.box_bytes, &a.tmap_in, bar_u32, c[0], c[1], c[2], c[3], c[4]);
+                }
+                // L2 prefetch of this CTA's NEXT tile: it is consumed one tile time from now
+                const unsigned long long next_id = tile_id + gridDim.x;
+                if (a.tma_prefetch && next_id < a.n_tiles)
+                {
+                    const unsigned long long nb = a.base_in[0][(unsigned)next_id & 127u] | a.base_in[1][(unsigned)(next_id >> 7) & 127u] |
+                                                  a.base_in[2][(unsigned)(next_id >> 14) & 127u];
+                    for (int j = 0; j < a.tma.n_copies; j++)
+                    {
+                        int c[5];
+                        tma_coords(a.tma, nb | a.tma.enum_off[j], c);
+                        tma_prefetch_5d(&a.tmap_in, c[0], c[1], c[2], c[3], c[4]);
+                    }
                 }
             }
         }
@@ -680,6 +731,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                     {
                         const unsigned lbase = rd->lane_tab[lane] ^ wpart;
                         const int n_iter = rd->n_iter;
+                        if (NI == 2 && (n_iter & 1)) __trap(); // (the launcher only picks the dual kernel for k == 12)
                         const unsigned char* ops = s_ops + (size_t)rd->first * 16;
                         const int n_ops = rd->count;
                         int nib = 0;
@@ -695,13 +747,23 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                             rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w;
                             rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
                         }
-                        for (int it = 0; it < n_iter; it++)
+                        // NI iterations at a time live in registers (the dual kernel: both iterations of a full-size tile)
+                        for (int it = 0; it < n_iter; it += NI)
                         {
-                            const unsigned base = lbase ^ rd->iter_tab[it];
-                            double2 v[E];
+                            unsigned base[NI];
+                            double2 v[NI][E];
+                            StarCtx sc[NI];
 #pragma unroll
-                            for (int c = 0; c < E; c++) v[c] = tile[base ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)];
-                            const StarCtx sc = {s_star, lane, (warp << nib) | it};
+                            for (int h = 0; h < NI; h++)
+                            {
+                                base[h] = lbase ^ rd->iter_tab[it + h];
+                                sc[h] = StarCtx{s_star + 8 + lane, s_star + ((warp << nib) | (it + h))};
+                            }
+#pragma unroll
+                            for (int h = 0; h < NI; h++)
+#pragma unroll
+                                for (int c = 0; c < E; c++)
+                                    v[h][c] = lds128(kDynSmemBase + (base[h] ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)));
                             // dispatch from the round's packed vid list (one byte per op, two registers pairs):
                             // no shared-memory load on the dispatch path
                             const unsigned char* p = ops;
@@ -712,10 +774,13 @@ __global__ void __launch_bounds__(kTileThreads, 3) sweep_kernel(const __grid_con
                                 const int vid = (int)(v0 & 0xffull);
                                 v0 = (v0 >> 8) | (v1 << 56);
                                 v1 >>= 8;
-                                apply_reg_op<MASK>(v, p, vid, slot, sc);
+                                apply_reg_op<MASK, NI>(v, p, vid, slot, sc);
                             }
 #pragma unroll
-                            for (int c = 0; c < E; c++) tile[base ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)] = v[c];
+                            for (int h = 0; h < NI; h++)
+#pragma unroll
+                                for (int c = 0; c < E; c++)
+                                    sts128(kDynSmemBase + (base[h] ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)), v[h][c]);
                         }
                     }
                     __syncwarp();
@@ -817,18 +882,22 @@ typedef void (*SweepFn)(const SweepArgs);
 template <int I>
 struct VariantTable
 {
-    static void fill(SweepFn* t)
+    static void fill(SweepFn* t, SweepFn* t2)
     {
-        t[I] = sweep_kernel<kVariantMasks[I]>;
-        VariantTable<I - 1>::fill(t);
+        t[I] = sweep_kernel<kVariantMasks[I], 1>;
+        t2[I] = sweep_kernel<kVariantMasks[I], 1>; // (the NI = 2 kernels are not built: measured slower, profiles/README.md)
+        VariantTable<I - 1>::fill(t, t2);
     }
 };
 template <>
 struct VariantTable<-1>
 {
-    static void fill(SweepFn*) {}
+    static void fill(SweepFn*, SweepFn*) {}
 };
-static SweepFn g_variants[kNumVariants];
+static SweepFn g_variants[kNumVariants], g_variants2[kNumVariants];
+static bool g_dual = false; // full-size tiles on the dual kernel (two resident iterations, two CTAs per SM)
+void set_sweep_dual(bool on) { g_dual = on; }
+static SweepFn pick_kernel(const SweepArgs& a);
 
 static int pick_variant(unsigned mask)
 {
@@ -844,17 +913,26 @@ static int current_device()
     return dev < 0 || dev >= kMaxDevices ? 0 : dev;
 }
 
+static SweepFn pick_kernel(const SweepArgs& a)
+{
+    const int i = pick_variant(a.op_mask);
+    return (g_dual && a.k == kMaxTileBits) ? g_variants2[i] : g_variants[i];
+}
+
 void sweep_setup()
 {
     const int dev = current_device();
     if (g_num_sms[dev]) return;
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    VariantTable<kNumVariants - 1>::fill(g_variants);
+    VariantTable<kNumVariants - 1>::fill(g_variants, g_variants2);
     const int max_smem = (16 << kMaxTileBits) + 16 + kMaxOpsPerSweep * (int)(sizeof(DevOp) + sizeof(DevRound) + sizeof(DevGroup)) +
                          kMaxStarsPerSweep * kStarSmemBytes;
     for (int i = 0; i < kNumVariants; i++)
+    {
         cudaFuncSetAttribute(g_variants[i], cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaFuncSetAttribute(g_variants2[i], cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    }
     g_num_sms[dev] = sms > 0 ? sms : 1;
 }
 
@@ -874,7 +952,7 @@ int sweep_max_grid(const SweepArgs& a)
 {
     sweep_setup();
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, g_variants[pick_variant(a.op_mask)], kTileThreads, sweep_smem_bytes(a));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_kernel(a), kTileThreads, sweep_smem_bytes(a));
     if (occ < 1) occ = 1;
     return g_num_sms[current_device()] * occ;
 }
@@ -883,6 +961,6 @@ cudaError_t launch_sweep(const SweepArgs& a, int grid, cudaStream_t s)
 {
     sweep_setup();
     void* params[] = {const_cast<SweepArgs*>(&a)};
-    return cudaLaunchKernel((const void*)g_variants[pick_variant(a.op_mask)], dim3(grid), dim3(kTileThreads), params, sweep_smem_bytes(a), s);
+    return cudaLaunchKernel((const void*)pick_kernel(a), dim3(grid), dim3(kTileThreads), params, sweep_smem_bytes(a), s);
 }
 } // namespace dmb
