@@ -22,6 +22,9 @@ HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", HOST_CXX, "--expt-relaxed-constexpr"]
+# experiments: DMB_GEOM=<thread bits>,<register bits> builds another CTA geometry (csrc/devop.hpp); default 7,4
+GEOM = [f"-DDMB_THREAD_BITS={int(a)}" for a in os.environ.get("DMB_GEOM", "").split(",")[:1] if a] + \
+       [f"-DDMB_REG_BITS={int(a)}" for a in os.environ.get("DMB_GEOM", "").split(",")[1:2] if a]
 
 
 def _newer(target, sources):
@@ -54,9 +57,9 @@ def build_core(force=False, verbose=False):
         o = os.path.join(LIB, os.path.basename(s) + ".o")
         if force or _newer(o, [s] + hdrs):
             if s.endswith(".cpp"):  # pure host code: the system compiler, no CUDA front-end
-                _run([HOST_CXX, "-O2", "-std=c++17", "-fPIC", "-Wall", "-c", s, "-o", o], verbose)
+                _run([HOST_CXX, "-O2", "-std=c++17", "-fPIC", "-Wall"] + GEOM + ["-c", s, "-o", o], verbose)
             else:
-                _run([NVCC] + ARCH + NVCC_FLAGS + ["-Xptxas", "-v" if verbose else "-O3", "-c", s, "-o", o], verbose)
+                _run([NVCC] + ARCH + NVCC_FLAGS + GEOM + ["-Xptxas", "-v" if verbose else "-O3", "-c", s, "-o", o], verbose)
         objs.append(o)
     _run([NVCC] + ARCH + ["-shared", "-ccbin", HOST_CXX, "-o", out] + objs + ["-ldl"], verbose)
     return out

@@ -232,7 +232,7 @@ struct dmb_sim
     std::vector<DevStar> host_stars;
     std::vector<DevRound> host_rounds;
     std::vector<DevGroup> host_groups;
-    unsigned long long fp64_per_16 = 0; // FP64 instructions per 16 shard elements over all sweeps of the plan
+    unsigned long long fp64_per_lane = 0; // FP64 instructions per kRegElems shard elements over all sweeps of the plan
 
     // Single-process multi-GPU (reference Simulation(n_qubits, n_gpus), :196-271: one host process drives all devices):
     // a GROUP handle (rank == DMB_ALL_RANKS) owns one shard object per device and no buffers of its own.  The shards
@@ -575,7 +575,7 @@ static int plan_and_encode(dmb_sim* s)
     s->star_offset.assign(nsteps, 0);
     s->n_dev_stars.assign(nsteps, 0);
     EncodedSweep enc;
-    s->fp64_per_16 = 0;
+    s->fp64_per_lane = 0;
     for (size_t i = 0; i < nsteps; i++)
     {
         s->op_offset[i] = s->host_ops.size();
@@ -591,7 +591,7 @@ static int plan_and_encode(dmb_sim* s)
         {
             return fail(DMB_ESTATE, e.what());
         }
-        s->fp64_per_16 += enc.fp64_per_16;
+        s->fp64_per_lane += enc.fp64_per_lane;
         s->n_dev_ops[i] = (int)enc.stream.size(); // bytes
         s->n_dev_stars[i] = (int)enc.stars.size();
         s->op_masks[i] = enc.op_mask;
@@ -615,7 +615,7 @@ static void adopt_plan(dmb_sim* s, const dmb_sim* src)
     s->n_dev_groups = src->n_dev_groups; s->n_dev_stars = src->n_dev_stars; s->op_masks = src->op_masks;
     s->host_ops = src->host_ops; s->host_stars = src->host_stars; s->host_rounds = src->host_rounds;
     s->host_groups = src->host_groups;
-    s->fp64_per_16 = src->fp64_per_16;
+    s->fp64_per_lane = src->fp64_per_lane;
 }
 
 // device part: the single H2D of the step (stream-ordered; the copies are flushed before returning because the host
@@ -984,7 +984,7 @@ static int group_run(dmb_sim* grp, dmb_stats* stats)
         stats->sweep_bytes = 32ull * lead->shard_elems;
         stats->exchange_bytes = lead->plan.n_exchanges * (uint64_t)(lead->world - 1) * (lead->shard_elems / lead->world) * 16ull;
         stats->h2d_bytes = lead->h2d_bytes * grp->shards.size();
-        stats->fp64_ops = lead->fp64_per_16 * (lead->shard_elems / 16);
+        stats->fp64_ops = lead->shard_elems >= (size_t)kRegElems ? lead->fp64_per_lane * (lead->shard_elems / kRegElems) : lead->fp64_per_lane;
     }
     return DMB_OK;
 }
@@ -1091,7 +1091,7 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
         stats->sweep_bytes = 32ull * s->shard_elems;
         stats->exchange_bytes = s->plan.n_exchanges * (uint64_t)(s->world - 1) * (s->shard_elems / s->world) * 16ull;
         stats->h2d_bytes = s->h2d_bytes;
-        stats->fp64_ops = s->fp64_per_16 * (s->shard_elems / 16);
+        stats->fp64_ops = s->shard_elems >= (size_t)kRegElems ? s->fp64_per_lane * (s->shard_elems / kRegElems) : s->fp64_per_lane;
     }
     return DMB_OK;
 }

@@ -5,14 +5,30 @@
 
 namespace dmb
 {
-constexpr int kMaxTileBits = 12;  // 2^12 complex FP64 = 64 KiB of shared memory per CTA
-constexpr int kTileThreads = 128; // 4 warps; 3 CTAs per SM overlap each other's load / compute / store phases and
-                                  // leave 170 registers per thread for the 16 resident elements of a round
-constexpr int kThreadBits = 7;    // log2(kTileThreads)
-constexpr int kWarpBits = 2;      // log2(warps per CTA)
-constexpr int kRegBits = 4;       // a lane keeps 2^4 tile elements (64 registers) resident per round
+// CTA geometry (compile-time): threads per CTA and tile elements a lane keeps in registers per round.
+//   DMB_THREAD_BITS = 7, DMB_REG_BITS = 4 (default): 4 warps x 3 CTAs per SM, 16 resident elements (64 registers) per
+//     lane: the fewest shared-memory round trips and dispatches per op;
+//   DMB_THREAD_BITS = 8, DMB_REG_BITS = 3: 8 warps x 3 CTAs = 24 warps per SM (80 registers per thread), 8 resident
+//     elements per lane.  Measured on B200 (profiles/README.md, r2j): twice the warps but 60 % more instructions per
+//     sweep (more rounds, dispatches and star multiplications per element): qft_n15 31.7 ms vs 24.8 ms, random_c1c2_n15
+//     505 ms vs 378 ms.  Kept buildable (python dm-sim_b200/build.py with DMB_GEOM=8,3) and covered by the CPU emulators.
+#ifndef DMB_THREAD_BITS
+#define DMB_THREAD_BITS 7
+#endif
+#ifndef DMB_REG_BITS
+#define DMB_REG_BITS 4
+#endif
+constexpr int kMaxTileBits = 12;  // 2^12 complex FP64 = 64 KiB of shared memory per CTA; 3 CTAs per SM overlap each
+                                  // other's load / compute / store phases
+constexpr int kThreadBits = DMB_THREAD_BITS;  // log2(kTileThreads)
+constexpr int kTileThreads = 1 << kThreadBits;
+constexpr int kWarpBits = kThreadBits - 5;    // log2(warps per CTA)
+constexpr int kRegBits = DMB_REG_BITS;        // a lane keeps 2^kRegBits tile elements resident per round
 constexpr int kRegElems = 1 << kRegBits;
 constexpr int kMaxIter = 1 << (kMaxTileBits - kThreadBits); // load / store iterations per thread
+constexpr int kStarW = 16;        // (warp << iteration bits) | iteration of a round: warps per CTA x iterations <= 16
+static_assert(kRegBits == 3 || kRegBits == 4, "register rounds hold 8 or 16 elements per lane");
+static_assert((1 << kWarpBits) * (1 << (kMaxTileBits - kThreadBits - kRegBits)) <= kStarW, "star table size");
 constexpr int kMaxOpsPerSweep = 112;
 
 // XOR swizzle of the shared-memory tile (element = 16 B): the low 3 element bits (the 16-byte bank group) are
@@ -76,7 +92,7 @@ enum RegOpCode : int32_t
 constexpr int kMaxStarOut = 28;
 struct alignas(16) DevStar
 {
-    double w[16];  // 8 complex: index = (warp << iteration bits) | iteration
+    double w[2 * kStarW]; // kStarW complex: index = (warp << iteration bits) | iteration
     double la[16]; // lane part, factored so that it fits shared memory: L[lane] = la[lane & 7] * lb[lane >> 3]
     double lb[8];
     int32_t n_out;
@@ -84,9 +100,9 @@ struct alignas(16) DevStar
     int32_t bit[kMaxStarOut];    // physical bit of the full index (>= M: rank bits)
     double phi[2 * kMaxStarOut]; // (re, im)
 };
-static_assert(sizeof(DevStar) == 896, "DevStar layout");
-constexpr int kMaxStarsPerSweep = 160; // 640 bytes of shared memory each: WO[8] (rebuilt per tile) | L[32] = la x lb (once)
-constexpr int kStarSmemBytes = 640;
+static_assert(sizeof(DevStar) == 768 + 16 * kStarW, "DevStar layout");
+constexpr int kMaxStarsPerSweep = 160; // shared memory of each: WO[kStarW] (rebuilt per tile) | L[32] = la x lb (once)
+constexpr int kStarSmemBytes = 16 * (kStarW + 32);
 
 // Device op stream: 16-byte header + payload (the used part of DevOp::m), 16-byte granularity; a zero header ends it.
 struct alignas(16) DevOpHdr
@@ -131,8 +147,8 @@ constexpr int dev_op_payload_bytes(int code)
     case RC_DENSE2: return 256;
     case RC_DENSE2_LU: return 256;
     case RC_PERM2: return 64;
-    case RC_DIAGR: return 256;
-    case RC_DIAGP: return 128;
+    case RC_DIAGR: return 16 * kRegElems;
+    case RC_DIAGP: return 8 * kRegElems;
     case RC_CP2: return 16;
     case RC_QFT2: return 16;
     case RC_DENSE1_RR: return 32;

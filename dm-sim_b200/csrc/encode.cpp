@@ -602,7 +602,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
                         sd.aux |= 1 << p;
                         DevStar st;
                         memset(&st, 0, sizeof(st));
-                        for (int iw = 0; iw < 8; iw++)
+                        for (int iw = 0; iw < kStarW; iw++)
                         {
                             const unsigned itv = (unsigned)iw & ((1u << nib) - 1u), wv = (unsigned)iw >> nib;
                             const unsigned idx = deposit(itv, iterp) | deposit(wv, wpos);
@@ -728,28 +728,29 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
     fold_hadamard_scales(out.ops);
     merge_butterflies(out);
 
-    // FP64 instructions per 16 elements (one lane, one iteration) of every device op: the sweep's algorithmic FP64 work
-    out.fp64_per_16 = 0;
+    // FP64 instructions per lane and iteration (kRegElems elements) of every device op: the sweep's algorithmic FP64 work
+    out.fp64_per_lane = 0;
     for (const DevOp& d : out.ops)
     {
+        const unsigned long long E = kRegElems;
         unsigned long long c = 0;
         switch (d.code)
         {
-        case RC_DENSE1: c = 128; break;
-        case RC_DENSE1_RR: case RC_DENSE1_RI: c = 64; break;
-        case RC_HAD: c = 32ull * __builtin_popcount((unsigned)d.aux & 15u); break;
-        case RC_MONO1: c = ((d.aux >> 12) & 1) ? 0 : 64; break;
-        case RC_SRN1: c = 48; break;
-        case RC_DENSE2: case RC_DENSE2_LU: c = 256; break;
-        case RC_PERM2: c = ((d.aux >> 12) & 1) ? 0 : 64; break;
-        case RC_DIAGR: c = 4ull * (16 - __builtin_popcount((unsigned)d.aux & 0xffffu)); break;
-        case RC_DIAGP: c = 4ull * (8 - __builtin_popcount((unsigned)d.aux & 0xffu)); break;
-        case RC_CP2: c = 16; break;
-        case RC_QFT2: c = 80; break;
-        case RC_STAR: c = 36ull * __builtin_popcount((unsigned)d.aux & 15u); break;
+        case RC_DENSE1: c = 8 * E; break;
+        case RC_DENSE1_RR: case RC_DENSE1_RI: c = 4 * E; break;
+        case RC_HAD: c = 2 * E * __builtin_popcount((unsigned)d.aux & 15u); break;
+        case RC_MONO1: c = ((d.aux >> 12) & 1) ? 0 : 4 * E; break;
+        case RC_SRN1: c = 3 * E; break;
+        case RC_DENSE2: case RC_DENSE2_LU: c = 16 * E; break;
+        case RC_PERM2: c = ((d.aux >> 12) & 1) ? 0 : 4 * E; break;
+        case RC_DIAGR: c = 4ull * (E - __builtin_popcount((unsigned)d.aux & ((1u << kRegElems) - 1u))); break;
+        case RC_DIAGP: c = 4ull * (E / 2 - __builtin_popcount((unsigned)d.aux & ((1u << (kRegElems / 2)) - 1u))); break;
+        case RC_CP2: c = E; break;
+        case RC_QFT2: c = 5 * E; break;
+        case RC_STAR: c = (4 + 2 * E) * __builtin_popcount((unsigned)d.aux & 15u); break;
         default: break;
         }
-        out.fp64_per_16 += c;
+        out.fp64_per_lane += c;
     }
 
     // ---- the device op stream: 16-byte header + the used part of the payload per op, a zero header at the end ----
@@ -896,7 +897,8 @@ std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a)
         for (int i = 0; i < n; i++) o << (i ? "," : "") << (unsigned long long)v[i] / div;
         o << "]";
     };
-    o << "{\"k\":" << a.k << ",\"n_comp\":" << a.n_comp << ",\"swz\":" << a.swz_mode << ",\"tma_load\":" << a.tma_load
+    o << "{\"k\":" << a.k << ",\"n_comp\":" << a.n_comp << ",\"geom\":{\"thread_bits\":" << kThreadBits << ",\"reg_bits\":" << kRegBits
+      << ",\"warp_bits\":" << kWarpBits << ",\"star_w\":" << kStarW << "},\"swz\":" << a.swz_mode << ",\"tma_load\":" << a.tma_load
       << ",\"tma_store\":" << a.tma_store << ",";
     if (a.tma_load)
     {
@@ -961,7 +963,7 @@ std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a)
     {
         const DevStar& st = e.stars[i];
         o << (i ? "," : "") << "{\"w\":[";
-        dbl(st.w, 16);
+        dbl(st.w, 2 * kStarW);
         o << "],\"la\":[";
         dbl(st.la, 16);
         o << "],\"lb\":[";

@@ -16,7 +16,7 @@ struct EncodedSweep
     std::vector<DevGroup> groups;
     std::vector<DevStar> stars;
     unsigned op_mask = 0;               // register-op codes present
-    unsigned long long fp64_per_16 = 0; // FP64 pipe slots (DFMA / DMUL / DADD instructions) the sweep spends on every 16 elements
+    unsigned long long fp64_per_lane = 0; // FP64 pipe slots (DFMA / DMUL / DADD) per lane and iteration (kRegElems elements)
 };
 void encode_sweep(const Sweep& sw, EncodedSweep& out);
 // fills k, n_comp, n_tiles and every address table of `a` (pointers / counts are the caller's job)

@@ -278,10 +278,10 @@ template <int PH, int PL>
 __device__ __forceinline__ void r_dense2(double2 (&v)[E], Op op)
 {
     constexpr int bh = 1 << PH, bl = 1 << PL;
-    constexpr int rest = (E - 1) & ~(bh | bl);   // the two register bits the op does not touch
+    constexpr int rest = (E - 1) & ~(bh | bl);   // the register bits the op does not touch (two for E = 16, one for E = 8)
     constexpr int r0 = rest & -rest, r1 = rest & ~r0;
 #pragma unroll
-    for (int half = 0; half < 2; half++)
+    for (int half = 0; half < E / 8; half++)
     {
         const int qa = half ? r1 : 0, qb = qa | r0;
         const double2 a0 = v[qa], a1 = v[qa | bl], a2 = v[qa | bh], a3 = v[qa | bh | bl];
@@ -297,7 +297,7 @@ __device__ __forceinline__ void r_dense2(double2 (&v)[E], Op op)
     }
 }
 // 4x4 dense as L U, in place (RC_DENSE2_LU): every matrix entry is loaded once (broadcast LDS.128) and applied to the four
-// quads of the lane -- 16 loads per 256 FP64 instructions, four independent chains per entry, no temporaries
+// quads of the lane (two for 8 resident elements) -- 16 loads per op, independent chains per entry, no temporaries
 __device__ __forceinline__ void cfma_ip(double2& c, const double2 a, const double2 b) // c += a * b
 {
     c.x = fma(a.x, b.x, fma(-a.y, b.y, c.x));
@@ -318,13 +318,13 @@ __device__ __forceinline__ void r_dense2_lu(double2 (&v)[E], Op op)
     {
         const double2 d = m[at++];
 #pragma unroll
-        for (int q = 0; q < 4; q++) cmul_ip(v[DMB_QUAD(q) | DMB_ELEM(i)], d);
+        for (int q = 0; q < E / 4; q++) cmul_ip(v[DMB_QUAD(q) | DMB_ELEM(i)], d);
 #pragma unroll
         for (int j = i + 1; j < 4; j++)
         {
             const double2 e = m[at++];
 #pragma unroll
-            for (int q = 0; q < 4; q++) cfma_ip(v[DMB_QUAD(q) | DMB_ELEM(i)], e, v[DMB_QUAD(q) | DMB_ELEM(j)]);
+            for (int q = 0; q < E / 4; q++) cfma_ip(v[DMB_QUAD(q) | DMB_ELEM(i)], e, v[DMB_QUAD(q) | DMB_ELEM(j)]);
         }
     }
 #pragma unroll
@@ -334,7 +334,7 @@ __device__ __forceinline__ void r_dense2_lu(double2 (&v)[E], Op op)
         {
             const double2 e = m[10 + (i * (i - 1)) / 2 + j];
 #pragma unroll
-            for (int q = 0; q < 4; q++) cfma_ip(v[DMB_QUAD(q) | DMB_ELEM(i)], e, v[DMB_QUAD(q) | DMB_ELEM(j)]);
+            for (int q = 0; q < E / 4; q++) cfma_ip(v[DMB_QUAD(q) | DMB_ELEM(i)], e, v[DMB_QUAD(q) | DMB_ELEM(j)]);
         }
 #undef DMB_QUAD
 #undef DMB_ELEM
@@ -419,7 +419,7 @@ __device__ __forceinline__ void r_diagp(double2 (&v)[E], Op op)
 // controlled-phase star: the elements whose register bit p is set get the phase  L_p[lane] * WO_p[iw]
 struct StarCtx
 {
-    // shared, per slot 40 entries: WO[8] (rebuilt per tile) | L[32] = la x lb per lane (built once); the two pointers
+    // shared, per slot: WO[kStarW] (rebuilt per tile) | L[32] = la x lb per lane (built once); the two pointers
     // address this lane's entry of slot 0 (lane: fixed for the kernel; wo: per warp and iteration)
     const double2* lane_p;
     const double2* wo_p;
@@ -456,7 +456,8 @@ __device__ __forceinline__ void r_hadm(double2 (&v)[E], int mask)
     if (mask & 1) r_had<0>(v);
     if (mask & 2) r_had<1>(v);
     if (mask & 4) r_had<2>(v);
-    if (mask & 8) r_had<3>(v);
+    if constexpr (kRegBits > 3)
+        if (mask & 8) r_had<3>(v);
 }
 
 // MASK = the register-op codes compiled into this instantiation of the kernel (bit c <-> RegOpCode c).  ptxas keeps
@@ -464,22 +465,28 @@ __device__ __forceinline__ void r_hadm(double2 (&v)[E], int mask)
 // bodies in one kernel it copies all 64 registers before and after every op (measured: 135 moves per op).
 // vid = dev_vid(code, pos, aux) (devop.hpp): one dense jump table for op kind and register position.
 #define DMB_HAS(c) ((MASK >> (c)) & 1u)
+#if DMB_REG_BITS > 3
+#define DMB_IF4(...) __VA_ARGS__
+#else
+#define DMB_IF4(...)
+#endif
 #define DMB_SZ(c) (16 + dev_op_payload_bytes(c))
 // (NI = iterations of the round a lane holds in registers at once: with NI == 2 every op is applied to both halves from
 // ONE dispatch -- two independent instruction streams for ptxas to interleave)
 #define DMB_DO(c, CALL0, CALL1) if (DMB_HAS(c)) { CALL0; if (NI == 2) { CALL1; } p += DMB_SZ(c); } break;
+// (positions on register bit 3 exist only with 16 resident elements; the jump table keeps its numbering)
 #define DMB_CASE1(base, c, FN)                                                     \
     case (base) + 0: DMB_DO(c, FN<0>(v[0], op), FN<0>(v[NI - 1], op))              \
     case (base) + 1: DMB_DO(c, FN<1>(v[0], op), FN<1>(v[NI - 1], op))              \
     case (base) + 2: DMB_DO(c, FN<2>(v[0], op), FN<2>(v[NI - 1], op))              \
-    case (base) + 3: DMB_DO(c, FN<3>(v[0], op), FN<3>(v[NI - 1], op))
+    DMB_IF4(case (base) + 3: DMB_DO(c, FN<kRegBits - 1>(v[0], op), FN<kRegBits - 1>(v[NI - 1], op)))
 #define DMB_CASE2(base, c, FN)                                                           \
     case (base) + 0: DMB_DO(c, (FN<1, 0>(v[0], op)), (FN<1, 0>(v[NI - 1], op)))          \
     case (base) + 1: DMB_DO(c, (FN<2, 0>(v[0], op)), (FN<2, 0>(v[NI - 1], op)))          \
     case (base) + 2: DMB_DO(c, (FN<2, 1>(v[0], op)), (FN<2, 1>(v[NI - 1], op)))          \
-    case (base) + 3: DMB_DO(c, (FN<3, 0>(v[0], op)), (FN<3, 0>(v[NI - 1], op)))          \
-    case (base) + 4: DMB_DO(c, (FN<3, 1>(v[0], op)), (FN<3, 1>(v[NI - 1], op)))          \
-    case (base) + 5: DMB_DO(c, (FN<3, 2>(v[0], op)), (FN<3, 2>(v[NI - 1], op)))
+    DMB_IF4(case (base) + 3: DMB_DO(c, (FN<kRegBits - 1, 0>(v[0], op)), (FN<kRegBits - 1, 0>(v[NI - 1], op))))  \
+    DMB_IF4(case (base) + 4: DMB_DO(c, (FN<kRegBits - 1, 1>(v[0], op)), (FN<kRegBits - 1, 1>(v[NI - 1], op))))  \
+    DMB_IF4(case (base) + 5: DMB_DO(c, (FN<kRegBits - 1, kRegBits - 2>(v[0], op)), (FN<kRegBits - 1, kRegBits - 2>(v[NI - 1], op))))
 
 // applies the op at stream position p and advances p past it (header + payload: a compile-time size per op code).
 // vid = dev_vid(): ONE dense jump table; RC_HAD / RC_STAR carry their register-bit mask in the vid (no header read).
@@ -557,7 +564,7 @@ __global__ void __launch_bounds__(kTileThreads, NI == 2 ? 2 : 3) sweep_kernel(co
             for (int i = t; i < a.n_stars * 32; i += NT) // the lane part L[lane] = la[lane & 7] * lb[lane >> 3], once per CTA
             {
                 const DevStar* st = a.stars + (i >> 5);
-                s_star[(i >> 5) * kStarEntries + 8 + (i & 31)] = cmul(__ldg(reinterpret_cast<const double2*>(st->la) + (i & 7)),
+                s_star[(i >> 5) * kStarEntries + kStarW + (i & 31)] = cmul(__ldg(reinterpret_cast<const double2*>(st->la) + (i & 7)),
                                                                       __ldg(reinterpret_cast<const double2*>(st->lb) + ((i & 31) >> 3)));
             }
     }
@@ -646,13 +653,13 @@ __global__ void __launch_bounds__(kTileThreads, NI == 2 ? 2 : 3) sweep_kernel(co
             const unsigned s_in = swz((unsigned)t, mode);
             if (n_it == kMaxIter)
             {
-                // full-size tile: no per-iteration predicates.  swz(it << 7) = (it << 7) | l3(it) with a 3-bit l3, and
-                // s_in < 128: the shared address is  tile + 16 * (s_in ^ l3(it)) + (it << 11)
+                // full-size tile: no per-iteration predicates.  swz(it << kThreadBits) = (it << kThreadBits) | l3(it) with a 3-bit
+                // l3, and s_in < kTileThreads: the shared address is  tile + 16 * (s_in ^ l3(it)) + 16 * (it << kThreadBits)
 #pragma unroll
                 for (int it = 0; it < kMaxIter; it++)
                 {
-                    const unsigned l3 = mode == kSwzTma ? 0u : ((((unsigned)it << 1) ^ ((unsigned)it >> 2)) & 7u);
-                    cp_async16_u32(tile_u32 + ((s_in ^ l3) << 4) + ((unsigned)it << 11), src + a.hin[it]);
+                    const unsigned l3 = swz((unsigned)it << kThreadBits, mode) & 7u;
+                    cp_async16_u32(tile_u32 + ((s_in ^ l3) << 4) + ((unsigned)it << (kThreadBits + 4)), src + a.hin[it]);
                 }
             }
             else
@@ -676,7 +683,9 @@ __global__ void __launch_bounds__(kTileThreads, NI == 2 ? 2 : 3) sweep_kernel(co
                 const DevStar* st = a.stars + (on ? (i >> 3) : 0);
                 // (bit[] is padded with 63 and phi[] with 1 up to kMaxStarOut: every load below is independent)
                 double2 acc = make_double2(1.0, 0.0);
-                const double2 wv = on ? __ldg(reinterpret_cast<const double2*>(st->w) + (i & 7)) : acc; // (in flight with the rest)
+                double2 wv[kStarW / 8]; // (in flight with the rest)
+#pragma unroll
+                for (int q = 0; q < kStarW / 8; q++) wv[q] = on ? __ldg(reinterpret_cast<const double2*>(st->w) + (i & 7) + 8 * q) : acc;
                 if (on)
                 {
                     int bj[(kMaxStarOut + 7) / 8];
@@ -698,7 +707,9 @@ __global__ void __launch_bounds__(kTileThreads, NI == 2 ? 2 : 3) sweep_kernel(co
                     const double ox = __shfl_xor_sync(0xffffffffu, acc.x, m), oy = __shfl_xor_sync(0xffffffffu, acc.y, m);
                     acc = cmul(acc, make_double2(ox, oy));
                 }
-                if (on) s_star[(i >> 3) * kStarEntries + (i & 7)] = cmul(acc, wv);
+                if (on)
+#pragma unroll
+                    for (int q = 0; q < kStarW / 8; q++) s_star[(i >> 3) * kStarEntries + (i & 7) + 8 * q] = cmul(acc, wv[q]);
             }
         }
         if (a.tma_load)
@@ -743,9 +754,12 @@ __global__ void __launch_bounds__(kTileThreads, NI == 2 ? 2 : 3) sweep_kernel(co
                         unsigned rw[E / 2];
                         {
                             const uint4 r0 = *reinterpret_cast<const uint4*>(rd->roff);
-                            const uint4 r1 = *(reinterpret_cast<const uint4*>(rd->roff) + 1);
                             rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w;
-                            rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
+                            if constexpr (E > 8)
+                            {
+                                const uint4 r1 = *(reinterpret_cast<const uint4*>(rd->roff) + 1);
+                                rw[E / 2 - 4] = r1.x; rw[E / 2 - 3] = r1.y; rw[E / 2 - 2] = r1.z; rw[E / 2 - 1] = r1.w;
+                            }
                         }
                         // NI iterations at a time live in registers (the dual kernel: both iterations of a full-size tile)
                         for (int it = 0; it < n_iter; it += NI)
@@ -757,7 +771,7 @@ __global__ void __launch_bounds__(kTileThreads, NI == 2 ? 2 : 3) sweep_kernel(co
                             for (int h = 0; h < NI; h++)
                             {
                                 base[h] = lbase ^ rd->iter_tab[it + h];
-                                sc[h] = StarCtx{s_star + 8 + lane, s_star + ((warp << nib) | (it + h))};
+                                sc[h] = StarCtx{s_star + kStarW + lane, s_star + ((warp << nib) | (it + h))};
                             }
 #pragma unroll
                             for (int h = 0; h < NI; h++)
@@ -928,10 +942,13 @@ void sweep_setup()
     VariantTable<kNumVariants - 1>::fill(g_variants, g_variants2);
     const int max_smem = (16 << kMaxTileBits) + 16 + kMaxOpsPerSweep * (int)(sizeof(DevOp) + sizeof(DevRound) + sizeof(DevGroup)) +
                          kMaxStarsPerSweep * kStarSmemBytes;
+    int optin = 0;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int smem_limit = optin > 0 && optin < max_smem ? optin : max_smem;
     for (int i = 0; i < kNumVariants; i++)
     {
-        cudaFuncSetAttribute(g_variants[i], cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-        cudaFuncSetAttribute(g_variants2[i], cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaFuncSetAttribute(g_variants[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit);
+        cudaFuncSetAttribute(g_variants2[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit);
     }
     g_num_sms[dev] = sms > 0 ? sms : 1;
 }

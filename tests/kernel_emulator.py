@@ -11,10 +11,21 @@ from __future__ import annotations
 import numpy as np
 
 CLS_DENSE1, CLS_DIAG1, CLS_MONO1, CLS_SRN1, CLS_DENSE2, CLS_DIAG2, CLS_MONO2 = range(7)
-NT = 128
-TB = 7  # log2(NT)
-E = 16  # elements a lane keeps in registers per round (2^kRegBits)
-WB = 2  # log2(warps per CTA)
+# CTA geometry of the build (devop.hpp DMB_THREAD_BITS / DMB_REG_BITS), taken from the "geom" object of every sweep
+NT = 256
+TB = 8  # log2(NT)
+E = 8   # elements a lane keeps in registers per round (2^kRegBits)
+WB = 3  # log2(warps per CTA)
+RB = 3  # register bits
+SW = 16 # star table entries per slot: (warp << iteration bits) | iteration
+
+
+def _set_geom(dev):
+    global NT, TB, E, WB, RB, SW
+    g = dev.get("geom")
+    if g:
+        TB, RB, WB, SW = g["thread_bits"], g["reg_bits"], g["warp_bits"], g["star_w"]
+        NT, E = 1 << TB, 1 << RB
 
 
 def swz(e, mode=0):
@@ -55,6 +66,7 @@ def _dep(v, pos):
 
 def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = None, rank: int = 0) -> np.ndarray:
     """One sweep_kernel launch over a shard given in PHYSICAL order; returns the output shard."""
+    _set_geom(dev)
     k, n_comp = dev["k"], dev["n_comp"]
     tile_elems, n_tiles = 1 << k, 1 << n_comp
     assert shard_in.size == tile_elems * n_tiles
@@ -139,7 +151,7 @@ def _cplx(a):
 def _apply_star(dev, op, v, lane, iw, full):
     """RC_STAR: elements with register bit p set get L_p[lane] * WO_p[tile, iw]; WO folds the outside partner bits."""
     slot = op["star"]
-    for p in range(4):
+    for p in range(RB):
         if not (op["aux"] >> p) & 1:
             continue
         st = dev["stars"][slot]
@@ -173,7 +185,7 @@ def _apply_reg_op(op, v):
                 v[c] = m[j] * v[c]
         return
     if code == RC_HAD:  # unscaled butterflies on every register bit of the mask; the scale sits in a dense op of the sweep
-        for pb in range(4):
+        for pb in range(RB):
             if not (aux >> pb) & 1:
                 continue
             b = 1 << pb
@@ -266,6 +278,7 @@ def _apply_reg_op(op, v):
 def check_group_partition(dev: dict):
     """Every round's warps x lanes x iterations x 16 registers must cover the 2^k tile elements exactly once
     (for tiles with fewer than 2^kRegBits register bits, duplicates of the same element are allowed)."""
+    _set_geom(dev)
     k = dev["k"]
     for grp in dev["groups"]:
         for ri in range(grp["first"], grp["first"] + grp["count"]):
@@ -279,7 +292,7 @@ def check_group_partition(dev: dict):
             allidx = np.concatenate(allidx)
             uniq = np.unique(allidx)
             assert len(uniq) == 1 << k, (k, grp, rd)
-            if k - (WB if grp["n_warps"] == (1 << WB) else 0) >= 4:
+            if k - (WB if grp["n_warps"] == (1 << WB) else 0) >= RB:
                 assert allidx.size == 1 << k
 
 
