@@ -108,6 +108,8 @@ def workload(name):
         return n, circuits.random_allops(n, 60)
     if fam == "single":   # one gate = one sweep with 2 ops: the memory pipeline of the sweep kernel
         return n, [("H", [5], 0.0, 0.0, 0.0)]
+    if fam == "hstride":  # ONE sweep over a strided tile (physical bits 0-2, 6-9, 21-24 at n = 15), 8 butterflies: the
+        return n, [("H", [q], 0.0, 0.0, 0.0) for q in (6, 7, 8, 9)]  # memory pipeline with 128-byte runs 1 KiB apart
     if fam == "hlayer":   # one dense 1-qubit gate per qubit
         return n, [("H", [q], 0.0, 0.0, 0.0) for q in range(n)]
     raise SystemExit(f"unknown workload {name}")

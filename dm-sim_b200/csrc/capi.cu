@@ -62,6 +62,7 @@ static void init_options()
     if (const char* e = getenv("DMB_DENSE2_LU")) set_sweep_dense2_lu(atoi(e) != 0);
     if (const char* e = getenv("DMB_GRID_PER_SM")) g_grid_per_sm = atoi(e);
     if (const char* e = getenv("DMB_DUAL")) set_sweep_dual(atoi(e) != 0);
+    if (const char* e = getenv("DMB_DIRECT_STORE")) set_sweep_direct_store(atoi(e) != 0);
     if (const char* e = getenv("DMB_TMA_PREFETCH")) g_tma_prefetch = atoi(e);
 }
 
@@ -205,6 +206,7 @@ struct dmb_sim
     std::vector<size_t> round_offset, group_offset; // per step: first DevRound / DevGroup
     std::vector<int> n_dev_ops, n_dev_rounds, n_dev_groups;
     std::vector<unsigned> op_masks;   // per step: register-op codes present (kernel instantiation)
+    std::vector<DevDirect> directs;   // per step: direct store of the last round
     DevRound* d_rounds = nullptr;
     DevGroup* d_groups = nullptr;
     size_t d_rounds_cap = 0, d_groups_cap = 0;
@@ -389,6 +391,7 @@ int dmb_set_option(const char* name, int64_t value)
     else if (!strcmp(name, "tma_box_bits")) set_sweep_tma_box_bits((int)value);
     else if (!strcmp(name, "dense2_lu")) set_sweep_dense2_lu(value != 0);
     else if (!strcmp(name, "tma_prefetch")) g_tma_prefetch = (int)value;
+    else if (!strcmp(name, "direct_store")) set_sweep_direct_store(value != 0);
     else return fail(DMB_EINVAL, std::string("unknown option ") + name);
     return DMB_OK;
 }
@@ -572,6 +575,7 @@ static int plan_and_encode(dmb_sim* s)
     s->n_dev_rounds.assign(nsteps, 0);
     s->n_dev_groups.assign(nsteps, 0);
     s->op_masks.assign(nsteps, 0u);
+    s->directs.assign(nsteps, DevDirect{});
     s->star_offset.assign(nsteps, 0);
     s->n_dev_stars.assign(nsteps, 0);
     EncodedSweep enc;
@@ -595,6 +599,7 @@ static int plan_and_encode(dmb_sim* s)
         s->n_dev_ops[i] = (int)enc.stream.size(); // bytes
         s->n_dev_stars[i] = (int)enc.stars.size();
         s->op_masks[i] = enc.op_mask;
+        s->directs[i] = enc.direct;
         s->host_stars.insert(s->host_stars.end(), enc.stars.begin(), enc.stars.end());
         s->n_dev_rounds[i] = (int)enc.rounds.size();
         s->n_dev_groups[i] = (int)enc.groups.size();
@@ -613,6 +618,7 @@ static void adopt_plan(dmb_sim* s, const dmb_sim* src)
     s->op_offset = src->op_offset; s->round_offset = src->round_offset; s->group_offset = src->group_offset;
     s->star_offset = src->star_offset; s->n_dev_ops = src->n_dev_ops; s->n_dev_rounds = src->n_dev_rounds;
     s->n_dev_groups = src->n_dev_groups; s->n_dev_stars = src->n_dev_stars; s->op_masks = src->op_masks;
+    s->directs = src->directs;
     s->host_ops = src->host_ops; s->host_stars = src->host_stars; s->host_rounds = src->host_rounds;
     s->host_groups = src->host_groups;
     s->fp64_per_lane = src->fp64_per_lane;
@@ -728,6 +734,10 @@ static int fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, dou
     a.tma_prefetch = g_tma_prefetch;
     if (a.n_comp > 21) return fail(DMB_EINVAL, "shard too large for the tile-base tables");
     fill_base_tables(a);
+    // direct store of the last round: in-place TMA tiles over the whole shard (not the reduced enumeration of a sparse start)
+    a.direct = s->directs[step];
+    if (!a.tma_load || !a.tma_store || in != out || a.n_comp != s->M - a.k) a.direct.enabled = 0;
+    if (a.direct.enabled) a.tma_store = 0;
     if (a.tma_load)
     {
         std::string why;

@@ -218,6 +218,24 @@ struct alignas(64) TmaDesc // CUtensorMap (opaque, 128 bytes, filled by cuTensor
     unsigned long long opaque[16];
 };
 
+// Direct store of the LAST round (full-size TMA-loaded tiles that do not permute bits): the lanes write the round's results
+// straight from registers to global memory (streaming 128-bit stores; lane bits 0..2 are the tile's 128-byte run, so every
+// quarter warp writes one full line) instead of going back through shared memory and a TMA store.  The tile buffer is
+// dead as soon as every warp has LOADED its last-round elements: the next tile's TMA load is issued then (per half when
+// the round's iteration bit is one of the TMA copy-enumeration bits), so that it lands while the last round computes
+// and nobody waits for a store to drain.
+struct DevDirect
+{
+    int32_t enabled;
+    int32_t half_enum;            // the round's iteration bit is enumeration bit `half_enum` of the TMA copies (-1: it is not)
+    unsigned char reg_pos[4];     // physical bit of register bit i of the last round
+    unsigned char lane_pos[5];    // ... of lane bit i
+    unsigned char warp_pos[3];    // ... of warp bit i
+    unsigned char iter_pos[4];    // ... of iteration bit i
+    unsigned long long reg_off[16]; // BYTE offset of register element c (its register bits deposited at reg_pos[])
+    unsigned long long iter_off[8]; // ELEMENT offset of iteration it (its bits deposited at iter_pos[])
+};
+
 // Kernel parameter block of one sweep (by value -> constant bank; the per-iteration tables become immediate
 // constant operands of the unrolled load / store loops).
 struct SweepArgs
@@ -254,6 +272,7 @@ struct SweepArgs
     // tile id -> element offset of the tile (the deposit of the id's bits at cin[] / cout[]), as three 7-bit lookups:
     // base = base_in[0][id & 127] | base_in[1][(id >> 7) & 127] | base_in[2][id >> 14]
     unsigned long long base_in[3][128], base_out[3][128];
+    DevDirect direct;
     TmaGeom tma;
     TmaDesc tmap_in, tmap_out;
 };

@@ -11,6 +11,8 @@
 namespace dmb
 {
 static int g_tma_box_bits = 10;
+static bool g_direct_store = true;
+void set_sweep_direct_store(bool on) { g_direct_store = on; }
 static bool g_dense2_lu = true;
 void set_sweep_dense2_lu(bool on) { g_dense2_lu = on; }
 bool sweep_dense2_lu() { return g_dense2_lu; }
@@ -174,6 +176,29 @@ DevOp make_reg_op(const TileOp& t, int p0, int p1)
     return d;
 }
 } // namespace
+
+// number of tile bits inside one TMA box (the rest is enumerated by separate copies) and the box's dimensions: runs of
+// consecutive physical bits, dimension 0 = the 128-byte run, <= 8 bits per dimension, <= 5 dimensions, <= tma_box_bits bits
+static int tma_box_layout(const Sweep& sw, int start[5], int len[5], int& nd)
+{
+    nd = 0;
+    int nbox = 0;
+    for (int d = 0; d < 5; d++) start[d] = len[d] = 0;
+    for (int i = 0; i < sw.k && nbox < sweep_tma_box_bits(); i++)
+    {
+        const int p = sw.in_pos[i];
+        const bool extend = nd > 0 && p == start[nd - 1] + len[nd - 1] && len[nd - 1] < (nd == 1 ? 3 : 8);
+        if (!extend)
+        {
+            if (nd == 5) break;
+            start[nd] = p;
+            len[nd++] = 0;
+        }
+        len[nd - 1]++;
+        nbox++;
+    }
+    return nbox;
+}
 
 namespace
 {
@@ -425,6 +450,7 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
     out.groups.clear();
     out.stars.clear();
     out.op_mask = 0;
+    memset(&out.direct, 0, sizeof(out.direct));
     const int k = sw.k;
     const int mode = sw.swz_mode;
     const int nwb = k >= kWarpBits + kRegBits ? kWarpBits : 0;
@@ -453,8 +479,12 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
         g.first = (int32_t)out.rounds.size();
         g.n_warps = 1 << nwb;
         std::vector<int> wpos; // the highest untouched bits carry the warp index
+        // (last group of a TMA tile: the top tile bit is left to the iteration index when other high bits are free -- the
+        // two halves of the tile buffer are then reloaded one after the other during the last round, see DevDirect)
+        const bool spare_top = mode == kSwzTma && end == nr && k == kMaxTileBits && g_direct_store &&
+                               __builtin_popcount(~used & high_mask & ~(1u << (k - 1))) >= nwb;
         for (int p = k - 1; p >= 0 && (int)wpos.size() < nwb; p--)
-            if (!((used >> p) & 1u)) wpos.push_back(p);
+            if (!((used >> p) & 1u) && !(spare_top && p == k - 1)) wpos.push_back(p);
         std::sort(wpos.begin(), wpos.end());
         unsigned wmask = 0;
         for (int p : wpos) wmask |= 1u << p;
@@ -467,9 +497,13 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
             for (int p = 0; p < k; p++)
                 if ((rp.touched >> p) & 1u) rb.push_back(p);
             // pad the register bits with free tile bits (lowest first; kSwzTma: highest first, the low ones are lane bits)
+            // (last round of a TMA tile: the top tile bit is not used as padding, it becomes the iteration bit -- DevDirect)
+            const bool keep_top = mode == kSwzTma && ri + 1 == nr && k == kMaxTileBits && g_direct_store && !((wmask >> (k - 1)) & 1u) &&
+                                  k - nwb - (int)rb.size() > R - (int)rb.size();
             for (int q = 0; q < k && (int)rb.size() < R; q++)
             {
                 const int p = mode == kSwzTma ? k - 1 - q : q;
+                if (keep_top && p == k - 1) continue;
                 if (!((wmask >> p) & 1u) && std::find(rb.begin(), rb.end(), p) == rb.end()) rb.push_back(p);
             }
             std::sort(rb.begin(), rb.end());
@@ -509,6 +543,32 @@ void encode_sweep(const Sweep& sw, EncodedSweep& out)
             for (int it = 0; it < 8; it++)
                 rd.iter_tab[it] = (uint16_t)(16u * swz_host(deposit((unsigned)it & ((unsigned)rd.n_iter - 1u), iterp), mode));
             out.rounds.push_back(rd);
+            if (ri + 1 == nr)
+            {
+                // direct store of the sweep's last round: full-size in-place TMA tile whose lane bits 0..2 are the 128-byte run
+                DevDirect& dd = out.direct;
+                memset(&dd, 0, sizeof(dd));
+                const bool run = nl == 5 && sw.out_pos[lanep[0]] < 3 && sw.out_pos[lanep[1]] < 3 && sw.out_pos[lanep[2]] < 3;
+                if (g_direct_store && mode == kSwzTma && k == kMaxTileBits && nwb == kWarpBits && R == kRegBits && sw.in_pos == sw.out_pos &&
+                    !sw.out_of_place && run && (int)iterp.size() <= 3)
+                {
+                    dd.enabled = 1;
+                    for (int i = 0; i < R; i++) dd.reg_pos[i] = (unsigned char)sw.out_pos[rb[i]];
+                    for (int i = 0; i < nl; i++) dd.lane_pos[i] = (unsigned char)sw.out_pos[lanep[i]];
+                    for (int i = 0; i < nwb; i++) dd.warp_pos[i] = (unsigned char)sw.out_pos[wpos[i]];
+                    for (size_t i = 0; i < iterp.size(); i++) dd.iter_pos[i] = (unsigned char)sw.out_pos[iterp[i]];
+                    for (int c = 0; c < kRegElems; c++)
+                        for (int i = 0; i < R; i++)
+                            if ((c >> i) & 1) dd.reg_off[c] |= 16ull << dd.reg_pos[i];
+                    for (int it = 0; it < 8; it++)
+                        for (size_t i = 0; i < iterp.size(); i++)
+                            if ((it >> i) & 1) dd.iter_off[it] |= 1ull << dd.iter_pos[i];
+                    dd.half_enum = -1;
+                    int bs[5], bl[5], bnd;
+                    const int nbox = tma_box_layout(sw, bs, bl, bnd); // tile bits [nbox, k) are enumerated by the TMA copies
+                    if (iterp.size() == 1 && iterp[0] >= nbox) dd.half_enum = iterp[0] - nbox;
+                }
+            }
 
             auto reg_pos = [&](int j) { // position of tile bit j among the round's register bits, -1 if none
                 const auto it = std::find(rb.begin(), rb.end(), j);
@@ -828,21 +888,9 @@ void fill_sweep_tables(const Sweep& sw, int M, SweepArgs& a)
         // the box: the lowest tile bits, as runs of consecutive physical bits (dimension 0 = the 128-byte run, <= 8 bits
         // per dimension, <= 5 dimensions, <= tma_box_bits bits); every other tile bit is enumerated by separate copies
         TmaGeom& t = a.tma;
-        int nd = 0, nbox = 0;
-        int len[5] = {0, 0, 0, 0, 0};
-        for (int i = 0; i < k && nbox < sweep_tma_box_bits(); i++)
-        {
-            const int p = sw.in_pos[i];
-            const bool extend = nd > 0 && p == t.start[nd - 1] + len[nd - 1] && len[nd - 1] < (nd == 1 ? 3 : 8);
-            if (!extend)
-            {
-                if (nd == 5) break;
-                t.start[nd] = (unsigned char)p;
-                len[nd++] = 0;
-            }
-            len[nd - 1]++;
-            nbox++;
-        }
+        int nd = 0, start[5], len[5];
+        const int nbox = tma_box_layout(sw, start, len, nd);
+        for (int d = 0; d < nd; d++) t.start[d] = (unsigned char)start[d];
         for (int d = 0; d < 5; d++)
         {
             if (d >= nd) t.start[d] = (unsigned char)M; // unit dimensions pad the rank to 5
@@ -919,6 +967,15 @@ std::string encoded_to_json(const EncodedSweep& e, const SweepArgs& a)
     arr("sout", a.sout, 12); o << ",";
     arr("cin", a.cin, a.n_comp); o << ",";
     arr("cout", a.cout, a.n_comp);
+    if (e.direct.enabled)
+    {
+        o << ",\"direct\":{\"half_enum\":" << e.direct.half_enum << ",";
+        arr("reg_pos", e.direct.reg_pos, kRegBits); o << ",";
+        arr("lane_pos", e.direct.lane_pos, 5); o << ",";
+        arr("warp_pos", e.direct.warp_pos, kWarpBits); o << ",";
+        arr("iter_pos", e.direct.iter_pos, 1);
+        o << "}";
+    }
     o << ",\"groups\":[";
     for (size_t g = 0; g < e.groups.size(); g++)
     {

@@ -15,6 +15,7 @@ struct EncodedSweep
     std::vector<DevRound> rounds;       // first = offset into `stream` in 16-byte units
     std::vector<DevGroup> groups;
     std::vector<DevStar> stars;
+    DevDirect direct;                   // direct store of the last round (enabled = 0: not applicable)
     unsigned op_mask = 0;               // register-op codes present
     unsigned long long fp64_per_lane = 0; // FP64 pipe slots (DFMA / DMUL / DADD) per lane and iteration (kRegElems elements)
 };
@@ -24,6 +25,8 @@ void fill_sweep_tables(const Sweep& sw, int M, SweepArgs& a);
 // largest TMA box in tile bits (2^bits elements of 16 bytes; default 10 = 16 KiB)
 void set_sweep_tma_box_bits(int bits);
 int sweep_tma_box_bits();
+// last round of full-size in-place TMA tiles stores straight from registers to global memory (default on)
+void set_sweep_direct_store(bool on);
 // dense 4x4 ops as in-place L U (RC_DENSE2_LU) where the factors stay small (default on)
 void set_sweep_dense2_lu(bool on);
 bool sweep_dense2_lu();

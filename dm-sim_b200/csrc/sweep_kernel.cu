@@ -599,6 +599,16 @@ __global__ void __launch_bounds__(kTileThreads, NI == 2 ? 2 : 3) sweep_kernel(co
     if (tile_u32 != kDynSmemBase) __trap();
     const unsigned bar_u32 = tile_u32 + 16u * tile_elems;
     unsigned tma_phase = 0;
+    const bool direct = a.direct.enabled != 0;
+    // direct store: this lane's part of the global element index of the last round's elements (lane and warp bits)
+    unsigned long long d_lane = 0;
+    if (direct)
+    {
+#pragma unroll
+        for (int i = 0; i < 5; i++) d_lane |= (unsigned long long)((lane >> i) & 1) << a.direct.lane_pos[i];
+#pragma unroll
+        for (int i = 0; i < kWarpBits; i++) d_lane |= (unsigned long long)((warp >> i) & 1) << a.direct.warp_pos[i];
+    }
     if (a.tma_load)
     {
         if (tile_u32 & 1023u) __trap(); // the hardware swizzle pattern is a function of the shared-memory ADDRESS
@@ -621,7 +631,8 @@ __global__ void __launch_bounds__(kTileThreads, NI == 2 ? 2 : 3) sweep_kernel(co
         {
             // TMA: one thread issues the tile's boxes (128-byte rows, hardware 128-byte swizzle); everybody waits on the
             // mbarrier after the star prologue below
-            if (t == 0)
+            // (direct store of the last round: every tile but the CTA's first was requested during the previous tile's last round)
+            if (t == 0 && (!direct || tile_id == blockIdx.x))
             {
                 if (a.tma_store) tma_store_wait_read(); // the previous tile has left the buffer (nobody else waits for it)
                 mbar_expect_tx(bar_u32, 16u * tile_elems);
@@ -778,6 +789,28 @@ __global__ void __launch_bounds__(kTileThreads, NI == 2 ? 2 : 3) sweep_kernel(co
 #pragma unroll
                                 for (int c = 0; c < E; c++)
                                     v[h][c] = lds128(kDynSmemBase + (base[h] ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)));
+                            const bool last_round = direct && ri + 1 == a.n_rounds;
+                            if (last_round)
+                            {
+                                // every warp has its elements of this iteration in registers: their half of the tile buffer
+                                // (the whole buffer after the last iteration) is dead -- request the CTA's next tile into it
+                                __syncthreads();
+                                const unsigned long long next_id = tile_id + gridDim.x;
+                                if (t == 0 && next_id < a.n_tiles)
+                                {
+                                    const unsigned long long nb = a.base_in[0][(unsigned)next_id & 127u] | a.base_in[1][(unsigned)(next_id >> 7) & 127u] |
+                                                                  a.base_in[2][(unsigned)(next_id >> 14) & 127u];
+                                    const int he = a.direct.half_enum;
+                                    if (it == 0) mbar_expect_tx(bar_u32, 16u * tile_elems);
+                                    for (int j = 0; j < a.tma.n_copies; j++)
+                                    {
+                                        if (he >= 0 ? ((j >> he) & 1) != it : it + NI != n_iter) continue;
+                                        int c[5];
+                                        tma_coords(a.tma, nb | a.tma.enum_off[j], c);
+                                        tma_load_5d(tile_u32 + (unsigned)j * (unsigned)a.tma.box_bytes, &a.tmap_in, bar_u32, c[0], c[1], c[2], c[3], c[4]);
+                                    }
+                                }
+                            }
                             // dispatch from the round's packed vid list (one byte per op, two registers pairs):
                             // no shared-memory load on the dispatch path
                             const unsigned char* p = ops;
@@ -790,11 +823,24 @@ __global__ void __launch_bounds__(kTileThreads, NI == 2 ? 2 : 3) sweep_kernel(co
                                 v1 >>= 8;
                                 apply_reg_op<MASK, NI>(v, p, vid, slot, sc);
                             }
-#pragma unroll
-                            for (int h = 0; h < NI; h++)
+                            if (last_round)
+                            {
+                                // streaming 128-bit stores straight to the state: quarter warps write whole 128-byte lines
+                                const unsigned long long e0 = base_out | d_lane | a.direct.iter_off[it];
+                                const char* const dst = reinterpret_cast<const char*>(gout + e0);
+                                // (the register bits' byte offsets come from the constant bank)
 #pragma unroll
                                 for (int c = 0; c < E; c++)
-                                    sts128(kDynSmemBase + (base[h] ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)), v[h][c]);
+                                    st_stream(reinterpret_cast<double2*>(const_cast<char*>(dst) + a.direct.reg_off[c]), v[0][c]);
+                            }
+                            else
+                            {
+#pragma unroll
+                                for (int h = 0; h < NI; h++)
+#pragma unroll
+                                    for (int c = 0; c < E; c++)
+                                        sts128(kDynSmemBase + (base[h] ^ ((rw[c >> 1] >> ((c & 1) * 16)) & 0xffffu)), v[h][c]);
+                            }
                         }
                     }
                     __syncwarp();
@@ -806,6 +852,7 @@ __global__ void __launch_bounds__(kTileThreads, NI == 2 ? 2 : 3) sweep_kernel(co
         }
 
         // ---- store ----
+        if (direct) continue; // (the last round stored its results itself)
         if (a.tma_store)
         {
             // TMA: one thread issues the boxes.  Nobody waits here: thread 0 waits for the boxes to be READ out of

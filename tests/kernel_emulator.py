@@ -94,13 +94,19 @@ def run_sweep(dev: dict, shard_in: np.ndarray, shard_out: np.ndarray | None = No
     assert not np.isnan(tiles.real).any(), "load did not fill the tile"
 
     full = base_in | (rank << (k + n_comp))  # the full physical index of the tile's first element (rank bits on top)
+    direct = dev.get("direct")
+    seen = np.zeros(shard_in.size, dtype=bool)
+    n_rounds = len(dev["rounds"])
     for grp in dev["groups"]:
         for w in range(grp["n_warps"]):
             wpart = grp["wtab"][w]
             for ri in range(grp["first"], grp["first"] + grp["count"]):
-                _run_round(dev, dev["rounds"][ri], tiles, wpart, w, full)
+                store = (direct, out, base_out, seen) if direct and ri == n_rounds - 1 else None
+                _run_round(dev, dev["rounds"][ri], tiles, wpart, w, full, store)
+    if direct:  # the last round wrote its results straight to the shard (DevDirect)
+        assert seen.all(), "direct store did not cover the shard"
+        return out
 
-    seen = np.zeros(shard_in.size, dtype=bool)
     for it in range(n_it):
         dst = (base_out[:, None] | g_out_lo[None, act]) + int(dev["hout"][it])
         assert not seen[dst].any()
@@ -122,7 +128,7 @@ def _round_items(rd, wpart):
     return ((lane[:, None] ^ wpart) ^ itab[None, :]).reshape(-1)
 
 
-def _run_round(dev, rd, tiles, wpart, warp, full):
+def _run_round(dev, rd, tiles, wpart, warp, full, store=None):
     """One register round of one warp: load 16 elements per work item, apply the round's ops, store back."""
     base = _round_items(rd, wpart)
     roff = [int(x) for x in rd["roff"]]
@@ -139,6 +145,18 @@ def _run_round(dev, rd, tiles, wpart, warp, full):
             _apply_star(dev, op, v, lane, iw, full)
         else:
             _apply_reg_op(op, v)
+    if store is not None:
+        # direct store: global element = tile base | lane bits | warp bits | iteration bits | register bits, each at the
+        # physical position the encoder recorded for the last round
+        direct, out, base_out, seen = store
+        g = _dep(lane, direct["lane_pos"]) | _dep(np.full_like(lane, warp), direct["warp_pos"]) | \
+            _dep(np.tile(np.arange(n_iter), rd["n_active"]), direct["iter_pos"])
+        for c in range(E):
+            dst = base_out[:, None] | (g | int(_dep(np.array([c]), direct["reg_pos"])[0]))[None, :]
+            assert not seen[dst].any()
+            seen[dst] = True
+            out[dst] = v[c]
+        return
     for c in range(E):  # duplicates (tiny tiles) carry identical values
         tiles[:, idx[c]] = v[c]
 
