@@ -92,6 +92,9 @@ def lib():
     L.dmb_plan_json.argtypes = [i32, i32, vp, sz, vp, sz, vp, i32, ctypes.c_char_p, sz]
     L.dmb_plan_json.restype = ctypes.c_int64
     L.dmb_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
+    L.dmb_jit_source.argtypes = [i32, i32, vp, sz, vp, sz, i32, i32, ctypes.c_char_p, sz]
+    L.dmb_jit_source.restype = ctypes.c_int64
+    L.dmb_query.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]
     L.dmb_last_error.restype = ctypes.c_char_p
     L.dmb_version.restype = ctypes.c_char_p
     _lib = L
@@ -105,6 +108,13 @@ def _check(rc):
 
 def set_option(name: str, value: int):
     _check(lib().dmb_set_option(name.encode(), int(value)))
+
+
+def query(name: str, handle=None) -> float:
+    """Counters of the run-time compiler ("jit_compiled", "jit_compile_ms", ...; with a handle: "jit_sweeps", "jit_pending")."""
+    v = ctypes.c_double(0)
+    _check(lib().dmb_query(handle, name.encode(), ctypes.byref(v)))
+    return v.value
 
 
 class Gate:
@@ -169,6 +179,24 @@ def plan_json(n_qubits, world_size, gates, start_layout=None, conj_state=False, 
     buf = ctypes.create_string_buffer(int(need))
     _check(min(0, int(L.dmb_plan_json(*args, buf, int(need)))))
     return json.loads(buf.value.decode())
+
+
+def jit_source(n_qubits, world_size, gates, sweep_index, peer=False):
+    """(defines, program): the CUDA text of the run-time specialised kernel of one sweep of the plan (host only), or None
+    when there is no such sweep / the generator does not cover it."""
+    rec, mats = gates if isinstance(gates, tuple) else pack_gates(gates)
+    L = lib()
+    args = (n_qubits, world_size, rec.ctypes.data, len(rec), mats.ctypes.data if mats.size else None, mats.size // 32,
+            int(sweep_index), int(bool(peer)))
+    need = L.dmb_jit_source(*args, None, 0)
+    if need < 0:
+        _check(int(need))
+    if need == 0:
+        return None
+    buf = ctypes.create_string_buffer(int(need))
+    _check(min(0, int(L.dmb_jit_source(*args, buf, int(need)))))
+    defines, program = buf.value.decode().split("//---- program\n", 1)
+    return defines, program
 
 
 class Simulation:

@@ -14,10 +14,12 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/dmsim_b200.h"
 #include "encode.hpp"
+#include "jit.hpp"
 #include "kernels.cuh"
 #include "plan.hpp"
 
@@ -43,6 +45,13 @@ static int fail(int code, const std::string& msg)
 
 static PlanOptions g_opt;
 static int g_use_graph = 1;
+static int g_plan_cache = 1;    // reuse the plan (and the device tables) of a circuit that is set again (DMB_PLAN_CACHE=0 / option "plan_cache")
+static int g_persistent = 1;    // small states: all sweeps of a run in one cooperative launch (DMB_PERSISTENT=0 / option "persistent")
+// run-time specialised sweep kernels (jit.cu): 0 off, 1 tiered (the interpreter kernel runs a sweep until its compiled kernel
+// is ready), 2 wait for the compiler (DMB_JIT / option "jit"); only for shards of >= 2^jit_min_bits elements (sweeps of
+// smaller states take microseconds; DMB_JIT_MIN_BITS / option "jit_min_bits")
+static int g_jit = 1;
+static int g_jit_min_bits = 24;
 static int g_tma_prefetch = 0;  // L2 prefetch of a CTA's next tile (DMB_TMA_PREFETCH=0 / option "tma_prefetch")
 static int g_grid_per_sm = 0;   // experiments: resident CTAs per SM of the sweep kernel (0 = what the occupancy query says)
 static int g_sparse_start = 1; // skip the tiles that are still all-zero after dmb_reset_dm (DMB_SPARSE=0 / option "sparse")
@@ -62,6 +71,11 @@ static void init_options()
     if (const char* e = getenv("DMB_DENSE2_LU")) set_sweep_dense2_lu(atoi(e) != 0);
     if (const char* e = getenv("DMB_GRID_PER_SM")) g_grid_per_sm = atoi(e);
     if (const char* e = getenv("DMB_DUAL")) set_sweep_dual(atoi(e) != 0);
+    if (const char* e = getenv("DMB_SMALL_STATE_BITS")) g_opt.small_state_bits = atoi(e);
+    if (const char* e = getenv("DMB_PERSISTENT")) g_persistent = atoi(e);
+    if (const char* e = getenv("DMB_JIT")) g_jit = atoi(e);
+    if (const char* e = getenv("DMB_JIT_MIN_BITS")) g_jit_min_bits = atoi(e);
+    if (const char* e = getenv("DMB_PLAN_CACHE")) g_plan_cache = atoi(e);
     if (const char* e = getenv("DMB_DIRECT_STORE")) set_sweep_direct_store(atoi(e) != 0);
     if (const char* e = getenv("DMB_TMA_PREFETCH")) g_tma_prefetch = atoi(e);
 }
@@ -212,6 +226,14 @@ struct dmb_sim
     size_t d_rounds_cap = 0, d_groups_cap = 0;
     cudaGraphExec_t graph_exec = nullptr;
     int graph_cur = -1;
+    // small states: the parameter blocks of all sweeps of the run, for the one-launch cooperative executor
+    SweepArgs* d_multi = nullptr;
+    size_t d_multi_cap = 0;
+    bool multi_valid = false;
+    int multi_cur = -1, multi_end_cur = 0, multi_n = 0;
+    unsigned long long multi_support = ~0ull, multi_max_tiles = 1;
+    unsigned multi_mask = 0;
+    size_t multi_smem = 0;
     // Sparse start: every element whose shard index has a 1 in a physical bit OUTSIDE `support` is exactly zero (after
     // dmb_reset_dm only element 0 is non-zero: support = 0).  A sweep maps each tile onto itself, so tiles with such a
     // bit set stay zero and are not launched at all; the sweep adds its tile bits to the support.  Single GPU only.
@@ -235,6 +257,38 @@ struct dmb_sim
     std::vector<DevRound> host_rounds;
     std::vector<DevGroup> host_groups;
     unsigned long long fp64_per_lane = 0; // FP64 instructions per kRegElems shard elements over all sweeps of the plan
+
+    // run-time specialised kernels of the current plan's sweeps: (step << 4 | I/O variant) -> cache entry (nullptr: the
+    // generator does not cover the sweep); jit_mode: 0 resolve and launch, 1 dry pass that only queues the compilations,
+    // 2 dry pass that resolves (waits / loads) without launching, 3 launching inside a stream capture (nothing may be loaded)
+    std::unordered_map<unsigned long long, JitKernel*> jit_memo;
+    int jit_mode = 0;
+    unsigned jit_missing = 0, jit_used = 0;      // sweeps of the last enqueue that ran interpreted because their kernel was not ready / specialised
+    unsigned graph_jit_missing = 0;              // ... of the captured graph
+    unsigned long long graph_jit_epoch = 0;      // jit_ready_count() when the graph was captured
+
+    // plan cache: the host pipeline (expand / fuse / schedule / encode) is skipped when the same circuit is set again on
+    // the same layout (repeated dmb_set_circuit of one circuit, runs that alternate between a few circuits); when the
+    // device still holds that plan's tables the upload and the captured graph survive as well
+    struct CachedPlan
+    {
+        unsigned long long key[2] = {0, 0};
+        Plan plan;
+        std::vector<int> plan_layout;
+        bool plan_conj = false, plan_nonherm = false;
+        std::vector<size_t> op_offset, star_offset, round_offset, group_offset;
+        std::vector<int> n_dev_stars, n_dev_ops, n_dev_rounds, n_dev_groups;
+        std::vector<unsigned> op_masks;
+        std::vector<DevDirect> directs;
+        std::vector<unsigned char> host_ops;
+        std::vector<DevStar> host_stars;
+        std::vector<DevRound> host_rounds;
+        std::vector<DevGroup> host_groups;
+        unsigned long long fp64_per_lane = 0;
+    };
+    std::vector<CachedPlan> plan_cache; // most recently used first, at most kPlanCacheEntries
+    unsigned long long device_key[2] = {0, 0}; // key of the plan whose tables are on the device (0, 0: none)
+    unsigned long long plan_key[2] = {0, 0};   // key of the current plan
 
     // Single-process multi-GPU (reference Simulation(n_qubits, n_gpus), :196-271: one host process drives all devices):
     // a GROUP handle (rank == DMB_ALL_RANKS) owns one shard object per device and no buffers of its own.  The shards
@@ -276,6 +330,7 @@ static void drop_graph(dmb_sim* s)
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     s->graph_exec = nullptr;
     s->graph_cur = -1;
+    s->multi_valid = false;
 }
 
 
@@ -283,6 +338,30 @@ static void drop_graph(dmb_sim* s)
 // helpers shared by the single-shard and the group forms
 // ------------------------------------------------------------------------------------------------
 static bool is_group(const dmb_sim* s) { return !s->shards.empty(); }
+
+constexpr size_t kPlanCacheEntries = 4;
+static unsigned long long g_option_epoch = 1; // bumped by dmb_set_option: plans made under other options are not reused
+static void fnv(unsigned long long (&h)[2], const void* data, size_t bytes)
+{
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < bytes; i++)
+    {
+        h[0] = (h[0] ^ p[i]) * 1099511628211ull;
+        h[1] = (h[1] + p[i] + 0x9e3779b97f4a7c15ull) * 0xff51afd7ed558ccdull;
+        h[1] ^= h[1] >> 29;
+    }
+}
+static void plan_key_of(const dmb_sim* s, unsigned long long (&h)[2])
+{
+    h[0] = 1469598103934665603ull; h[1] = 0x2545f4914f6cdd1dull;
+    const unsigned long long hdr[6] = {(unsigned long long)s->n, (unsigned long long)s->world, s->gates.size(), s->mats.size(),
+                                       (unsigned long long)(s->conj_flag ? 1 : 0) | (s->non_hermitian ? 2 : 0), g_option_epoch};
+    fnv(h, hdr, sizeof(hdr));
+    if (!s->gates.empty()) fnv(h, s->gates.data(), s->gates.size() * sizeof(dmb_gate));
+    if (!s->mats.empty()) fnv(h, s->mats.data(), s->mats.size() * sizeof(double));
+    if (!s->layout.empty()) fnv(h, s->layout.data(), s->layout.size() * sizeof(int));
+    if (!h[0] && !h[1]) h[0] = 1;
+}
 
 // cross-rank sum of `count` doubles in place on s->stream (one-process-per-GPU form, communicator attached)
 static int all_reduce_sum(dmb_sim* s, double* d_buf, size_t count)
@@ -338,6 +417,7 @@ static int destroy_shard(dmb_sim* s)
     if (s->d_rounds) cudaFree(s->d_rounds);
     if (s->d_groups) cudaFree(s->d_groups);
     if (s->d_scratch) cudaFree(s->d_scratch);
+    if (s->d_multi) cudaFree(s->d_multi);
     delete s;
     return DMB_OK;
 }
@@ -379,6 +459,7 @@ int dmb_set_option(const char* name, int64_t value)
 {
     init_options();
     if (!name) return fail(DMB_EINVAL, "null option name");
+    g_option_epoch++;
     if (!strcmp(name, "tile_bits")) g_opt.tile_bits = (int)value;
     else if (!strcmp(name, "low_bits")) g_opt.low_bits = (int)value;
     else if (!strcmp(name, "min_tiles_log2")) g_opt.min_tiles_log2 = (int)value;
@@ -392,6 +473,11 @@ int dmb_set_option(const char* name, int64_t value)
     else if (!strcmp(name, "dense2_lu")) set_sweep_dense2_lu(value != 0);
     else if (!strcmp(name, "tma_prefetch")) g_tma_prefetch = (int)value;
     else if (!strcmp(name, "direct_store")) set_sweep_direct_store(value != 0);
+    else if (!strcmp(name, "small_state_bits")) g_opt.small_state_bits = (int)value;
+    else if (!strcmp(name, "persistent")) g_persistent = (int)value;
+    else if (!strcmp(name, "jit")) g_jit = (int)value;
+    else if (!strcmp(name, "jit_min_bits")) g_jit_min_bits = (int)value;
+    else if (!strcmp(name, "plan_cache")) g_plan_cache = (int)value;
     else return fail(DMB_EINVAL, std::string("unknown option ") + name);
     return DMB_OK;
 }
@@ -547,7 +633,45 @@ int dmb_set_dm(dmb_handle s, const double* real, const double* imag)
 
 // ---- circuit ----------------------------------------------------------------------------------
 // host part: plan + encode into s->host_* (no CUDA calls)
+static int plan_and_encode_uncached(dmb_sim* s);
 static int plan_and_encode(dmb_sim* s)
+{
+    unsigned long long key[2];
+    plan_key_of(s, key);
+    s->plan_key[0] = key[0]; s->plan_key[1] = key[1];
+    if (!g_plan_cache)
+    {
+        s->plan_cache.clear();
+        s->plan_key[0] = s->plan_key[1] = 0; // (never equal to device_key: the tables are uploaded every time)
+        return plan_and_encode_uncached(s);
+    }
+    for (size_t i = 0; i < s->plan_cache.size(); i++)
+    {
+        dmb_sim::CachedPlan& c = s->plan_cache[i];
+        if (c.key[0] != key[0] || c.key[1] != key[1]) continue;
+        s->plan = c.plan; s->plan_layout = c.plan_layout; s->plan_conj = c.plan_conj; s->plan_nonherm = c.plan_nonherm;
+        s->op_offset = c.op_offset; s->star_offset = c.star_offset; s->round_offset = c.round_offset; s->group_offset = c.group_offset;
+        s->n_dev_stars = c.n_dev_stars; s->n_dev_ops = c.n_dev_ops; s->n_dev_rounds = c.n_dev_rounds; s->n_dev_groups = c.n_dev_groups;
+        s->op_masks = c.op_masks; s->directs = c.directs; s->fp64_per_lane = c.fp64_per_lane;
+        s->host_ops = c.host_ops; s->host_stars = c.host_stars; s->host_rounds = c.host_rounds; s->host_groups = c.host_groups;
+        if (i) std::rotate(s->plan_cache.begin(), s->plan_cache.begin() + (long)i, s->plan_cache.begin() + (long)i + 1);
+        return DMB_OK;
+    }
+    int rc = plan_and_encode_uncached(s);
+    if (rc) return rc;
+    dmb_sim::CachedPlan c;
+    c.key[0] = key[0]; c.key[1] = key[1];
+    c.plan = s->plan; c.plan_layout = s->plan_layout; c.plan_conj = s->plan_conj; c.plan_nonherm = s->plan_nonherm;
+    c.op_offset = s->op_offset; c.star_offset = s->star_offset; c.round_offset = s->round_offset; c.group_offset = s->group_offset;
+    c.n_dev_stars = s->n_dev_stars; c.n_dev_ops = s->n_dev_ops; c.n_dev_rounds = s->n_dev_rounds; c.n_dev_groups = s->n_dev_groups;
+    c.op_masks = s->op_masks; c.directs = s->directs; c.fp64_per_lane = s->fp64_per_lane;
+    c.host_ops = s->host_ops; c.host_stars = s->host_stars; c.host_rounds = s->host_rounds; c.host_groups = s->host_groups;
+    s->plan_cache.insert(s->plan_cache.begin(), std::move(c));
+    if (s->plan_cache.size() > kPlanCacheEntries) s->plan_cache.pop_back();
+    return DMB_OK;
+}
+
+static int plan_and_encode_uncached(dmb_sim* s)
 {
     try
     {
@@ -622,13 +746,21 @@ static void adopt_plan(dmb_sim* s, const dmb_sim* src)
     s->host_ops = src->host_ops; s->host_stars = src->host_stars; s->host_rounds = src->host_rounds;
     s->host_groups = src->host_groups;
     s->fp64_per_lane = src->fp64_per_lane;
+    s->plan_key[0] = src->plan_key[0]; s->plan_key[1] = src->plan_key[1];
 }
 
 // device part: the single H2D of the step (stream-ordered; the copies are flushed before returning because the host
 // vectors may be rebuilt by the next dmb_set_circuit)
 static int upload_tables(dmb_sim* s)
 {
+    if (s->device_key[0] == s->plan_key[0] && s->device_key[1] == s->plan_key[1] && (s->plan_key[0] || s->plan_key[1]))
+    {
+        s->h2d_bytes = 0; // the device still holds this plan's tables (and the graph / parameter list captured from them)
+        return DMB_OK;
+    }
     drop_graph(s);
+    s->jit_memo.clear();
+    s->device_key[0] = s->device_key[1] = 0;
     CU(cudaSetDevice(s->device));
     int rc;
     if ((rc = grow_device(s->d_ops, s->d_ops_cap, s->host_ops.size()))) return rc;
@@ -649,6 +781,7 @@ static int upload_tables(dmb_sim* s)
                            s->stream));
         CU(cudaStreamSynchronize(s->stream));
     }
+    s->device_key[0] = s->plan_key[0]; s->device_key[1] = s->plan_key[1];
     return DMB_OK;
 }
 
@@ -747,6 +880,59 @@ static int fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, dou
     return DMB_OK;
 }
 
+// the run-time specialised kernel of sweep `step` with the I/O variant of `a`, or nullptr (interpreter kernel)
+static const void* jit_resolve(dmb_sim* s, size_t step, const SweepArgs& a)
+{
+    if (!g_jit || s->M < g_jit_min_bits) return nullptr;
+    const unsigned long long key = ((unsigned long long)step << 4) | (a.tma_load ? 1u : 0u) | (a.tma_store ? 2u : 0u) | (a.direct.enabled ? 4u : 0u) |
+                                   (a.peer_shift >= 0 ? 8u : 0u);
+    JitKernel* k = nullptr;
+    auto it = s->jit_memo.find(key);
+    if (it != s->jit_memo.end()) k = it->second;
+    else
+    {
+        std::string defines, program;
+        if (jit_available(nullptr) &&
+            jit_generate(a, s->host_ops.data() + s->op_offset[step], s->host_rounds.data() + s->round_offset[step],
+                         s->host_groups.data() + s->group_offset[step], defines, program))
+            k = jit_request(defines, program);
+        s->jit_memo[key] = k;
+    }
+    if (!k || s->jit_mode == 1) return nullptr;
+    int st = k->state.load(std::memory_order_acquire);
+    if (st == 0 && g_jit >= 2 && s->jit_mode != 3) { jit_wait(k); st = k->state.load(std::memory_order_acquire); }
+    if (st == 0) { s->jit_missing++; return nullptr; }
+    if (st != 1) return nullptr;
+    if (s->jit_mode == 3 && !(k->kern && s->device >= 0 && s->device < 64 && ((k->attr_mask >> s->device) & 1ull)))
+    {
+        s->jit_missing++; // became ready after the dry pass: the graph is re-captured at the next run
+        return nullptr;
+    }
+    const void* fn = nullptr;
+    if (jit_kernel(k, s->device, sweep_smem_limit(), &fn) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return fn;
+}
+
+// one sweep on the stream: its specialised kernel when there is one, the interpreter kernel otherwise
+static int launch_sweep_any(dmb_sim* s, size_t step, const SweepArgs& a, int grid_per_sm)
+{
+    const void* fn = jit_resolve(s, step, a);
+    if (s->jit_mode == 1 || s->jit_mode == 2) return DMB_OK; // dry pass
+    if (fn)
+    {
+        const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)(grid_per_sm > 0 ? grid_per_sm * device_num_sms() : sweep_max_grid_fn(fn, a)));
+        CU(launch_sweep_fn(fn, a, grid, s->stream));
+        s->jit_used++;
+    }
+    else
+    {
+        const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)(grid_per_sm > 0 ? grid_per_sm * device_num_sms() : sweep_max_grid(a)));
+        CU(launch_sweep(a, grid, s->stream));
+    }
+    CU(cudaGetLastError());
+    return DMB_OK;
+}
+
 static int comm_events(dmb_sim* s, size_t comm_idx)
 {
     CU(cudaSetDevice(s->device)); // an event belongs to the device that is current when it is created
@@ -776,10 +962,7 @@ static int launch_fused_remap(dmb_sim* s, size_t i, int cur)
     a.peer_shift = s->M - s->g;
     a.peer_rank = s->rank;
     for (int r = 0; r < s->world; r++) a.peer_out[r] = (unsigned long long)s->peer[cur ^ 1][r];
-    const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)sweep_max_grid(a));
-    CU(launch_sweep(a, grid, s->stream));
-    CU(cudaGetLastError());
-    return DMB_OK;
+    return launch_sweep_any(s, i, a, 0);
 }
 
 static bool is_fused_remap(const dmb_sim* s, size_t i)
@@ -805,9 +988,8 @@ static int enqueue_sweep(dmb_sim* s, size_t i, int& cur, uint64_t& launches, uns
     int rca = fill_sweep_args(s, i, in, out, a, support);
     if (rca) return rca;
     for (int j = 0; j < sw.k; j++) support |= 1ull << sw.in_pos[j];
-    const int grid = (int)std::min<unsigned long long>(a.n_tiles, (unsigned long long)(g_grid_per_sm > 0 ? g_grid_per_sm * device_num_sms() : sweep_max_grid(a)));
-    CU(launch_sweep(a, grid, s->stream));
-    CU(cudaGetLastError());
+    int rcl = launch_sweep_any(s, i, a, g_grid_per_sm);
+    if (rcl) return rcl;
     launches++;
     if (sw.out_of_place) cur ^= 1;
     return DMB_OK;
@@ -825,6 +1007,18 @@ static int enqueue_steps(dmb_sim* s, int& cur, uint64_t& launches, bool allow_ex
         // kernel = pack + all-to-all over NVLink) between two one-element all-reduces: the first makes sure every peer
         // is done with the buffer that is about to be overwritten (its earlier sweeps, readouts or resets may still be
         // running), the second that every peer's stores have landed
+        const bool dry = s->jit_mode == 1 || s->jit_mode == 2; // (resolving the specialised kernels only: nothing is enqueued)
+        if (dry && (st.kind == 1 || (allow_exchange && is_fused_remap(s, i))))
+        {
+            if (st.kind == 0)
+            {
+                int rc = launch_fused_remap(s, i, cur);
+                if (rc) return rc;
+                i++;
+            }
+            cur ^= 1;
+            continue;
+        }
         if (allow_exchange && is_fused_remap(s, i))
         {
             int rc = comm_events(s, comm_idx);
@@ -877,6 +1071,20 @@ static int enqueue_steps(dmb_sim* s, int& cur, uint64_t& launches, bool allow_ex
     return DMB_OK;
 }
 
+// resolves the run-time specialised kernels of the plan without enqueuing anything (mode 1: queue the compilations; 2: wait /
+// load as the "jit" option says)
+static int jit_dry_pass(dmb_sim* s, int mode)
+{
+    if (!g_jit || s->M < g_jit_min_bits) return DMB_OK;
+    s->jit_mode = mode;
+    int c2 = s->cur;
+    uint64_t l2 = 0;
+    unsigned long long sup2 = s->support;
+    const int rc = enqueue_steps(s, c2, l2, true, sup2);
+    s->jit_mode = 0;
+    return rc;
+}
+
 // every shard's stream waits until all the OTHER shards have reached the event `which` (0 = ev_pre, 1 = ev_post)
 static int group_barrier(dmb_sim* grp, int which)
 {
@@ -908,6 +1116,12 @@ static int group_run(dmb_sim* grp, dmb_stats* stats)
     }
     uint64_t launches = 0;
     size_t comm_idx = 0;
+    if (lead->jit_memo.empty())
+    {
+        CU(cudaSetDevice(lead->device));
+        int rcj = jit_dry_pass(lead, 1); // queue every compilation of the plan at once (the shards share the kernels)
+        if (rcj) return rcj;
+    }
     for (size_t i = 0; i < nsteps; i++)
     {
         const Step& st = lead->plan.steps[i];
@@ -1024,11 +1238,81 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
         if (rc) return rc;
     }
     uint64_t launches = 0;
-    const bool graphable = g_use_graph && s->plan.n_exchanges == 0 && s->plan.n_sweeps > 1;
     int cur = s->cur;
-    if (graphable)
+    // small states (no sweep of the plan uses TMA tile I/O: PlanOptions::small_state_bits) -> ONE cooperative launch for the whole run
+    bool persistent = g_persistent && s->world == 1 && s->plan.n_exchanges == 0 && s->plan.n_sweeps > 1;
+    for (const Step& st : s->plan.steps)
+        if (st.kind != 0 || st.sweep.swz_mode != kSwzXor3) persistent = false;
+    if (persistent)
     {
-        if (!s->graph_exec || s->graph_cur != s->cur || s->graph_support != s->support)
+        if (!s->multi_valid || s->multi_cur != s->cur || s->multi_support != s->support)
+        {
+            std::vector<SweepArgs> list;
+            int c2 = s->cur;
+            unsigned long long sup = s->support, max_tiles = 1;
+            unsigned mask = 0;
+            size_t smem = 0;
+            for (size_t i = 0; i < s->plan.steps.size(); i++)
+            {
+                const Sweep& sw = s->plan.steps[i].sweep;
+                double2* in = s->buf[c2];
+                double2* out = in;
+                if (sw.out_of_place)
+                {
+                    int rc = ensure_second_buffer(s);
+                    if (rc) return rc;
+                    out = s->buf[c2 ^ 1];
+                    sup = ~0ull;
+                }
+                SweepArgs a;
+                int rc = fill_sweep_args(s, i, in, out, a, sup);
+                if (rc) return rc;
+                for (int j = 0; j < sw.k; j++) sup |= 1ull << sw.in_pos[j];
+                if (sw.out_of_place) c2 ^= 1;
+                mask |= a.op_mask;
+                smem = std::max(smem, sweep_smem_bytes(a));
+                max_tiles = std::max(max_tiles, a.n_tiles);
+                list.push_back(a);
+            }
+            if (list.size() > s->d_multi_cap)
+            {
+                if (s->d_multi) cudaFree(s->d_multi);
+                s->d_multi = nullptr;
+                s->d_multi_cap = 0;
+                CU(cudaMalloc(&s->d_multi, list.size() * sizeof(SweepArgs)));
+                s->d_multi_cap = list.size();
+            }
+            CU(cudaMemcpyAsync(s->d_multi, list.data(), list.size() * sizeof(SweepArgs), cudaMemcpyHostToDevice, s->stream));
+            CU(cudaStreamSynchronize(s->stream)); // (list is a local vector)
+            s->h2d_bytes += list.size() * sizeof(SweepArgs);
+            s->multi_valid = true;
+            s->multi_cur = s->cur; s->multi_support = s->support; s->multi_end_cur = c2; s->multi_n = (int)list.size();
+            s->multi_mask = mask; s->multi_smem = smem; s->multi_max_tiles = max_tiles;
+        }
+        CU(cudaEventRecord(s->ev_begin, s->stream));
+        int grid = 0;
+        cudaError_t le = launch_multi_sweep(s->d_multi, s->multi_n, s->multi_mask, s->multi_smem, s->multi_max_tiles, s->stream, &grid);
+        if (le == cudaSuccess)
+        {
+            CU(cudaEventRecord(s->ev_end, s->stream));
+            launches = 1;
+            cur = s->multi_end_cur;
+            for (const Step& st : s->plan.steps)
+                for (int j = 0; j < st.sweep.k; j++) s->support |= 1ull << st.sweep.in_pos[j];
+        }
+        else
+        {
+            cudaGetLastError(); // (no cooperative launch here: the per-sweep executors below take over)
+            persistent = false;
+        }
+    }
+    const bool graphable = !persistent && g_use_graph && s->plan.n_exchanges == 0 && s->plan.n_sweeps > 1;
+    if (persistent) {}
+    else if (graphable)
+    {
+        // (tiered execution: sweeps captured on the interpreter kernel move to their specialised kernel once it is compiled)
+        const bool stale = s->graph_exec && s->graph_jit_missing > 0 && jit_ready_count() != s->graph_jit_epoch;
+        if (!s->graph_exec || s->graph_cur != s->cur || s->graph_support != s->support || stale)
         {
             drop_graph(s);
             for (const Step& st : s->plan.steps)
@@ -1038,12 +1322,21 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
                     if (rc) return rc;
                 }
             sweep_setup(); // attribute setup must not happen inside capture
+            // ... nor the loading of run-time specialised kernels: resolve them first (all compilations queued, then waited for / loaded)
+            int rcj = jit_dry_pass(s, 1);
+            if (!rcj) rcj = jit_dry_pass(s, 2);
+            if (rcj) return rcj;
             cudaGraph_t graph = nullptr;
             CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
             int c2 = s->cur;
             uint64_t l2 = 0;
             unsigned long long sup2 = s->support;
+            s->jit_mode = 3;
+            s->jit_missing = s->jit_used = 0;
             int rc = enqueue_steps(s, c2, l2, false, sup2);
+            s->jit_mode = 0;
+            s->graph_jit_missing = s->jit_missing;
+            s->graph_jit_epoch = jit_ready_count();
             cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
             if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
             CU(ce);
@@ -1066,6 +1359,12 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
     else
     {
         sweep_setup();
+        if (s->jit_memo.empty())
+        {
+            int rcj = jit_dry_pass(s, 1); // queue every compilation of the plan at once
+            if (rcj) return rcj;
+        }
+        s->jit_missing = s->jit_used = 0;
         CU(cudaEventRecord(s->ev_begin, s->stream));
         int rc = enqueue_steps(s, cur, launches, true, s->support);
         if (rc) return rc;
@@ -1465,6 +1764,86 @@ int64_t dmb_plan_json(int n_qubits, int world_size, const dmb_gate* gates, size_
     {
         return fail(DMB_ESTATE, e.what());
     }
+}
+
+// The CUDA text the run-time compiler would be given for sweep `sweep_index` of the plan (its structural #defines, a
+// separator line "//---- program", then the generated body of "dmb_jit_program.inc"): host only, for the CPU test-suite.
+// peer != 0: the variant whose stores go to the peers' shards.  Returns the bytes needed (including NUL), 0 when the step is
+// not a sweep or the generator does not cover it.
+int64_t dmb_jit_source(int n_qubits, int world_size, const dmb_gate* gates, size_t n_gates, const double* mats, size_t n_mats,
+                       int sweep_index, int peer, char* out, size_t cap)
+{
+    init_options();
+    try
+    {
+        Plan p = make_plan(n_qubits, world_size, gates, n_gates, mats, n_mats, std::vector<int>(), g_opt, false, false);
+        int seen = -1;
+        for (size_t i = 0; i < p.steps.size(); i++)
+        {
+            if (p.steps[i].kind != 0 || ++seen != sweep_index) continue;
+            const Sweep& sw = p.steps[i].sweep;
+            EncodedSweep enc;
+            encode_sweep(sw, enc);
+            SweepArgs a;
+            memset(&a, 0, sizeof(a));
+            fill_sweep_tables(sw, 2 * n_qubits - p.g, a);
+            a.ops_bytes = (int)enc.stream.size();
+            a.n_rounds = (int)enc.rounds.size();
+            a.n_groups = (int)enc.groups.size();
+            a.n_stars = (int)enc.stars.size();
+            a.op_mask = enc.op_mask;
+            a.peer_shift = peer ? 0 : -1;
+            a.direct = enc.direct;
+            if (!a.tma_load || !a.tma_store || sw.out_of_place) a.direct.enabled = 0;
+            if (a.direct.enabled || peer) a.tma_store = 0;
+            std::string defines, program;
+            if (!jit_generate(a, enc.stream.data(), enc.rounds.data(), enc.groups.data(), defines, program)) return 0;
+            const std::string js = defines + "//---- program\n" + program;
+            if (out && cap > 0)
+            {
+                const size_t ncopy = std::min(cap - 1, js.size());
+                memcpy(out, js.data(), ncopy);
+                out[ncopy] = 0;
+            }
+            return (int64_t)js.size() + 1;
+        }
+        return 0;
+    }
+    catch (const std::invalid_argument& e)
+    {
+        return fail(DMB_EINVAL, e.what());
+    }
+    catch (const std::exception& e)
+    {
+        return fail(DMB_ESTATE, e.what());
+    }
+}
+
+// Counters of the run-time compiler (process-wide) and of handle h's last dmb_run (h may be NULL for the process-wide ones):
+// "jit_compiled", "jit_disk_hits", "jit_failed", "jit_compile_ms", "jit_ready", "jit_available";
+// "jit_sweeps" (sweeps of the last run on specialised kernels), "jit_pending" (... still interpreted: kernel not ready yet).
+int dmb_query(dmb_handle h, const char* name, double* value)
+{
+    if (!name || !value) return fail(DMB_EINVAL, "null argument");
+    unsigned long long compiled = 0, disk = 0, failed = 0;
+    double ms = 0;
+    jit_counters(&compiled, &disk, &failed, &ms);
+    if (!strcmp(name, "jit_compiled")) *value = (double)compiled;
+    else if (!strcmp(name, "jit_disk_hits")) *value = (double)disk;
+    else if (!strcmp(name, "jit_failed")) *value = (double)failed;
+    else if (!strcmp(name, "jit_compile_ms")) *value = ms;
+    else if (!strcmp(name, "jit_ready")) *value = (double)jit_ready_count();
+    else if (!strcmp(name, "jit_available")) *value = jit_available(nullptr) ? 1.0 : 0.0;
+    else if (h && (!strcmp(name, "jit_sweeps") || !strcmp(name, "jit_pending")))
+    {
+        const bool used = !strcmp(name, "jit_sweeps");
+        double v = 0;
+        if (is_group(h)) for (const dmb_sim* c : h->shards) v += used ? c->jit_used : c->jit_missing;
+        else v = used ? h->jit_used : h->jit_missing;
+        *value = v;
+    }
+    else return fail(DMB_EINVAL, std::string("unknown counter ") + name);
+    return DMB_OK;
 }
 
 } // extern "C"

@@ -1,7 +1,18 @@
 // dm-sim_b200/csrc/devop.hpp -- plain-old-data shared by the host encoder (encode.cpp, system compiler) and the
 // device code (kernels.cu).  No CUDA types here.
 #pragma once
+#ifdef __CUDACC_RTC__ // (run-time compilation of the sweep program: no host headers)
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <cstdint>
+#endif
 
 namespace dmb
 {

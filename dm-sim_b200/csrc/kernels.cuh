@@ -19,9 +19,16 @@ struct LayoutArgs
 size_t sweep_smem_bytes(const SweepArgs& a);
 cudaError_t launch_sweep(const SweepArgs& a, int grid, cudaStream_t s);
 void set_sweep_dual(bool on);           // experiments: full-size tiles on the two-iterations-resident kernel
+// every sweep of a small-state run in ONE cooperative launch (grid barrier between sweeps)
+cudaError_t launch_multi_sweep(const SweepArgs* d_list, int n, unsigned op_mask_union, size_t max_body_smem, unsigned long long max_tiles,
+                               cudaStream_t s, int* grid_out);
 int device_num_sms();                   // SM count of the current device
 int sweep_max_grid(const SweepArgs& a); // resident CTAs for this sweep's shared-memory footprint (SMs * occupancy)
 void sweep_setup();                     // one-time function attributes (must not run inside a stream capture)
+int sweep_smem_limit();                 // dynamic shared-memory limit the sweep kernels are set up with on the current device
+// launch on a run-time specialised kernel of the sweep (jit.cu)
+int sweep_max_grid_fn(const void* fn, const SweepArgs& a);
+cudaError_t launch_sweep_fn(const void* fn, const SweepArgs& a, int grid, cudaStream_t s);
 
 void launch_init_state(double2* buf, size_t n_elems, bool owns_origin, cudaStream_t s);
 void launch_diag(const double2* buf, const LayoutArgs& L, double* out_real, double* out_abs, cudaStream_t s);

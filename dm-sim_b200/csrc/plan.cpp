@@ -841,7 +841,8 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
         }
         for (auto& mv : moves) phys[mv.first] = mv.second;
         for (int j = 0; j < sw.k; j++) sw.out_pos.push_back(phys[order[j]]);
-        sw.swz_mode = (opt.tma && sw.k == 12 && lowb >= 3) ? 1 : 0;
+        // (L2-resident states: no TMA -- every sweep of the run then fits the one-launch cooperative executor, capi.cu)
+        sw.swz_mode = (opt.tma && sw.k == 12 && lowb >= 3 && M > opt.small_state_bits) ? 1 : 0;
         sw.out_of_place = !moves.empty() && !in_place; // a permutation INSIDE the tile may run in place: every tile is read
                                                        // completely before it is written, to the same set of addresses
         plan.steps.push_back(st);

@@ -164,6 +164,17 @@ int64_t dmb_plan_json(int n_qubits, int world_size, const dmb_gate* gates, size_
                       size_t n_mats, const int32_t* start_layout /* NULL = identity */, int conj_state, char* out,
                       size_t cap);
 
+/* ---- run-time specialised sweep kernels (csrc/jit.cu) ----
+ * dmb_jit_source: the CUDA text the run-time compiler is given for sweep `sweep_index` of the plan of this circuit (host
+ * only, needs no GPU; for the CPU test-suite).  Returns the bytes needed (including NUL), 0 if there is no such sweep or
+ * the generator does not cover it; writes at most cap bytes.
+ * dmb_query: counters -- process-wide "jit_available", "jit_compiled", "jit_disk_hits", "jit_failed", "jit_compile_ms",
+ * "jit_ready"; of handle h's last dmb_run "jit_sweeps" (sweeps that ran on specialised kernels) and "jit_pending"
+ * (sweeps that were still interpreted because their kernel was not compiled yet). */
+int64_t dmb_jit_source(int n_qubits, int world_size, const dmb_gate* gates, size_t n_gates, const double* mats,
+                       size_t n_mats, int sweep_index, int peer, char* out, size_t cap);
+int dmb_query(dmb_handle h /* may be NULL */, const char* name, double* value);
+
 /* Tuning knobs (process-wide; also read once from env DMB_TILE_BITS, DMB_LOW_BITS, DMB_GRAPH):
  * "tile_bits" (<= 12), "low_bits" (contiguous run = 2^low_bits elements), "graph" (0/1). */
 int dmb_set_option(const char* name, int64_t value);

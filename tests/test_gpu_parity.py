@@ -1,4 +1,6 @@
 """-m gpu: the CUDA path (through the C-ABI) against the oracle, 1e-12 absolute on every element."""
+import os
+
 import numpy as np
 import pytest
 
@@ -172,19 +174,89 @@ def test_tile_geometries(dm, oracle_mod, opts):
 
 
 def test_graph_and_stream_paths_agree(dm):
+    """The three executors of a single-GPU run -- one cooperative launch for all sweeps (small states), CUDA graph, plain
+    stream launches -- give bit-identical results."""
     n = 8
     rng = np.random.default_rng(31)
     gates = random_gates(n, 50, rng)
-    outs = []
-    for graph in (1, 0):
+    outs, launches = [], []
+    for persistent, graph in ((1, 1), (0, 1), (0, 0)):
+        dm.set_option("persistent", persistent)
         dm.set_option("graph", graph)
         dm.set_option("tile_bits", 8)
         try:
             sim = run_gpu(dm, n, gates)
             outs.append(sim.get_dm())
+            launches.append((sim.last_stats["n_launches"], sim.last_stats["n_sweeps"]))
         finally:
-            dm.set_option("graph", 1); dm.set_option("tile_bits", 12)
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+            dm.set_option("graph", 1); dm.set_option("tile_bits", 12); dm.set_option("persistent", 1)
+    for o in outs[1:]:
+        assert np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1])
+    assert launches[0][1] > 1 and launches[0][0] == 1, "the small-state run should be ONE launch"
+    assert launches[2][0] == launches[2][1]
+
+
+def test_one_launch_executor_vqe_golden_and_continuation(dm, oracle_mod):
+    """benchmark/vqe_uccsd_n8.qasm (10808 gates, ~100 sweeps) as one cooperative launch against the reference's golden
+    diagonal, then a second circuit continuing from the evolved state."""
+    import importlib
+    circuits = importlib.import_module("dm-sim_b200.circuits")
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "vqe_uccsd_n8.npz"))
+    gates = circuits.vqe_uccsd_n8()
+    sim = run_gpu(dm, 8, gates)
+    assert sim.last_stats["n_launches"] == 1 and sim.last_stats["n_sweeps"] > 50
+    assert np.abs(sim.diag() - z["diag"]).max() < TOL
+    rng = np.random.default_rng(5)
+    more = random_gates(8, 30, rng)
+    sim.clear_circuit()
+    for g in more:
+        sim.append(dm.Gate(g[0], *(list(g[1]) + [0] * (5 - len(g[1]))), theta=g[2], phi=g[3], lam=g[4], matrix=g[5] if len(g) > 5 else None))
+    sim.upload()
+    sim.run()
+    o = oracle_mod.Oracle(8).sim(gates + more)
+    assert np.abs(sim.diag() - o.diag()).max() < 1e-11  # (10838 gates deep: the reference itself drifts by 1e-12)
+
+
+def test_plan_cache_reuses_and_alternates(dm, oracle_mod):
+    """A circuit that is set again reuses its plan and the device tables (h2d_bytes == 0); alternating circuits, resets and
+    the cache switched off give the same state as the oracle."""
+    n = 9
+    rng = np.random.default_rng(77)
+    a, b = random_gates(n, 40, rng), random_gates(n, 40, rng)
+    L = dm.lib()
+
+    def set_(sim, gates):
+        rec, mats = dm.pack_gates(gates)
+        dm._check(L.dmb_set_circuit(sim._h, rec.ctypes.data, len(rec), mats.ctypes.data if mats.size else None, mats.size // 32))
+        sim._uploaded = True
+
+    try:
+        for cache in (1, 0):
+            dm.set_option("plan_cache", cache)
+            sim = dm.Simulation(n, 1)
+            o = oracle_mod.Oracle(n)
+            h2d = []
+            for gates in (a, a, b, a, b, b):
+                sim.reset_dm()
+                set_(sim, gates)
+                sim.run()
+                h2d.append(sim.last_stats["h2d_bytes"])
+                re, im = sim.get_dm()
+                ore, oim = oracle_mod.Oracle(n).sim(gates).dm()
+                assert max(np.abs(re - ore).max(), np.abs(im - oim).max()) < TOL
+            if cache:
+                assert h2d[0] > 0 and h2d[1] == 0 and h2d[2] > 0 and h2d[5] == 0
+            else:
+                assert all(x > 0 for x in h2d)
+            # continuation (no reset): the second run of `a` starts from another layout / state -> another plan
+            set_(sim, a)
+            sim.run()
+            o.sim(b).sim(a)
+            re, im = sim.get_dm()
+            ore, oim = o.dm()
+            assert max(np.abs(re - ore).max(), np.abs(im - oim).max()) < TOL
+    finally:
+        dm.set_option("plan_cache", 1)
 
 
 @pytest.mark.parametrize("n,tile_bits", [(9, 8), (10, 12), (7, 5)])

@@ -68,7 +68,7 @@ def test_random_circuits_every_geometry(dm, oracle_mod, opts, n, world, o):
 def test_full_size_tiles_tma_addressing(dm, oracle_mod, opts, n, world, o):
     """k = 12 tiles: TMA boxes (5-D tensor view of the shard, enumerated copies), the hardware 128-byte swizzle and the
     lane-bit choice that goes with it -- walked by the kernel emulator exactly as the device does."""
-    opts(**o)
+    opts(small_state_bits=0, **o)  # (states this small would otherwise keep the plain tile I/O)
     try:
         rng = np.random.default_rng(77 + world)
         gates = random_gates(n, 60, rng, exclude=("SRN",))
@@ -87,7 +87,7 @@ def test_full_size_tiles_tma_addressing(dm, oracle_mod, opts, n, world, o):
                     assert st["dev"]["tma_store"] == int(st["in_pos"] == st["out_pos"] and not st["out_of_place"])
         assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - to_complex(re, im)).max() < TOL
     finally:
-        dm.set_option("tma", 1); dm.set_option("tma_box_bits", 10)
+        dm.set_option("tma", 1); dm.set_option("tma_box_bits", 10); dm.set_option("small_state_bits", 20)
 
 
 def test_each_op_alone(dm, oracle_mod):
