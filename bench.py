@@ -202,7 +202,10 @@ class Job:
             self.dist.destroy_process_group()
 
 
-def measure(job, dm, name, steps, warmup, world=None, sampler=None, e2e=True, keep=False):
+JIT_MODE = 2  # --jit: 2 = wait for the run-time specialised sweep kernels (deterministic timing), 1 = tiered, 0 = interpreter kernels only
+
+
+def measure(job, dm, name, steps, warmup, world=None, sampler=None, e2e=True, keep=False, first_call=False):
     """Device time of `steps` runs of workload `name` on the DENSE resident state (+ the end-to-end legs).
     world = None: the job's ranks (one shard per process); world = 1 inside a multi-rank job: this process alone."""
     import numpy as np
@@ -220,10 +223,31 @@ def measure(job, dm, name, steps, warmup, world=None, sampler=None, e2e=True, ke
 
     # `value` / `roofline` are measured on the DENSE resident state: every tile of every sweep is launched (after a reset
     # the engine would otherwise skip the tiles that are still all-zero, see the e2e leg below)
+    first_ms = None
+    if first_call:
+        # the very first call of this circuit in the process, as a user's one-shot run sees it (tiered execution: nothing
+        # waits for the run-time compiler -- the interpreter kernels run while the specialised ones are being built)
+        dm.set_option("jit", 1 if JIT_MODE else 0)
+        dm.set_option("sparse", 1)
+        d0 = np.empty(1 << n)
+        barrier()
+        t1 = time.perf_counter()
+        sim.reset_dm()
+        set_circuit()
+        sim.run()
+        dm._check(L.dmb_get_diag(sim._h, d0.ctypes.data))
+        barrier()
+        first_ms = (time.perf_counter() - t1) * 1e3
+    # A step = the circuit applied to a freshly reset state with sparse start OFF (every tile of every sweep is processed: the
+    # work of a dense state; FP64 timing does not depend on the values).  Starting every step from the same bit layout lets the
+    # engine reuse the circuit's plan, its captured graph and its specialised kernels -- a circuit that CONTINUES from the
+    # previous run's state starts from the layout that run left behind and is planned anew (`continued_state` below).
+    dm.set_option("jit", JIT_MODE)
     dm.set_option("sparse", 0)
     sim.reset_dm()
     set_circuit()
     for _ in range(warmup):
+        sim.reset_dm()
         sim.run()
     if sampler is not None:
         sampler.start()
@@ -231,6 +255,7 @@ def measure(job, dm, name, steps, warmup, world=None, sampler=None, e2e=True, ke
     t0 = time.perf_counter()
     dev_ms, comm_ms, launches, sweeps = 0.0, 0.0, 0, 0
     for _ in range(steps):
+        sim.reset_dm()
         sim.run()
         st = sim.last_stats
         dev_ms += st["sim_ms"]; comm_ms += st["comm_ms"]
@@ -241,7 +266,20 @@ def measure(job, dm, name, steps, warmup, world=None, sampler=None, e2e=True, ke
     st = dict(sim.last_stats)
     if not solo and world > 1:
         dev_ms, comm_ms, wall_ms = job.max([dev_ms, comm_ms, wall_ms])
-    out = {"name": name, "n": n, "gates": gates, "n_gates": len(gates), "st": st, "ms_step": dev_ms / steps, "dev_ms": dev_ms,
+    jit = {"mode": JIT_MODE, "sweeps_specialised": int(dm.query("jit_sweeps", sim._h)), "sweeps_pending": int(dm.query("jit_pending", sim._h)),
+           "sweeps_per_step": int(st["n_sweeps"])}
+    cont_ms = None
+    if first_call:
+        # the same circuit CONTINUING from the state (and bit layout) the previous run left: tiered execution, no waiting
+        dm.set_option("jit", 1 if JIT_MODE else 0)
+        cont = []
+        for _ in range(2):
+            sim.run()
+            cont.append(sim.last_stats["sim_ms"])
+        cont_ms = job.max([min(cont)])[0] if (not solo and world > 1) else min(cont)
+        dm.set_option("jit", JIT_MODE)
+    out = {"name": name, "n": n, "gates": gates, "n_gates": len(gates), "st": st, "ms_step": dev_ms / steps, "dev_ms": dev_ms, "jit": jit,
+           "first_ms": first_ms, "cont_ms": cont_ms,
            "comm_ms": comm_ms, "wall_ms_step": wall_ms / steps, "launches": launches, "sweeps": sweeps, "clocks": clocks,
            "steps": steps, "world": world}
     if e2e:
@@ -322,7 +360,8 @@ def roofline(m, peak, peak_src):
     fp64 = 2.0 * st["fp64_ops"] * m["steps"] / comp_s / 1e12 if comp_s > 0 else 0.0  # FMA-equivalent TFLOP/s
     frac_hbm, frac_fp64 = hbm / peak, fp64 / FP64_TFLOPS
     bound = "fp64" if frac_fp64 > frac_hbm else "hbm"
-    r = {"bound": bound, "kernel": "sweep_kernel",
+    specialised = m.get("jit", {}).get("sweeps_specialised", 0) > 0
+    r = {"bound": bound, "kernel": "dmb_jit_sweep (run-time specialised sweep_kernel)" if specialised else "sweep_kernel",
          "achieved": fp64 if bound == "fp64" else hbm, "peak": FP64_TFLOPS if bound == "fp64" else peak,
          "unit": "TFLOP/s" if bound == "fp64" else "GB/s", "frac": max(frac_hbm, frac_fp64),
          "frac_hbm": frac_hbm, "achieved_GBps": hbm, "peak_GBps": peak, "frac_of_8TBs_nominal": hbm / 8000.0, "peak_source": peak_src,
@@ -339,7 +378,7 @@ def brief(m, peak, peak_src):
     r = roofline(m, peak, peak_src)
     d = {"workload": m["name"], "n_qubits": m["n"], "n_gates": m["n_gates"], "n_gpus": m["world"], "steps": m["steps"],
          "ms_per_step": m["ms_step"], "gates_per_s": m["n_gates"] / (m["ms_step"] * 1e-3), "sweeps_per_step": m["st"]["n_sweeps"],
-         "gpu_launches_per_step": m["launches"] // max(1, m["steps"]),
+         "gpu_launches_per_step": m["launches"] // max(1, m["steps"]), "jit": m["jit"],
          "roofline": {k: r[k] for k in ("bound", "frac", "frac_hbm", "frac_fp64", "achieved_GBps", "achieved_fp64_TFLOPs", "avg_launch_ms")}}
     if "e2e_ms" in m:
         d["e2e"] = {"ms_per_step": m["e2e_ms"], "gates_per_s": m["n_gates"] / (m["e2e_ms"] * 1e-3),
@@ -402,7 +441,11 @@ def main():
     ap.add_argument("--cpu-full-size", action="store_true", help="reference arm: run the named size itself (n = 15: 64 GiB, minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip extra_workloads / strong_scaling / parity (quick A/B runs)")
+    ap.add_argument("--jit", type=int, default=int(os.environ.get("DMB_JIT", "2")),
+                    help="run-time specialised sweep kernels: 2 wait for the compiler (default), 1 tiered, 0 interpreter kernels only")
     args = ap.parse_args()
+    global JIT_MODE
+    JIT_MODE = args.jit
 
     job = Job()
     rank, world = job.rank, job.world
@@ -430,12 +473,20 @@ def main():
         parity["small"] = parity_small(job, dm)
 
     sampler = ClockSampler(job.local_rank) if rank == 0 else None
-    m = measure(job, dm, args.workload, args.steps, args.warmup, sampler=sampler, keep=True)
+    m = measure(job, dm, args.workload, args.steps, args.warmup, sampler=sampler, keep=True, first_call=True)
     if extras and world > 1:
         parity["workload"] = parity_workload(job, m)
     m.pop("sim", None)
 
-    extra_workloads, strong = [], None
+    extra_workloads, strong, interpreted = [], None, None
+    if extras and world == 1 and JIT_MODE:
+        # the same workload on the ahead-of-time INTERPRETER kernels (what runs until the specialised kernels are compiled)
+        JIT_MODE = 0
+        try:
+            mi = measure(job, dm, args.workload, 3, 1, e2e=False)
+            interpreted = {"ms_per_step": mi["ms_step"], "roofline_frac": roofline(mi, peak, peak_src)["frac"]}
+        finally:
+            JIT_MODE = args.jit
     if extras and world == 1:
         # the other single-GPU configurations of BASELINE.json, each outside the timed region of the headline
         for name, k, w in (("bv_n15", 5, 3), ("adder_n10", 20, 3), ("vqe_uccsd_n8", 5, 3), ("random_c1c2_n15", 2, 1), ("random_c1c2_n16", 2, 1)):
@@ -473,12 +524,15 @@ def main():
                    "scaling_note": "BASELINE.json names a different configuration per GPU count (15 q on 1 GPU, 16 q on 2 / 4, 17 q "
                                    "on 8): `value` of different N is NOT one scaling series.  The same-workload series is "
                                    "`strong_scaling` (random_c1c2_n16 on 1 GPU, measured by rank 0 in this run, vs N GPUs)",
+                   "step": "dmb_reset_dm + dmb_run with sparse start OFF (all tiles of all sweeps processed, the work of a dense state); "
+                           "device time of dmb_run (CUDA events on the engine's stream)",
                    "l2_policy": "state per GPU (>= 16 GiB at the named sizes) is far larger than the 126 MB L2; no flush needed",
                    "parallelism": f"shard on top {world.bit_length() - 1} index bits, one process per GPU" if world > 1 else "single GPU"},
         "roofline": roofline(m, peak, peak_src),
         "e2e": {"value": n_gates / (m["e2e_ms"] * 1e-3), "unit": "gates/s", "ms_per_step": m["e2e_ms"],
                 "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 8 * (1 << n),
                 "host_call_ms": dict(zip(("reset_dm", "set_circuit", "run", "get_diag"), m["e2e_parts"])),
+                "first_call_ms": m["first_ms"],
                 "quoted": "from |0..0><0..0| (dmb_reset_dm inside the timed region; on one GPU the leading sweeps skip the tiles "
                           "that are still all-zero, 'sparse start')",
                 "resident_state": {"value": n_gates / (m["e2e_res_ms"] * 1e-3), "ms_per_step": m["e2e_res_ms"],
@@ -491,6 +545,14 @@ def main():
                         "probabilities), wall clock"},
         # size-independent rate (gates/s shrinks 4x per added qubit): gates x density-matrix elements updated per second
         "work_rate": {"value": n_gates * float(4 ** n) / (ms_step * 1e-3), "unit": "gate x element updates/s"},
+        "jit": dict(m["jit"], compiled_kernels=int(dm.query("jit_compiled")), disk_cache_hits=int(dm.query("jit_disk_hits")),
+                    failed=int(dm.query("jit_failed")), compile_ms_total=dm.query("jit_compile_ms"), interpreter_kernels=interpreted,
+                    what="sweeps run on kernels specialised at run time (NVRTC, csrc/jit.cu: the sweep's program as straight-line "
+                         "code over the same op bodies); compiled on worker threads, cached by program text in memory and on disk; "
+                         "`value` waits for them (mode 2), e2e.first_call_ms does not (tiered: interpreter kernels meanwhile)"),
+        "continued_state": {"ms_per_step": m["cont_ms"],
+                            "what": "dmb_run again WITHOUT the reset (tiered): the circuit continues from the bit layout the previous run "
+                                    "left, so it is planned anew and runs on the interpreter kernels until its own kernels are compiled"},
         "gpu_launches": int(m["launches"]), "wall_ms_per_step": m["wall_ms_step"],
         "trace_after_run": m["trace"], "clocks": m["clocks"],
     }

@@ -46,7 +46,7 @@ static int fail(int code, const std::string& msg)
 static PlanOptions g_opt;
 static int g_use_graph = 1;
 static int g_plan_cache = 1;    // reuse the plan (and the device tables) of a circuit that is set again (DMB_PLAN_CACHE=0 / option "plan_cache")
-static int g_persistent = 1;    // small states: all sweeps of a run in one cooperative launch (DMB_PERSISTENT=0 / option "persistent")
+static int g_persistent = 0;    // small states: all sweeps of a run in one cooperative launch (DMB_PERSISTENT=1 / option "persistent"); measured SLOWER than the captured graph on B200 (vqe_uccsd_n8: 10.1 vs 7.8 ms, profiles/README.md): off by default
 // run-time specialised sweep kernels (jit.cu): 0 off, 1 tiered (the interpreter kernel runs a sweep until its compiled kernel
 // is ready), 2 wait for the compiler (DMB_JIT / option "jit"); only for shards of >= 2^jit_min_bits elements (sweeps of
 // smaller states take microseconds; DMB_JIT_MIN_BITS / option "jit_min_bits")
@@ -1108,6 +1108,17 @@ static int group_run(dmb_sim* grp, dmb_stats* stats)
 {
     dmb_sim* lead = grp->shards[0];
     const size_t nsteps = lead->plan.steps.size();
+    for (dmb_sim* c : grp->shards) c->jit_missing = c->jit_used = 0;
+    if (lead->jit_memo.empty())
+    {
+        // queue every compilation of the plan at once (the shards share the kernels); the waiting mode waits here, before
+        // the timed region
+        CU(cudaSetDevice(lead->device));
+        sweep_setup();
+        int rcj = jit_dry_pass(lead, 1);
+        if (!rcj && g_jit >= 2) rcj = jit_dry_pass(lead, 2);
+        if (rcj) return rcj;
+    }
     for (dmb_sim* c : grp->shards)
     {
         CU(cudaSetDevice(c->device));
@@ -1116,12 +1127,6 @@ static int group_run(dmb_sim* grp, dmb_stats* stats)
     }
     uint64_t launches = 0;
     size_t comm_idx = 0;
-    if (lead->jit_memo.empty())
-    {
-        CU(cudaSetDevice(lead->device));
-        int rcj = jit_dry_pass(lead, 1); // queue every compilation of the plan at once (the shards share the kernels)
-        if (rcj) return rcj;
-    }
     for (size_t i = 0; i < nsteps; i++)
     {
         const Step& st = lead->plan.steps[i];
@@ -1361,7 +1366,9 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
         sweep_setup();
         if (s->jit_memo.empty())
         {
-            int rcj = jit_dry_pass(s, 1); // queue every compilation of the plan at once
+            // queue every compilation of the plan at once; the waiting mode waits HERE, before the timed region
+            int rcj = jit_dry_pass(s, 1);
+            if (!rcj && g_jit >= 2) rcj = jit_dry_pass(s, 2);
             if (rcj) return rcj;
         }
         s->jit_missing = s->jit_used = 0;

@@ -570,7 +570,7 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, unsigned char* sm
 #ifdef DMB_JIT
     constexpr int k = DMB_J_K, A_swz_mode = DMB_J_SWZ, A_tma_load = DMB_J_TMA_LOAD, A_tma_store = DMB_J_TMA_STORE, A_n_stars = DMB_J_N_STARS,
                   A_n_rounds = DMB_J_N_ROUNDS, A_n_groups = DMB_J_N_GROUPS, A_ops_bytes = DMB_J_OPS_BYTES, A_direct = DMB_J_DIRECT,
-                  A_half_enum = DMB_J_HALF_ENUM, A_peer = DMB_J_PEER, A_tma_prefetch = 0;
+                  A_half_enum = DMB_J_HALF_ENUM, A_peer = DMB_J_PEER, A_tma_prefetch = DMB_J_TMA_PREFETCH;
 #else
     const int k = a.k, A_swz_mode = a.swz_mode, A_tma_load = a.tma_load, A_tma_store = a.tma_store, A_n_stars = a.n_stars,
               A_n_rounds = a.n_rounds, A_n_groups = a.n_groups, A_ops_bytes = a.ops_bytes, A_direct = a.direct.enabled,
@@ -655,6 +655,31 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, unsigned char* sm
     }
     const double2* __restrict__ gin = reinterpret_cast<const double2*>(a.in);
     double2* __restrict__ gout = reinterpret_cast<double2*>(a.out);
+    // star prologue inputs of thread t (8 lanes per star: its share of the partner phases and of the w table).  The specialised
+    // kernels have registers to spare and keep them across the whole sweep when one pass of the CTA covers every star; the
+    // interpreter kernels re-read them per tile (L1 hits, but a dependent global-load latency in every tile's prologue)
+    constexpr int kStarQ = (kMaxStarOut + 7) / 8;
+#ifdef DMB_JIT
+    constexpr bool star_hoist = DMB_HAS(RC_STAR) && A_n_stars * 8 <= NT;
+#else
+    constexpr bool star_hoist = false;
+#endif
+    double2 h_wv[kStarW / 8], h_fj[kStarQ];
+    int h_bj[kStarQ];
+    auto star_inputs = [&](int i, bool on, double2 (&wv)[kStarW / 8], int (&bj)[kStarQ], double2 (&fj)[kStarQ]) {
+        const DevStar* st = a.stars + (on ? (i >> 3) : 0);
+        // (bit[] is padded with 63 and phi[] with 1 up to kMaxStarOut: every load is independent)
+#pragma unroll
+        for (int q = 0; q < kStarW / 8; q++) wv[q] = on ? __ldg(reinterpret_cast<const double2*>(st->w) + (i & 7) + 8 * q) : make_double2(1.0, 0.0);
+#pragma unroll
+        for (int q = 0; q < kStarQ; q++)
+        {
+            const int j = (i & 7) + 8 * q;
+            bj[q] = on && j < kMaxStarOut ? __ldg(st->bit + j) : 63;
+            fj[q] = on && j < kMaxStarOut ? __ldg(reinterpret_cast<const double2*>(st->phi) + j) : make_double2(1.0, 0.0);
+        }
+    };
+    if (star_hoist) star_inputs(t, t < A_n_stars * 8, h_wv, h_bj, h_fj);
     __syncthreads(); // program tables visible
 
     for (unsigned long long tile_id = blockIdx.x; tile_id < a.n_tiles; tile_id += gridDim.x)
@@ -728,27 +753,21 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, unsigned char* sm
             {
                 const int i = i0 + t;
                 const bool on = i < A_n_stars * 8;
-                const DevStar* st = a.stars + (on ? (i >> 3) : 0);
-                // (bit[] is padded with 63 and phi[] with 1 up to kMaxStarOut: every load below is independent)
                 double2 acc = make_double2(1.0, 0.0);
-                double2 wv[kStarW / 8]; // (in flight with the rest)
-#pragma unroll
-                for (int q = 0; q < kStarW / 8; q++) wv[q] = on ? __ldg(reinterpret_cast<const double2*>(st->w) + (i & 7) + 8 * q) : acc;
-                if (on)
+                double2 wv[kStarW / 8], fj[kStarQ];
+                int bj[kStarQ];
+                if (star_hoist)
                 {
-                    int bj[(kMaxStarOut + 7) / 8];
-                    double2 fj[(kMaxStarOut + 7) / 8];
 #pragma unroll
-                    for (int q = 0; q < (kMaxStarOut + 7) / 8; q++)
-                    {
-                        const int j = (i & 7) + 8 * q;
-                        bj[q] = j < kMaxStarOut ? __ldg(st->bit + j) : 63;
-                        fj[q] = j < kMaxStarOut ? __ldg(reinterpret_cast<const double2*>(st->phi) + j) : make_double2(1.0, 0.0);
-                    }
+                    for (int q = 0; q < kStarW / 8; q++) wv[q] = h_wv[q];
 #pragma unroll
-                    for (int q = 0; q < (kMaxStarOut + 7) / 8; q++)
-                        if ((full >> bj[q]) & 1ull) acc = cmul(acc, fj[q]);
+                    for (int q = 0; q < kStarQ; q++) { bj[q] = h_bj[q]; fj[q] = h_fj[q]; }
                 }
+                else star_inputs(i, on, wv, bj, fj);
+                // (a lane that is not `on` holds bit 63 / phase 1 everywhere: the full index never has bit 63 set)
+#pragma unroll
+                for (int q = 0; q < kStarQ; q++)
+                    if ((full >> bj[q]) & 1ull) acc = cmul(acc, fj[q]);
 #pragma unroll
                 for (int m = 1; m < 8; m <<= 1)
                 {
@@ -787,7 +806,24 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, unsigned char* sm
                 const unsigned long long nb = a.base_in[0][(unsigned)next_id & 127u] | a.base_in[1][(unsigned)(next_id >> 7) & 127u] |
                                               a.base_in[2][(unsigned)(next_id >> 14) & 127u];
                 const int he = A_half_enum;
-                if (it == 0) mbar_expect_tx(bar_u32, 16u * tile_elems);
+                if (it == 0)
+                {
+                    mbar_expect_tx(bar_u32, 16u * tile_elems);
+                    // L2 prefetch of the tile AFTER the next one: its load (one tile time from now) then finds it in L2 -- the
+                    // last round alone is too short to cover the DRAM latency of the load it shadows
+                    const unsigned long long pf_id = next_id + gridDim.x;
+                    if (A_tma_prefetch && pf_id < a.n_tiles)
+                    {
+                        const unsigned long long pb = a.base_in[0][(unsigned)pf_id & 127u] | a.base_in[1][(unsigned)(pf_id >> 7) & 127u] |
+                                                      a.base_in[2][(unsigned)(pf_id >> 14) & 127u];
+                        for (int j = 0; j < a.tma.n_copies; j++)
+                        {
+                            int c[5];
+                            tma_coords(a.tma, pb | a.tma.enum_off[j], c);
+                            tma_prefetch_5d(&a.tmap_in, c[0], c[1], c[2], c[3], c[4]);
+                        }
+                    }
+                }
                 for (int j = 0; j < a.tma.n_copies; j++)
                 {
                     if (he >= 0 ? ((j >> he) & 1) != it : !last_it) continue;

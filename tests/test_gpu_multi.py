@@ -167,6 +167,31 @@ def test_single_process_group_matches_oracle(dm, oracle_mod, world, n):
     del sim
 
 
+@pytest.mark.parametrize("world,n", [(2, 9), (4, 9), (8, 10)])
+def test_group_on_specialised_kernels(dm, oracle_mod, world, n):
+    """The run-time specialised kernels (csrc/jit.cu) on a sharded state: local sweeps and the fused remap sweep whose
+    stores go to the peers' shards, forced on at a size the oracle checks in full."""
+    _need(world)
+    from helpers import random_gates
+    gates = random_gates(n, 60, np.random.default_rng(90 + n + world))
+    dm.set_option("jit", 2); dm.set_option("jit_min_bits", 0)
+    try:
+        sim = dm.Simulation(n, world)
+        for g in gates:
+            sim.append(dm.Gate(g[0], *(list(g[1]) + [0] * (5 - len(g[1]))), theta=g[2], phi=g[3], lam=g[4],
+                               matrix=g[5] if len(g) > 5 else None))
+        sim.upload()
+        sim.run()
+        assert sim.last_stats["n_exchanges"] >= 1
+        assert dm.query("jit_sweeps", sim._h) == world * sim.last_stats["n_sweeps"] and dm.query("jit_pending", sim._h) == 0
+        re, im = oracle_mod.Oracle(n).sim(gates).dm()
+        gre, gim = sim.get_dm()
+        assert max(np.abs(gre - re).max(), np.abs(gim - im).max()) < 1e-12
+        del sim
+    finally:
+        dm.set_option("jit", 1); dm.set_option("jit_min_bits", 24)
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_reference_example_runs_on_n_gpus(dm, world, tmp_path):
     """examples/adder_n10.cpp (the reference's example/adder_n10_nvgpu_omp.cu with one include changed) as `./adder P`:
