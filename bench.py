@@ -441,6 +441,7 @@ def main():
     ap.add_argument("--cpu-full-size", action="store_true", help="reference arm: run the named size itself (n = 15: 64 GiB, minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip extra_workloads / strong_scaling / parity (quick A/B runs)")
+    ap.add_argument("--no-first-call", action="store_true", help="skip the first_call / continued_state legs (profiling runs)")
     ap.add_argument("--jit", type=int, default=int(os.environ.get("DMB_JIT", "2")),
                     help="run-time specialised sweep kernels: 2 wait for the compiler (default), 1 tiered, 0 interpreter kernels only")
     args = ap.parse_args()
@@ -473,7 +474,7 @@ def main():
         parity["small"] = parity_small(job, dm)
 
     sampler = ClockSampler(job.local_rank) if rank == 0 else None
-    m = measure(job, dm, args.workload, args.steps, args.warmup, sampler=sampler, keep=True, first_call=True)
+    m = measure(job, dm, args.workload, args.steps, args.warmup, sampler=sampler, keep=True, first_call=not args.no_first_call)
     if extras and world > 1:
         parity["workload"] = parity_workload(job, m)
     m.pop("sim", None)

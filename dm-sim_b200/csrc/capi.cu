@@ -71,12 +71,13 @@ static void init_options()
     if (const char* e = getenv("DMB_DENSE2_LU")) set_sweep_dense2_lu(atoi(e) != 0);
     if (const char* e = getenv("DMB_GRID_PER_SM")) g_grid_per_sm = atoi(e);
     if (const char* e = getenv("DMB_DUAL")) set_sweep_dual(atoi(e) != 0);
-    if (const char* e = getenv("DMB_SMALL_STATE_BITS")) g_opt.small_state_bits = atoi(e);
     if (const char* e = getenv("DMB_PERSISTENT")) g_persistent = atoi(e);
+    g_opt.small_state_bits = g_persistent ? 20 : 0;
     if (const char* e = getenv("DMB_JIT")) g_jit = atoi(e);
     if (const char* e = getenv("DMB_JIT_MIN_BITS")) g_jit_min_bits = atoi(e);
     if (const char* e = getenv("DMB_PLAN_CACHE")) g_plan_cache = atoi(e);
     if (const char* e = getenv("DMB_DIRECT_STORE")) set_sweep_direct_store(atoi(e) != 0);
+    if (const char* e = getenv("DMB_HEAVY_LAST")) set_sweep_heavy_last(atoi(e) != 0);
     if (const char* e = getenv("DMB_TMA_PREFETCH")) g_tma_prefetch = atoi(e);
 }
 
@@ -473,8 +474,12 @@ int dmb_set_option(const char* name, int64_t value)
     else if (!strcmp(name, "dense2_lu")) set_sweep_dense2_lu(value != 0);
     else if (!strcmp(name, "tma_prefetch")) g_tma_prefetch = (int)value;
     else if (!strcmp(name, "direct_store")) set_sweep_direct_store(value != 0);
-    else if (!strcmp(name, "small_state_bits")) g_opt.small_state_bits = (int)value;
-    else if (!strcmp(name, "persistent")) g_persistent = (int)value;
+    else if (!strcmp(name, "heavy_last")) set_sweep_heavy_last(value != 0);
+    else if (!strcmp(name, "persistent"))
+    {
+        g_persistent = (int)value;
+        g_opt.small_state_bits = value ? 20 : 0; // (the cooperative executor runs sweeps with the plain tile I/O only)
+    }
     else if (!strcmp(name, "jit")) g_jit = (int)value;
     else if (!strcmp(name, "jit_min_bits")) g_jit_min_bits = (int)value;
     else if (!strcmp(name, "plan_cache")) g_plan_cache = (int)value;
@@ -1824,6 +1829,12 @@ int64_t dmb_jit_source(int n_qubits, int world_size, const dmb_gate* gates, size
     {
         return fail(DMB_ESTATE, e.what());
     }
+}
+
+int dmb_device_synchronize(void)
+{
+    CU(cudaDeviceSynchronize());
+    return DMB_OK;
 }
 
 // Counters of the run-time compiler (process-wide) and of handle h's last dmb_run (h may be NULL for the process-wide ones):

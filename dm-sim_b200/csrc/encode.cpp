@@ -16,6 +16,8 @@ void set_sweep_direct_store(bool on) { g_direct_store = on; }
 static bool g_dense2_lu = true;
 void set_sweep_dense2_lu(bool on) { g_dense2_lu = on; }
 bool sweep_dense2_lu() { return g_dense2_lu; }
+static bool g_heavy_last = false; // (measured on B200, r2u: qft_n15 23.1 vs 21.6 ms -- the diagonals of a round planned from the back cannot be deferred and merged; random_c1c2_n15 344 vs 347 ms)
+void set_sweep_heavy_last(bool on) { g_heavy_last = on; }
 void set_sweep_tma_box_bits(int bits) { g_tma_box_bits = bits < 3 ? 3 : (bits > kMaxTileBits ? kMaxTileBits : bits); }
 int sweep_tma_box_bits() { return g_tma_box_bits; }
 namespace
@@ -214,14 +216,17 @@ inline bool is_cp(const TileOp& t) { return t.cls == CLS_CPHASE; }
 // gain (how much of the remaining list becomes executable: per-bit program order, diagonal ops hop over skipped
 // diagonal ops), run everything that fits, repeat.  A controlled phase (CLS_CPHASE) runs as soon as ONE of its bits is
 // a register bit.  Sweeps containing SRN (a full barrier) keep strict list order.
-std::vector<RoundPlan> plan_rounds(const Sweep& sw, int R)
+// `backward`: the same greedy choice made from the END of the list (every rule above is symmetric under reversal): the round
+// built first -- the fullest one -- then runs LAST and the leftovers first.
+static std::vector<RoundPlan> plan_rounds_dir(const Sweep& sw, int R, bool backward)
 {
     const int n = (int)sw.ops.size();
     std::vector<char> done(n, 0), diag(n, 0);
     bool has_srn = false;
+    auto op_at = [&](int i) -> const TileOp& { return sw.ops[backward ? n - 1 - i : i]; };
     for (int i = 0; i < n; i++)
     {
-        const TileOp& t = sw.ops[i];
+        const TileOp& t = op_at(i);
         if (t.cls == CLS_SRN1) has_srn = true;
         else if (is_cp(t)) diag[i] = 1;
         else
@@ -231,14 +236,15 @@ std::vector<RoundPlan> plan_rounds(const Sweep& sw, int R)
         }
     }
     auto bits_of = [&](int i) { // the op's bits INSIDE the tile
-        unsigned m = 1u << sw.ops[i].j0;
-        if (sw.ops[i].nb == 2 && sw.ops[i].j1 >= 0) m |= 1u << sw.ops[i].j1;
+        unsigned m = 1u << op_at(i).j0;
+        if (op_at(i).nb == 2 && op_at(i).j1 >= 0) m |= 1u << op_at(i).j1;
         return m;
     };
     std::vector<RoundPlan> rounds;
     int first = 0, left = n;
     if (has_srn)
     {
+        if (backward) return rounds; // (SRN sweeps keep strict list order: forward only)
         while (first < n)
         {
             RoundPlan rp;
@@ -259,7 +265,7 @@ std::vector<RoundPlan> plan_rounds(const Sweep& sw, int R)
         {
             if (done[i]) continue;
             const unsigned m = bits_of(i);
-            const bool fits = is_cp(sw.ops[i]) ? (m & rb) != 0 : (m & ~rb) == 0;
+            const bool fits = is_cp(op_at(i)) ? (m & rb) != 0 : (m & ~rb) == 0;
             const bool ok = fits && !(m & hard) && (diag[i] || !(m & soft));
             if (ok)
             {
@@ -290,7 +296,7 @@ std::vector<RoundPlan> plan_rounds(const Sweep& sw, int R)
                 if (done[i]) continue;
                 looked++;
                 const unsigned m = bits_of(i);
-                if (is_cp(sw.ops[i]))
+                if (is_cp(op_at(i)))
                 {
                     if (m & rb) continue;
                     for (int p = 0; p < 16; p++)
@@ -318,13 +324,46 @@ std::vector<RoundPlan> plan_rounds(const Sweep& sw, int R)
         for (int i : rp.ops)
         {
             done[i] = 1;
-            rp.touched |= is_cp(sw.ops[i]) ? (bits_of(i) & rb) : bits_of(i);
+            rp.touched |= is_cp(op_at(i)) ? (bits_of(i) & rb) : bits_of(i);
             left--;
         }
         if (rp.ops.empty()) break; // cannot happen: the first pending op always fits a fresh round
         rounds.push_back(rp);
     }
+    if (backward)
+    {
+        // back to list indices and execution order
+        std::reverse(rounds.begin(), rounds.end());
+        for (RoundPlan& rp : rounds)
+        {
+            for (int& i : rp.ops) i = n - 1 - i;
+            std::reverse(rp.ops.begin(), rp.ops.end());
+        }
+    }
     return rounds;
+}
+
+// Forward plan, or (option "heavy_last", off by default) the backward one when it needs no more rounds and ends on a heavier
+// round.  The last round of a full-size tile shadows the load of the CTA's next tile (DevDirect): on qft_n15 the sweep whose last
+// round is its fullest runs at 0.86 of the HBM peak, the two that end on a one-op leftover round at 0.69 -- but rounds planned
+// from the back get their controlled phases BEFORE the butterflies of their bits, where the encoder's deferred-diagonal merging
+// (one star per round, RC_QFT2) does not apply, and the extra device ops cost more than the better overlap wins.
+std::vector<RoundPlan> plan_rounds(const Sweep& sw, int R)
+{
+    std::vector<RoundPlan> fwd = plan_rounds_dir(sw, R, false);
+    if (!g_heavy_last || fwd.size() < 2) return fwd;
+    std::vector<RoundPlan> bwd = plan_rounds_dir(sw, R, true);
+    if (bwd.empty() || bwd.size() > fwd.size()) return fwd;
+    auto weight = [&](const RoundPlan& rp) {
+        double w = 0;
+        for (int i : rp.ops) w += is_cp(sw.ops[i]) ? 2 : (sw.ops[i].nb == 2 ? 16 : 4); // (rough FP64 cost per element)
+        return w;
+    };
+    size_t nf = 0, nb = 0;
+    for (const RoundPlan& rp : fwd) nf += rp.ops.size();
+    for (const RoundPlan& rp : bwd) nb += rp.ops.size();
+    if (nf != nb) return fwd; // (cannot happen: both cover every op)
+    return (bwd.size() < fwd.size() || weight(bwd.back()) > weight(fwd.back())) ? bwd : fwd;
 }
 
 // H gates of a sweep: s*[[1,1],[1,-1]] becomes the payload-free butterfly RC_HAD (2 FP64 instructions per pair and

@@ -87,8 +87,8 @@ struct PlanOptions
     int max_cphase = 160;    // controlled phases per sweep (<= kMaxStarsPerSweep: each may need its own star slot)
     bool cphase = true;      // schedule controlled phases with only one bit in the tile (CLS_CPHASE)
     bool tma = true;         // full-size tiles (k == 12) are loaded / stored by TMA (128-byte hardware swizzle)
-    int small_state_bits = 20; // shards of <= 2^20 elements (16 MiB: they stay in L2) keep the plain tile I/O; with no exchange
-                               // all their sweeps run as ONE cooperative launch
+    int small_state_bits = 0;  // shards of <= 2^small_state_bits elements keep the plain tile I/O (no TMA): set to 20 (16 MiB, L2
+                               // resident) by the option "persistent", whose one-launch cooperative executor needs it
     int tma_box_bits = 10;   // largest TMA box: 2^10 elements = 16 KiB (the rest of the tile bits: separate copies)
 };
 

@@ -16,6 +16,7 @@ user-defined gates may be used inside their bodies, and several statements may s
 """
 from __future__ import annotations
 
+import ast
 import math
 import re
 
@@ -57,10 +58,33 @@ _SAFE = {"pi": math.pi, "sin": math.sin, "cos": math.cos, "tan": math.tan, "exp"
          "sqrt": math.sqrt, "asin": math.asin, "acos": math.acos, "atan": math.atan}
 
 
+_BINOPS = {ast.Add: lambda a, b: a + b, ast.Sub: lambda a, b: a - b, ast.Mult: lambda a, b: a * b,
+           ast.Div: lambda a, b: a / b, ast.Pow: lambda a, b: a ** b}
+
+
+def _eval_node(node, names):
+    """Arithmetic over numbers, the names in `names` and calls of the functions in it -- nothing else (the text comes from
+    an untrusted .qasm file: no attribute access, subscripts, comprehensions, lambdas ...)."""
+    if isinstance(node, ast.Expression):
+        return _eval_node(node.body, names)
+    if isinstance(node, ast.Constant) and type(node.value) in (int, float):
+        return node.value
+    if isinstance(node, ast.Name) and node.id in names and not callable(names[node.id]):
+        return names[node.id]
+    if isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.UAdd, ast.USub)):
+        v = _eval_node(node.operand, names)
+        return -v if isinstance(node.op, ast.USub) else +v
+    if isinstance(node, ast.BinOp) and type(node.op) in _BINOPS:
+        return _BINOPS[type(node.op)](_eval_node(node.left, names), _eval_node(node.right, names))
+    if isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and callable(names.get(node.func.id)) and not node.keywords:
+        return names[node.func.id](*[_eval_node(a, names) for a in node.args])
+    raise ValueError(f"unsupported syntax: {ast.dump(node)[:60]}")
+
+
 def _eval_raw(expr: str, env=None):
     """the Python value of a parameter expression (int stays int: the reference prints str(eval(expr)))"""
     try:
-        v = eval(expr, {"__builtins__": {}}, {**_SAFE, **(env or {})})
+        v = _eval_node(ast.parse(expr.strip(), mode="eval"), {**_SAFE, **(env or {})})
         float(v)
         return v
     except Exception as e:  # noqa: BLE001
@@ -89,7 +113,28 @@ def _split_args(s: str):
     return out
 
 
-_STMT = re.compile(r"^\s*([A-Za-z_][A-Za-z0-9_]*)\s*(?:\((.*?)\))?\s*(.*)$", re.S)
+_HEAD = re.compile(r"^\s*([A-Za-z_][A-Za-z0-9_]*)\s*", re.S)
+
+
+def _split_stmt(s: str):
+    """(name, parameter text or None, rest) of `name(params) rest`; the parameter list is cut at the MATCHING parenthesis,
+    so that nested ones (`u1(-(pi/4)) q[0]`) parse -- the reference's non-greedy regex stops at the first `)`."""
+    m = _HEAD.match(s)
+    if not m:
+        return None
+    name, i = m.group(1), m.end()
+    par = None
+    if i < len(s) and s[i] == "(":
+        depth = 0
+        for j in range(i, len(s)):
+            depth += s[j] == "("
+            depth -= s[j] == ")"
+            if depth == 0:
+                par, i = s[i + 1:j], j + 1
+                break
+        else:
+            return None
+    return name, par, s[i:].strip()
 
 
 class Program:
@@ -125,10 +170,10 @@ def parse(text: str) -> Program:
         s = s.strip()
         if not s:
             return
-        m = _STMT.match(s)
+        m = _split_stmt(s)
         if not m:
             raise QasmError(f"cannot parse statement {s!r}")
-        op, par, rest = m.group(1), m.group(2), m.group(3).strip()
+        op, par, rest = m
         if op in OTHER_KEYS:
             return
         if op == "qreg":
@@ -195,8 +240,10 @@ def _define_gate(prog: Program, head: str, body: str):
         stmt = stmt.strip()
         if not stmt:
             continue
-        mm = _STMT.match(stmt)
-        op, par, rest = mm.group(1), mm.group(2), mm.group(3).strip()
+        mm = _split_stmt(stmt)
+        if not mm:
+            raise QasmError(f"cannot parse statement {stmt!r} in a gate body")
+        op, par, rest = mm
         if op == "barrier":
             continue
         low = op.lower()
@@ -312,7 +359,7 @@ def _fmt_param(expr: str, symbols=()):
         return str(_eval_raw(expr))
     except QasmError:
         if any(re.search(r"\b%s\b" % re.escape(s), expr) for s in symbols):
-            return expr.replace("pi", str(math.pi)) if False else expr
+            return expr
         raise
 
 

@@ -179,6 +179,9 @@ int dmb_query(dmb_handle h /* may be NULL */, const char* name, double* value);
  * "tile_bits" (<= 12), "low_bits" (contiguous run = 2^low_bits elements), "graph" (0/1). */
 int dmb_set_option(const char* name, int64_t value);
 
+/* cudaDeviceSynchronize() on the current device (for host-only users of the C++ header: gpu_timer). */
+int dmb_device_synchronize(void);
+
 const char* dmb_last_error(void);
 const char* dmb_version(void);
 

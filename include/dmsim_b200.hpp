@@ -110,6 +110,69 @@ typedef struct CPU_TIMER
     double start, stop;
 } cpu_timer;
 
+#define CHECK_NULL_POINTER(X) DMSim::__checkNullPointer(__FILE__, __LINE__, (void**)&(X))
+inline void __checkNullPointer(const char* file, const int line, void** ptr)
+{
+    if ((*ptr) == NULL)
+    {
+        fprintf(stderr, "Error: NULL pointer at %s:%i.\n", file, line);
+        exit(-1);
+    }
+}
+#if defined(__CUDACC__) || defined(__CUDA_RUNTIME_H__)
+// compiled by nvcc / after <cuda_runtime.h>, like the reference's users: the CUDA helpers of util_nvgpu.cuh:29-136 as they are there
+#define cudaSafeCall(err) DMSim::__cudaSafeCall(err, __FILE__, __LINE__)
+inline void __cudaSafeCall(cudaError_t err, const char* file, const int line)
+{
+    if (cudaSuccess != err)
+    {
+        fprintf(stderr, "cudaSafeCall() failed at %s:%i : %s\n", file, line, cudaGetErrorString(err));
+        exit(-1);
+    }
+}
+#define cudaCheckError() DMSim::__cudaCheckError(__FILE__, __LINE__)
+inline void __cudaCheckError(const char* file, const int line)
+{
+    cudaError_t err = cudaGetLastError();
+    if (cudaSuccess == err) err = cudaDeviceSynchronize();
+    if (cudaSuccess != err)
+    {
+        fprintf(stderr, "cudaCheckError() failed at %s:%i : %s\n", file, line, cudaGetErrorString(err));
+        exit(-1);
+    }
+}
+#define SAFE_ALOC_HOST(X, Y) cudaSafeCall(cudaMallocHost((void**)&(X), (Y)));
+#define SAFE_ALOC_GPU(X, Y) cudaSafeCall(cudaMalloc((void**)&(X), (Y)));
+#define SAFE_FREE_HOST(X) if ((X) != NULL) { cudaSafeCall(cudaFreeHost((X))); (X) = NULL; }
+#define SAFE_FREE_GPU(X) if ((X) != NULL) { cudaSafeCall(cudaFree((X))); (X) = NULL; }
+typedef struct GPU_Timer
+{
+    GPU_Timer() { cudaSafeCall(cudaEventCreate(&this->start)); cudaSafeCall(cudaEventCreate(&this->stop)); }
+    ~GPU_Timer() { cudaEventDestroy(this->start); cudaEventDestroy(this->stop); }
+    void start_timer() { cudaSafeCall(cudaEventRecord(this->start)); }
+    void stop_timer() { cudaSafeCall(cudaEventRecord(this->stop)); }
+    double measure()
+    {
+        cudaSafeCall(cudaEventSynchronize(this->stop));
+        float ms = 0;
+        cudaSafeCall(cudaEventElapsedTime(&ms, this->start, this->stop));
+        return (double)ms;
+    }
+    cudaEvent_t start, stop;
+} gpu_timer;
+#else
+// host-only build (g++, no CUDA headers): gpu_timer keeps its name and meaning -- device work between start_timer() and
+// stop_timer() -- by synchronising the device through the C ABI around a host clock
+typedef struct GPU_Timer
+{
+    GPU_Timer() { start = stop = 0.0; }
+    void start_timer() { dmb_device_synchronize(); start = get_cpu_timer(); }
+    void stop_timer() { dmb_device_synchronize(); stop = get_cpu_timer(); }
+    double measure() { return stop - start; }
+    double start, stop;
+} gpu_timer;
+#endif
+
 #define DMSIM_CHECK(call)                                                                     \
     do                                                                                        \
     {                                                                                         \

@@ -24,22 +24,22 @@ def jit(dm):
         for k, v in kw.items():
             dm.set_option(k, v)
     yield set_
-    dm.set_option("jit", 1); dm.set_option("jit_min_bits", 24); dm.set_option("small_state_bits", 20)
-    dm.set_option("persistent", 1); dm.set_option("graph", 1)
+    dm.set_option("jit", 1); dm.set_option("jit_min_bits", 24); dm.set_option("tma", 1)
+    dm.set_option("persistent", 0); dm.set_option("graph", 1)
 
 
-@pytest.mark.parametrize("n,small", [(6, 20), (8, 0), (9, 20), (10, 0)])
+@pytest.mark.parametrize("n,small", [(6, 1), (8, 1), (9, 0), (10, 1)])
 def test_specialised_kernels_match_oracle_and_interpreter(dm, oracle_mod, jit, n, small):
     """Random circuits over every op: specialised == oracle (1e-12) and == the interpreter kernels (same op bodies, same
-    order: 1e-14).  small = 0: full-size tiles go through TMA (+ direct store of the last round); 20: plain tile I/O."""
+    order: 1e-14).  small = 1: full-size tiles go through TMA (+ direct store of the last round); 0: plain tile I/O."""
     rng = np.random.default_rng(500 + n)
     gates = random_gates(n, 70, rng)
     ore, oim = oracle_mod.Oracle(n).sim(gates).dm()
-    jit(0, small_state_bits=small, persistent=0)
+    jit(0, tma=small, persistent=0)
     ref = run_gpu(dm, n, gates)
     assert dm.query("jit_sweeps", ref._h) == 0
     rre, rim = ref.get_dm()
-    jit(2, small_state_bits=small, persistent=0)
+    jit(2, tma=small, persistent=0)
     before = dm.query("jit_failed")
     sim = run_gpu(dm, n, gates)
     assert dm.query("jit_failed") == before
@@ -71,7 +71,7 @@ def test_tiered_execution_switches_to_specialised_kernels(dm, oracle_mod, jit):
     captured graph is refreshed), with the same result, and a second circuit of the same STRUCTURE (other angles) reuses
     the kernels without compiling."""
     n = 9
-    jit(1, small_state_bits=0, persistent=0)
+    jit(1, persistent=0)
 
     def circuit(scale):
         rng = np.random.default_rng(77)

@@ -68,7 +68,7 @@ def test_random_circuits_every_geometry(dm, oracle_mod, opts, n, world, o):
 def test_full_size_tiles_tma_addressing(dm, oracle_mod, opts, n, world, o):
     """k = 12 tiles: TMA boxes (5-D tensor view of the shard, enumerated copies), the hardware 128-byte swizzle and the
     lane-bit choice that goes with it -- walked by the kernel emulator exactly as the device does."""
-    opts(small_state_bits=0, **o)  # (states this small would otherwise keep the plain tile I/O)
+    opts(**o)
     try:
         rng = np.random.default_rng(77 + world)
         gates = random_gates(n, 60, rng, exclude=("SRN",))
@@ -87,7 +87,7 @@ def test_full_size_tiles_tma_addressing(dm, oracle_mod, opts, n, world, o):
                     assert st["dev"]["tma_store"] == int(st["in_pos"] == st["out_pos"] and not st["out_of_place"])
         assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - to_complex(re, im)).max() < TOL
     finally:
-        dm.set_option("tma", 1); dm.set_option("tma_box_bits", 10); dm.set_option("small_state_bits", 20)
+        dm.set_option("tma", 1); dm.set_option("tma_box_bits", 10)
 
 
 def test_each_op_alone(dm, oracle_mod):
@@ -214,6 +214,12 @@ def test_deferred_diagonals_and_new_device_ops(dm, oracle_mod):
     circuits = importlib.import_module("dm-sim_b200.circuits")
     RC = dict(DIAGR=7, RR=8, STAR=10, HAD=11, DIAGP=12, CP2=13)
     rng = np.random.default_rng(5)
+    # (the shapes asserted below are those of rounds planned from the front of the op list, the default)
+    dm.set_option("heavy_last", 0)
+    _deferred_diagonals_body(dm, oracle_mod, circuits, RC, rng)
+
+
+def _deferred_diagonals_body(dm, oracle_mod, circuits, RC, rng):
 
     def codes(plan):
         return [o["code"] for st in plan["steps"] if st["kind"] == "sweep" for o in st["dev"]["ops"]]
@@ -335,3 +341,19 @@ def test_hot_bits_move_to_the_low_tile_positions(dm, oracle_mod, opts, world):
     finally:
         dm.set_option("hot_low", 1)
     assert p1["n_sweeps"] < p0["n_sweeps"]
+
+
+@pytest.mark.parametrize("family,n", [("qft", 7), ("random", 7), ("allops", 6)])
+def test_rounds_planned_from_the_back(dm, oracle_mod, family, n):
+    """Option heavy_last: a sweep's rounds chosen from the END of its op list (the fullest round runs last) give the same state."""
+    import importlib
+    circuits = importlib.import_module("dm-sim_b200.circuits")
+    rng = np.random.default_rng(123)
+    gates = circuits.qft(n) if family == "qft" else (circuits.random_c1c2(n, 60, seed=4) if family == "random" else random_gates(n, 70, rng, exclude=("SRN",)))
+    re, im = oracle_mod.Oracle(n).sim(gates).dm()
+    dm.set_option("heavy_last", 1)
+    try:
+        plan = dm.plan_json(n, 1, gates)
+    finally:
+        dm.set_option("heavy_last", 0)
+    assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - to_complex(re, im)).max() < TOL

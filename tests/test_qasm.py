@@ -207,3 +207,18 @@ def test_cplus_translator_against_the_reference(tmp_path, name):
     assert f"Number of qubits: {stats['n_qubits']}" in ref_printed
     assert f"Number of basic gates: {stats['basic_gates']}" in ref_printed
     assert f"Number of cnot gates: {stats['cnot_gates']}" in ref_printed
+
+
+def test_parameter_expressions_are_not_python_eval():
+    """Parameter text comes from an untrusted file: arithmetic, pi and the qelib functions only; nested parentheses in a
+    parameter list parse (the reference's non-greedy regex stops at the first ')')."""
+    qasm = importlib.import_module("dm-sim_b200.qasm")
+    src = ('OPENQASM 2.0;\ninclude "qelib1.inc";\ngate foo(a,b) x { u1((a-b)/2) x; }\nqreg q[2];\n'
+           'u1(-(pi/4)) q[0];\nfoo(pi, sin(pi/2)) q[1];\n')
+    n, gates = qasm.load(src)
+    assert n == 2 and [g[0] for g in gates] == ["U1", "U1"]
+    lam = [g[4] if g[4] else g[2] for g in gates]
+    assert abs(abs(lam[0]) - np.pi / 4) < 1e-15 and abs(abs(lam[1]) - (np.pi - 1) / 2) < 1e-15
+    for bad in ("().__class__", "__import__('os')", "[1][0]", "pi.real", "(lambda: 1)()"):
+        with pytest.raises(qasm.QasmError):
+            qasm._eval_raw(bad)

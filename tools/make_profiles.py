@@ -41,8 +41,8 @@ for rep in sorted(glob.glob(os.path.join(G, f"{tag}_sweep_full_*.ncu-rep"))):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
-    txt = [f"# ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 3 -c 3 python bench.py --workload {wl} --steps 1 --warmup 1 --no-cpu-baseline",
-           f"# round 1 ({tag}); {len(data)} consecutive sweep_kernel launches of {wl}; numbers are per launch (cold caches, serialised replays)"]
+    txt = [f"# ncu --set full --clock-control none --import-source on -k regex:<sweep kernel> -s 3 -c 3 python bench.py --workload {wl} --steps 1 --warmup 1 --no-cpu-baseline --no-extra",
+           f"# ({tag}); {len(data)} consecutive sweep_kernel launches of {wl}; numbers are per launch (cold caches, serialised replays)"]
     stall = [k for k in hdr if "issue_stalled" in k and k.endswith("per_issue_active.ratio") and "not_issued" not in k]
     tot = []
     for li, r in enumerate(data):
@@ -73,19 +73,20 @@ def row(d):
     r, e = d.get("roofline") or {}, d.get("e2e") or {}
     cfg = d.get("config", {})
     if d.get("impl") == "reference":
-        return f"| {cfg.get('workload')} (reference `dmsim_cpu_omp`, {d['cpu_baseline']['cores']} host threads) | {d['n_gpus']} | – | {d['ms_per_step']:.0f} | {d['value']:.2f} | – | – | – | {d['cpu_baseline']['sample']} |"
+        return f"| {cfg.get('workload')} (reference `dmsim_cpu_omp`, {d['cpu_baseline']['cores']} host threads) | {d['n_gpus']} | – | {d['ms_per_step']:.0f} | {d['value']:.2f} | – | – | – | – | {d['cpu_baseline']['sample']} |"
     res = (e.get("resident_state") or {}).get("ms_per_step")
+    jit = d.get("jit") or {}
+    ach = f"{r.get('bound', 'hbm')}: {r.get('achieved', 0):.1f} {r.get('unit', 'GB/s')} ({r.get('frac', 0):.3f})"
     return (f"| {cfg.get('workload')} | {d['n_gpus']} | {cfg.get('sweeps_per_step')} | {d['ms_per_step']:.2f} | {d['value']:.0f} | "
-            f"{r.get('achieved', 0):.0f} ({r.get('frac', 0):.3f}) | {e.get('ms_per_step', 0):.2f} ({e.get('value', 0):.0f}) | "
+            f"{ach} | {jit.get('sweeps_specialised', 0)}/{jit.get('sweeps_per_step', cfg.get('sweeps_per_step'))} | {e.get('ms_per_step', 0):.2f} ({e.get('value', 0):.0f}) | "
             f"{'' if res is None else format(res, '.2f')} | {(d.get('comm') or {}).get('GBps_per_direction') or ''} |")
 
-md = ["# profiles/ -- measured on B200 (round 1)", "",
-      "Every number here was printed by `bench.py` / `ncu` on a `gpurun` B200 box; nothing is taken under a profiler except",
-      "the ncu files themselves. `value` = device time of `dmb_run` on the DENSE resident state (CUDA events on the engine's",
-      "stream); `e2e` = wall clock of reset + circuit upload + run + diagonal readback from |0><0| (sparse start on, single",
-      "GPU); `resident e2e` = the same calls without the reset, on the dense state.", "",
-      "| workload | GPUs | sweeps/step | ms/step | gates/s | achieved GB/s (frac of measured HBM peak) | e2e ms (gates/s) | resident e2e ms | exchange GB/s per direction | file |",
-      "|---|---|---|---|---|---|---|---|---|---|"]
+md = ["# Bench lines under profiles/ (generated by tools/make_profiles.py; the narrative is in README.md)", "",
+      "`ms/step` = device time of `dmb_run` (CUDA events on the engine's stream), sparse start off; `achieved` is GB/s when the",
+      "binding floor is HBM and FMA-equivalent TFLOP/s when it is the FP64 pipe (`roofline.bound`); `e2e` = wall clock of reset +",
+      "circuit upload + run + diagonal readback from |0><0|; `jit` = sweeps of a step that ran on run-time specialised kernels.", "",
+      "| workload | GPUs | sweeps/step | ms/step | gates/s | bound: achieved (frac of the measured peak) | jit | e2e ms (gates/s) | resident e2e ms | exchange GB/s per direction | file |",
+      "|---|---|---|---|---|---|---|---|---|---|---|"]
 seen = set()
 for f in sorted(glob.glob(os.path.join(P, "*bench_lines*.jsonl"))):
     if "older_kernel" in f:
@@ -98,23 +99,8 @@ for f in sorted(glob.glob(os.path.join(P, "*bench_lines*.jsonl"))):
             if key not in seen:
                 seen.add(key)
                 md.append(row(d) + f" `{os.path.basename(f)}` |")
-md += ["", "Files:", ""]
-for f in sorted(os.listdir(P)):
-    if f != "README.md":
-        md.append(f"* `{f}`")
-md += ["", "`*_sweep_full_<workload>.txt`: per-launch key metrics of `ncu --set full --clock-control none --import-source on` on",
-       "consecutive `sweep_kernel` launches, then the executed SASS of the first launch by opcode and by basic block with the",
-       "stall reasons (tools/ncu_sass_summary.py, tools/ncu_blocks.py). `*_launches_*.csv`: the ncu launch list",
-       "(`--metrics gpu__time_duration.sum`) of `bench.py --steps 2 --warmup 1`. `ncu_traffic.json`: DRAM bytes per launch.",
-       "`r1_bench_lines_8gpu_nccl_path_older_kernel.jsonl`: the 8-GPU lines of an earlier session (NCCL exchange, sweep kernel",
-       "before this session's rewrite); 2- and 4-GPU lines are from this session (peer-memory remap).", "",
-       "`r1_bench_lines_1gpu.jsonl`, the launch list and the ncu captures belong to one run (tools/gpu_round.sh) taken before",
-       "the last two changes of the round; `r1_bench_lines_1gpu_final_code.jsonl` is the same bench on the final code:",
-       "`RC_QFT2` fusion (qft_n15 26.96 -> 26.57 ms) and hot bits in the low tile positions (bv_n15 4 -> 3 sweeps, 33.4 ->",
-       "29.4 ms; random_c1c2_n15 19 -> 15 sweeps, 389 -> 372 ms; adder_n10 4 -> 2 sweeps).  Fewer sweeps lower",
-       "`roofline.frac` (it counts sweeps x bytes / time) while the circuit gets faster."]
-open(os.path.join(P, "README.md"), "w").write("\n".join(md) + "\n")
-print("README.md rows:", len(seen))
+open(os.path.join(P, "TABLE.md"), "w").write("\n".join(md) + "\n")
+print("TABLE.md rows:", len(seen))
 for f in glob.glob(os.path.join(G, f"{tag}_launches_*.csv")):
     dst = os.path.join(P, os.path.basename(f).replace(tag, out, 1))
     open(dst, "w").write(open(f).read())
