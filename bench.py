@@ -310,6 +310,7 @@ def measure(job, dm, name, steps, warmup, world=None, sampler=None, e2e=True, ke
         # the same call sequence WITHOUT the reset: the circuit is re-uploaded and applied to the resident (dense) state,
         # so that no tile is skipped as still-zero
         dm.set_option("sparse", 0)
+        dm.set_option("jit", 1 if JIT_MODE else 0)  # (a continued state is planned anew every time: tiered, never waiting)
         sim.reset_dm()
         res_ms = []
         for i in range(1 + min(steps, 3)):
@@ -322,6 +323,7 @@ def measure(job, dm, name, steps, warmup, world=None, sampler=None, e2e=True, ke
             if i >= 1:
                 res_ms.append((time.perf_counter() - t1) * 1e3)
         e2e_res = sum(res_ms) / len(res_ms)
+        dm.set_option("jit", JIT_MODE)
         h2d = int(sim.last_stats["h2d_bytes"])
         # the same circuit set again with the plan cache ON (the engine's default): the host pipeline and the H2D of the
         # tables are skipped, the captured graph / parameter list is reused

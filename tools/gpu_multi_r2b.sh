@@ -1,7 +1,7 @@
 # Usage: tools/gpu_multi_r2b.sh TAG N : the specialised-kernel group test, then the default bench line of N GPUs
 TAG=${1:-r2s}; N=${2:-2}
 mkdir -p gpurun_out
-(time timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -k "specialised") > gpurun_out/${TAG}_pytest_multi.log 2>&1
+[ -n "$SKIP_TESTS" ] || (time timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -k "specialised") > gpurun_out/${TAG}_pytest_multi.log 2>&1
 tail -3 gpurun_out/${TAG}_pytest_multi.log
 (time timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3) > gpurun_out/${TAG}_bench_${N}gpu.json 2> gpurun_out/${TAG}_bench_${N}gpu.err
 tail -c 800 gpurun_out/${TAG}_bench_${N}gpu.err
