@@ -95,6 +95,7 @@ def lib():
     L.dmb_jit_source.argtypes = [i32, i32, vp, sz, vp, sz, i32, i32, ctypes.c_char_p, sz]
     L.dmb_jit_source.restype = ctypes.c_int64
     L.dmb_query.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]
+    L.dmb_jit_compile.argtypes = [i32, i32, vp, sz, vp, sz, i32, i32, i32]
     L.dmb_last_error.restype = ctypes.c_char_p
     L.dmb_version.restype = ctypes.c_char_p
     _lib = L
@@ -197,6 +198,17 @@ def jit_source(n_qubits, world_size, gates, sweep_index, peer=False):
     _check(min(0, int(L.dmb_jit_source(*args, buf, int(need)))))
     defines, program = buf.value.decode().split("//---- program\n", 1)
     return defines, program
+
+
+def jit_compile(n_qubits, world_size, gates, sweep_index, peer=False, wait=True) -> int:
+    """Builds the specialised kernel of one sweep with the library's run-time compiler (no GPU needed): 1 built, 0 queued,
+    -1 failed, -2 no such sweep."""
+    rec, mats = gates if isinstance(gates, tuple) else pack_gates(gates)
+    rc = lib().dmb_jit_compile(n_qubits, world_size, rec.ctypes.data, len(rec), mats.ctypes.data if mats.size else None, mats.size // 32,
+                               int(sweep_index), int(bool(peer)), int(bool(wait)))
+    if rc < -2:
+        _check(rc)
+    return rc
 
 
 class Simulation:

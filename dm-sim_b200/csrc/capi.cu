@@ -78,6 +78,7 @@ static void init_options()
     if (const char* e = getenv("DMB_PLAN_CACHE")) g_plan_cache = atoi(e);
     if (const char* e = getenv("DMB_DIRECT_STORE")) set_sweep_direct_store(atoi(e) != 0);
     if (const char* e = getenv("DMB_HEAVY_LAST")) set_sweep_heavy_last(atoi(e) != 0);
+    if (const char* e = getenv("DMB_LIGHT_FIRST")) set_sweep_light_first(atoi(e) != 0);
     if (const char* e = getenv("DMB_TMA_PREFETCH")) g_tma_prefetch = atoi(e);
 }
 
@@ -475,6 +476,7 @@ int dmb_set_option(const char* name, int64_t value)
     else if (!strcmp(name, "tma_prefetch")) g_tma_prefetch = (int)value;
     else if (!strcmp(name, "direct_store")) set_sweep_direct_store(value != 0);
     else if (!strcmp(name, "heavy_last")) set_sweep_heavy_last(value != 0);
+    else if (!strcmp(name, "light_first")) set_sweep_light_first(value != 0);
     else if (!strcmp(name, "persistent"))
     {
         g_persistent = (int)value;
@@ -1778,6 +1780,35 @@ int64_t dmb_plan_json(int n_qubits, int world_size, const dmb_gate* gates, size_
     }
 }
 
+// host-only: plan + encode the circuit and generate the program text of sweep `sweep_index` (0: no such sweep / not covered)
+static int jit_text_of(int n_qubits, int world_size, const dmb_gate* gates, size_t n_gates, const double* mats, size_t n_mats,
+                       int sweep_index, int peer, std::string& defines, std::string& program)
+{
+    Plan p = make_plan(n_qubits, world_size, gates, n_gates, mats, n_mats, std::vector<int>(), g_opt, false, false);
+    int seen = -1;
+    for (size_t i = 0; i < p.steps.size(); i++)
+    {
+        if (p.steps[i].kind != 0 || ++seen != sweep_index) continue;
+        const Sweep& sw = p.steps[i].sweep;
+        EncodedSweep enc;
+        encode_sweep(sw, enc);
+        SweepArgs a;
+        memset(&a, 0, sizeof(a));
+        fill_sweep_tables(sw, 2 * n_qubits - p.g, a);
+        a.ops_bytes = (int)enc.stream.size();
+        a.n_rounds = (int)enc.rounds.size();
+        a.n_groups = (int)enc.groups.size();
+        a.n_stars = (int)enc.stars.size();
+        a.op_mask = enc.op_mask;
+        a.peer_shift = peer ? 0 : -1;
+        a.direct = enc.direct;
+        if (!a.tma_load || !a.tma_store || sw.out_of_place) a.direct.enabled = 0;
+        if (a.direct.enabled || peer) a.tma_store = 0;
+        return jit_generate(a, enc.stream.data(), enc.rounds.data(), enc.groups.data(), defines, program) ? 1 : 0;
+    }
+    return 0;
+}
+
 // The CUDA text the run-time compiler would be given for sweep `sweep_index` of the plan (its structural #defines, a
 // separator line "//---- program", then the generated body of "dmb_jit_program.inc"): host only, for the CPU test-suite.
 // peer != 0: the variant whose stores go to the peers' shards.  Returns the bytes needed (including NUL), 0 when the step is
@@ -1788,38 +1819,44 @@ int64_t dmb_jit_source(int n_qubits, int world_size, const dmb_gate* gates, size
     init_options();
     try
     {
-        Plan p = make_plan(n_qubits, world_size, gates, n_gates, mats, n_mats, std::vector<int>(), g_opt, false, false);
-        int seen = -1;
-        for (size_t i = 0; i < p.steps.size(); i++)
+        std::string defines, program;
+        if (!jit_text_of(n_qubits, world_size, gates, n_gates, mats, n_mats, sweep_index, peer, defines, program)) return 0;
+        const std::string js = defines + "//---- program\n" + program;
+        if (out && cap > 0)
         {
-            if (p.steps[i].kind != 0 || ++seen != sweep_index) continue;
-            const Sweep& sw = p.steps[i].sweep;
-            EncodedSweep enc;
-            encode_sweep(sw, enc);
-            SweepArgs a;
-            memset(&a, 0, sizeof(a));
-            fill_sweep_tables(sw, 2 * n_qubits - p.g, a);
-            a.ops_bytes = (int)enc.stream.size();
-            a.n_rounds = (int)enc.rounds.size();
-            a.n_groups = (int)enc.groups.size();
-            a.n_stars = (int)enc.stars.size();
-            a.op_mask = enc.op_mask;
-            a.peer_shift = peer ? 0 : -1;
-            a.direct = enc.direct;
-            if (!a.tma_load || !a.tma_store || sw.out_of_place) a.direct.enabled = 0;
-            if (a.direct.enabled || peer) a.tma_store = 0;
-            std::string defines, program;
-            if (!jit_generate(a, enc.stream.data(), enc.rounds.data(), enc.groups.data(), defines, program)) return 0;
-            const std::string js = defines + "//---- program\n" + program;
-            if (out && cap > 0)
-            {
-                const size_t ncopy = std::min(cap - 1, js.size());
-                memcpy(out, js.data(), ncopy);
-                out[ncopy] = 0;
-            }
-            return (int64_t)js.size() + 1;
+            const size_t ncopy = std::min(cap - 1, js.size());
+            memcpy(out, js.data(), ncopy);
+            out[ncopy] = 0;
         }
-        return 0;
+        return (int64_t)js.size() + 1;
+    }
+    catch (const std::invalid_argument& e)
+    {
+        return fail(DMB_EINVAL, e.what());
+    }
+    catch (const std::exception& e)
+    {
+        return fail(DMB_ESTATE, e.what());
+    }
+}
+
+// Hands that text to the library's own run-time compiler (worker threads, memory + disk cache; compiling needs no GPU).
+// wait != 0: until the kernel is built.  Returns 1 built, 0 queued / still compiling, -1 the compilation failed
+// (dmb_last_error has the log), -2 no such sweep / not covered, or a DMB_E* code.
+int dmb_jit_compile(int n_qubits, int world_size, const dmb_gate* gates, size_t n_gates, const double* mats, size_t n_mats,
+                    int sweep_index, int peer, int wait)
+{
+    init_options();
+    try
+    {
+        std::string defines, program, why;
+        if (!jit_available(&why)) return fail(DMB_ESTATE, "run-time compiler unavailable: " + why);
+        if (!jit_text_of(n_qubits, world_size, gates, n_gates, mats, n_mats, sweep_index, peer, defines, program)) return -2;
+        JitKernel* k = jit_request(defines, program);
+        if (wait) jit_wait(k);
+        const int st = k->state.load();
+        if (st < 0) { fail(DMB_ESTATE, "run-time compilation failed: " + k->log); return -1; }
+        return st;
     }
     catch (const std::invalid_argument& e)
     {

@@ -16,6 +16,8 @@ void set_sweep_direct_store(bool on) { g_direct_store = on; }
 static bool g_dense2_lu = true;
 void set_sweep_dense2_lu(bool on) { g_dense2_lu = on; }
 bool sweep_dense2_lu() { return g_dense2_lu; }
+static bool g_light_first = true;
+void set_sweep_light_first(bool on) { g_light_first = on; }
 static bool g_heavy_last = false; // (measured on B200, r2u: qft_n15 23.1 vs 21.6 ms -- the diagonals of a round planned from the back cannot be deferred and merged; random_c1c2_n15 344 vs 347 ms)
 void set_sweep_heavy_last(bool on) { g_heavy_last = on; }
 void set_sweep_tma_box_bits(int bits) { g_tma_box_bits = bits < 3 ? 3 : (bits > kMaxTileBits ? kMaxTileBits : bits); }
@@ -218,8 +220,11 @@ inline bool is_cp(const TileOp& t) { return t.cls == CLS_CPHASE; }
 // a register bit.  Sweeps containing SRN (a full barrier) keep strict list order.
 // `backward`: the same greedy choice made from the END of the list (every rule above is symmetric under reversal): the round
 // built first -- the fullest one -- then runs LAST and the leftovers first.
-static std::vector<RoundPlan> plan_rounds_dir(const Sweep& sw, int R, bool backward)
+// `first_R`: register-bit budget of the FIRST round (<= R): a sweep whose bits do not fill its last round is planned
+// "light first" instead, so that the leftover round runs first and a full one last.
+static std::vector<RoundPlan> plan_rounds_dir(const Sweep& sw, int R, bool backward, int first_R = -1)
 {
+    if (first_R < 1 || first_R > R) first_R = R;
     const int n = (int)sw.ops.size();
     std::vector<char> done(n, 0), diag(n, 0);
     bool has_srn = false;
@@ -282,9 +287,10 @@ static std::vector<RoundPlan> plan_rounds_dir(const Sweep& sw, int R, bool backw
         while (first < n && done[first]) first++;
         unsigned rb = 0;
         int cur = 0;
-        while (__builtin_popcount(rb) < R)
+        const int Rcur = rounds.empty() ? first_R : R;
+        while (__builtin_popcount(rb) < Rcur)
         {
-            const int room = R - __builtin_popcount(rb);
+            const int room = Rcur - __builtin_popcount(rb);
             std::vector<unsigned> cands;
             int looked = 0;
             auto add_cand = [&](unsigned miss) {
@@ -351,6 +357,27 @@ static std::vector<RoundPlan> plan_rounds_dir(const Sweep& sw, int R, bool backw
 std::vector<RoundPlan> plan_rounds(const Sweep& sw, int R)
 {
     std::vector<RoundPlan> fwd = plan_rounds_dir(sw, R, false);
+    if (g_light_first && fwd.size() >= 2)
+    {
+        // the last round of a full-size tile shadows the load of the CTA's next tile: when it is a leftover (fewer register
+        // bits than the others), plan again with that budget for the FIRST round; same number of rounds or the plan is dropped
+        auto cost = [&](const RoundPlan& rp) {
+            double w = 0;
+            for (int i : rp.ops) w += is_cp(sw.ops[i]) ? 2 : (sw.ops[i].nb == 2 ? 16 : 4); // (rough FP64 cost per element)
+            return w;
+        };
+        const int left = __builtin_popcount(fwd.back().touched);
+        bool srn = false;
+        for (const TileOp& t : sw.ops) srn = srn || t.cls == CLS_SRN1;
+        if (!srn && left >= 1 && left < R)
+        {
+            std::vector<RoundPlan> lf = plan_rounds_dir(sw, R, false, left);
+            size_t n0 = 0, n1 = 0;
+            for (const RoundPlan& rp : fwd) n0 += rp.ops.size();
+            for (const RoundPlan& rp : lf) n1 += rp.ops.size();
+            if (n0 == n1 && lf.size() <= fwd.size() && cost(lf.back()) > cost(fwd.back())) fwd.swap(lf);
+        }
+    }
     if (!g_heavy_last || fwd.size() < 2) return fwd;
     std::vector<RoundPlan> bwd = plan_rounds_dir(sw, R, true);
     if (bwd.empty() || bwd.size() > fwd.size()) return fwd;

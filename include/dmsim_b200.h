@@ -173,6 +173,10 @@ int64_t dmb_plan_json(int n_qubits, int world_size, const dmb_gate* gates, size_
  * (sweeps that were still interpreted because their kernel was not compiled yet). */
 int64_t dmb_jit_source(int n_qubits, int world_size, const dmb_gate* gates, size_t n_gates, const double* mats,
                        size_t n_mats, int sweep_index, int peer, char* out, size_t cap);
+/* dmb_jit_compile: hands that text to the library's run-time compiler (worker threads, memory + disk cache; compiling
+ * needs no GPU).  Returns 1 built, 0 queued or still compiling (wait == 0), -1 compilation failed, -2 no such sweep. */
+int dmb_jit_compile(int n_qubits, int world_size, const dmb_gate* gates, size_t n_gates, const double* mats, size_t n_mats,
+                    int sweep_index, int peer, int wait);
 int dmb_query(dmb_handle h /* may be NULL */, const char* name, double* value);
 
 /* Tuning knobs (process-wide; also read once from env DMB_TILE_BITS, DMB_LOW_BITS, DMB_GRAPH):

@@ -1,6 +1,7 @@
-"""CPU: the run-time compiler's input (csrc/jit.cu).  The generated program of a sweep must be accepted by NVRTC for sm_100a
-together with the device headers exactly as the library embeds them -- no GPU is needed to compile.  (What the compiled
-kernels compute is checked on the GPU: tests/test_gpu_jit.py.)"""
+"""CPU: the run-time compiler (csrc/jit.cu).  The generated program of a sweep must be accepted by NVRTC for sm_100a together
+with the device headers exactly as the library embeds them -- compiling needs no GPU, so the library's own compile path
+(dlopen of NVRTC, worker threads, caches) runs here.  (What the compiled kernels compute is checked on the GPU:
+tests/test_gpu_jit.py.)"""
 import importlib
 import os
 
@@ -10,32 +11,6 @@ import pytest
 from helpers import each_op_once, random_gates
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CSRC = os.path.join(ROOT, "dm-sim_b200", "csrc")
-ENTRY = '''#include "sweep_device.cuh"
-extern "C" __global__ void __launch_bounds__(dmb::kTileThreads, 3) dmb_jit_sweep(const __grid_constant__ dmb::SweepArgs a)
-{
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    dmb::sweep_body<DMB_J_MASK, 1>(a, smem_raw);
-}
-'''
-
-
-def nvrtc_compile(defines, program):
-    nvrtc = pytest.importorskip("cuda.bindings.nvrtc")
-    hdrs = {"devop.hpp": open(os.path.join(CSRC, "devop.hpp")).read(),
-            "sweep_device.cuh": open(os.path.join(CSRC, "sweep_device.cuh")).read(), "dmb_jit_program.inc": program}
-    names = [n.encode() for n in hdrs]
-    err, prog = nvrtc.nvrtcCreateProgram((defines + ENTRY).encode(), b"dmb_jit_sweep.cu", len(names), [hdrs[n].encode() for n in hdrs], names)
-    assert err == nvrtc.nvrtcResult.NVRTC_SUCCESS
-    opts = [b"--gpu-architecture=sm_100a", b"-std=c++17", b"-default-device", b"-lineinfo"]
-    (res,) = nvrtc.nvrtcCompileProgram(prog, len(opts), opts)
-    _, n = nvrtc.nvrtcGetProgramLogSize(prog)
-    log = b" " * n
-    nvrtc.nvrtcGetProgramLog(prog, log)
-    assert res == nvrtc.nvrtcResult.NVRTC_SUCCESS, log.decode()[:3000]
-    _, n = nvrtc.nvrtcGetCUBINSize(prog)
-    assert n > 0
-    return n
 
 
 def sweeps_of(dm, n, world, gates, peer=False):
@@ -51,6 +26,8 @@ def sweeps_of(dm, n, world, gates, peer=False):
 def test_generated_programs_compile_for_sm_100a(dm):
     """Every op body through the generator (all 38 ops + C1 / C2 + SRN on small tiles), the TMA / direct-store skeleton
     (full-size tiles of a QFT) and the peer-store variant of a sharded plan."""
+    if not dm.query("jit_available"):
+        pytest.skip("libnvrtc not loadable here")
     circuits = importlib.import_module("dm-sim_b200.circuits")
     rng = np.random.default_rng(3)
     allops = random_gates(6, 10, rng, names=["U3", "CX", "H", "T"], with_raw=False) + each_op_once(6, rng) + [("SRN", [2], 0, 0, 0)]
@@ -59,10 +36,11 @@ def test_generated_programs_compile_for_sm_100a(dm):
     for n, world, gates, peer in cases:
         progs = sweeps_of(dm, n, world, gates, peer)
         assert progs, "the generator must cover these sweeps"
-        for defines, program in progs[:4]:
+        for i, (defines, program) in enumerate(progs[:4]):
             assert "#define DMB_JIT 1" in defines
             assert "__syncthreads();" in program or "#define DMB_J_N_GROUPS 0\n" in defines  # (a pure remap pack sweep has no ops)
-            nvrtc_compile(defines, program)
+            rc = dm.jit_compile(n, world, gates, i, peer=peer, wait=True)
+            assert rc == 1, dm.lib().dmb_last_error().decode()[:3000]
             n_compiled += 1
     assert n_compiled >= 4
 
@@ -81,3 +59,32 @@ def test_program_text_is_independent_of_the_payload(dm):
     a, b, c = (sweeps_of(dm, 7, 1, g) for g in (circuit(1.0), circuit(0.6), circuit(1.0, extra=True)))
     assert a and a == b
     assert a != c
+
+
+def test_library_compiler_builds_caches_and_survives_exit(dm, tmp_path):
+    """The library's own compile path (dlopen of NVRTC, worker threads, disk cache) without a GPU; and a process that EXITS
+    while compilations are queued / running must not crash (the workers are drained at exit)."""
+    import subprocess
+    import sys
+    if not dm.query("jit_available"):
+        pytest.skip("libnvrtc not loadable here")
+    code = (
+        "import sys, os, importlib\n"
+        "sys.path.insert(0, %r)\n"
+        "dm = importlib.import_module('dm-sim_b200'); circuits = importlib.import_module('dm-sim_b200.circuits')\n"
+        "g = circuits.qft(8)\n"
+        "mode = sys.argv[1]\n"
+        "if mode == 'wait':\n"
+        "    assert dm.jit_compile(8, 1, g, 0) == 1\n"
+        "    print('COUNTERS', int(dm.query('jit_compiled')), int(dm.query('jit_disk_hits')))\n"
+        "else:\n"
+        "    rs = [dm.jit_compile(8, 1, circuits.random_c1c2(8, 40, seed=s), 0, wait=False) for s in range(6)]\n"
+        "    assert all(r in (0, 1) for r in rs), rs\n"
+        "    print('QUEUED')\n" % ROOT)
+    env = dict(os.environ, DMB_JIT_CACHE=str(tmp_path / "jitcache"))
+    a = subprocess.run([sys.executable, "-c", code, "wait"], env=env, capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0 and "COUNTERS 1 0" in a.stdout, a.stdout + a.stderr
+    b = subprocess.run([sys.executable, "-c", code, "wait"], env=env, capture_output=True, text=True, timeout=300)
+    assert b.returncode == 0 and "COUNTERS 0 1" in b.stdout, b.stdout + b.stderr  # second process: disk cache hit, nothing compiled
+    c = subprocess.run([sys.executable, "-c", code, "exit"], env=env, capture_output=True, text=True, timeout=300)
+    assert c.returncode == 0 and "QUEUED" in c.stdout, (c.returncode, c.stdout + c.stderr)
