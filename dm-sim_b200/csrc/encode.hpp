@@ -27,7 +27,7 @@ void set_sweep_tma_box_bits(int bits);
 int sweep_tma_box_bits();
 // last round of full-size in-place TMA tiles stores straight from registers to global memory (default on)
 void set_sweep_direct_store(bool on);
-// a sweep whose last round would be a leftover runs that leftover FIRST (default on)
+// a sweep whose last round would be a leftover runs that leftover FIRST (default off: measured neutral)
 void set_sweep_light_first(bool on);
 // rounds planned from the end of the op list when that ends the sweep on a heavier round (default off: measured slower)
 void set_sweep_heavy_last(bool on);
