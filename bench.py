@@ -160,6 +160,18 @@ def reference_arm(args, name):
                              "measured_at_full_size": not extrapolated},
             "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if extrapolated:
+        # the same reference backend measured ONCE at the full size on a box of this pool (committed line; 64 GiB of host
+        # memory and minutes per run are outside the bounded sample every bench run takes)
+        try:
+            f = os.path.join(ROOT, "profiles", "r2_bench_reference_full_size.jsonl")
+            d = json.loads(open(f).read().strip().splitlines()[-1])
+            if d["config"]["workload"] == name:
+                line["cpu_baseline"]["full_size_measurement"] = {"ms_per_step": d["ms_per_step"], "value": d["value"], "cores": d["cpu_baseline"]["cores"],
+                                                                 "file": "profiles/r2_bench_reference_full_size.jsonl",
+                                                                 "what": "bench.py --impl reference --cpu-full-size --steps 1, round 2, same pool"}
+        except Exception:  # noqa: BLE001
+            pass
     return line
 
 

@@ -52,6 +52,10 @@ static int g_persistent = 0;    // small states: all sweeps of a run in one coop
 // smaller states take microseconds; DMB_JIT_MIN_BITS / option "jit_min_bits")
 static int g_jit = 1;
 static int g_jit_min_bits = 24;
+// tiered mode: a plan's kernels are only compiled from its `jit_hot`-th run on (DMB_JIT_HOT / option "jit_hot").  A one-shot
+// run, or a circuit that continues from the layout its previous run left (planned anew every time), would never get to
+// use them: compiling for those only burns host cores
+static int g_jit_hot = 2;
 static int g_tma_prefetch = 0;  // L2 prefetch of a CTA's next tile (DMB_TMA_PREFETCH=0 / option "tma_prefetch")
 static int g_grid_per_sm = 0;   // experiments: resident CTAs per SM of the sweep kernel (0 = what the occupancy query says)
 static int g_sparse_start = 1; // skip the tiles that are still all-zero after dmb_reset_dm (DMB_SPARSE=0 / option "sparse")
@@ -75,6 +79,7 @@ static void init_options()
     g_opt.small_state_bits = g_persistent ? 20 : 0;
     if (const char* e = getenv("DMB_JIT")) g_jit = atoi(e);
     if (const char* e = getenv("DMB_JIT_MIN_BITS")) g_jit_min_bits = atoi(e);
+    if (const char* e = getenv("DMB_JIT_HOT")) g_jit_hot = atoi(e);
     if (const char* e = getenv("DMB_PLAN_CACHE")) g_plan_cache = atoi(e);
     if (const char* e = getenv("DMB_DIRECT_STORE")) set_sweep_direct_store(atoi(e) != 0);
     if (const char* e = getenv("DMB_HEAVY_LAST")) set_sweep_heavy_last(atoi(e) != 0);
@@ -265,6 +270,7 @@ struct dmb_sim
     // 2 dry pass that resolves (waits / loads) without launching, 3 launching inside a stream capture (nothing may be loaded)
     std::unordered_map<unsigned long long, JitKernel*> jit_memo;
     int jit_mode = 0;
+    unsigned plan_runs = 0;                      // dmb_run calls on the device tables of the current plan (tiered mode: hotness)
     unsigned jit_missing = 0, jit_used = 0;      // sweeps of the last enqueue that ran interpreted because their kernel was not ready / specialised
     unsigned graph_jit_missing = 0;              // ... of the captured graph
     unsigned long long graph_jit_epoch = 0;      // jit_ready_count() when the graph was captured
@@ -484,6 +490,7 @@ int dmb_set_option(const char* name, int64_t value)
     }
     else if (!strcmp(name, "jit")) g_jit = (int)value;
     else if (!strcmp(name, "jit_min_bits")) g_jit_min_bits = (int)value;
+    else if (!strcmp(name, "jit_hot")) g_jit_hot = (int)value;
     else if (!strcmp(name, "plan_cache")) g_plan_cache = (int)value;
     else return fail(DMB_EINVAL, std::string("unknown option ") + name);
     return DMB_OK;
@@ -767,6 +774,7 @@ static int upload_tables(dmb_sim* s)
     }
     drop_graph(s);
     s->jit_memo.clear();
+    s->plan_runs = 0;
     s->device_key[0] = s->device_key[1] = 0;
     CU(cudaSetDevice(s->device));
     int rc;
@@ -891,6 +899,11 @@ static int fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, dou
 static const void* jit_resolve(dmb_sim* s, size_t step, const SweepArgs& a)
 {
     if (!g_jit || s->M < g_jit_min_bits) return nullptr;
+    if (g_jit == 1 && (int)s->plan_runs < g_jit_hot)
+    {
+        s->jit_missing++; // (cold plan: interpreted for now)
+        return nullptr;
+    }
     const unsigned long long key = ((unsigned long long)step << 4) | (a.tma_load ? 1u : 0u) | (a.tma_store ? 2u : 0u) | (a.direct.enabled ? 4u : 0u) |
                                    (a.peer_shift >= 0 ? 8u : 0u);
     JitKernel* k = nullptr;
@@ -1115,7 +1128,11 @@ static int group_run(dmb_sim* grp, dmb_stats* stats)
 {
     dmb_sim* lead = grp->shards[0];
     const size_t nsteps = lead->plan.steps.size();
-    for (dmb_sim* c : grp->shards) c->jit_missing = c->jit_used = 0;
+    for (dmb_sim* c : grp->shards)
+    {
+        c->jit_missing = c->jit_used = 0;
+        c->plan_runs++;
+    }
     if (lead->jit_memo.empty())
     {
         // queue every compilation of the plan at once (the shards share the kernels); the waiting mode waits here, before
@@ -1249,6 +1266,7 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
         int rc = build_plan(s); // state layout changed since planning (reset / previous run): re-plan
         if (rc) return rc;
     }
+    s->plan_runs++;
     uint64_t launches = 0;
     int cur = s->cur;
     // small states (no sweep of the plan uses TMA tile I/O: PlanOptions::small_state_bits) -> ONE cooperative launch for the whole run
@@ -1323,6 +1341,11 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
     else if (graphable)
     {
         // (tiered execution: sweeps captured on the interpreter kernel move to their specialised kernel once it is compiled)
+        if (s->graph_exec && g_jit == 1 && (int)s->plan_runs == g_jit_hot && s->jit_memo.empty())
+        {
+            int rcj = jit_dry_pass(s, 1); // the plan has turned hot: queue its compilations (the graph is refreshed when they are done)
+            if (rcj) return rcj;
+        }
         const bool stale = s->graph_exec && s->graph_jit_missing > 0 && jit_ready_count() != s->graph_jit_epoch;
         if (!s->graph_exec || s->graph_cur != s->cur || s->graph_support != s->support || stale)
         {
