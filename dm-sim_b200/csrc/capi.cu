@@ -48,14 +48,16 @@ static int g_use_graph = 1;
 static int g_plan_cache = 1;    // reuse the plan (and the device tables) of a circuit that is set again (DMB_PLAN_CACHE=0 / option "plan_cache")
 static int g_persistent = 0;    // small states: all sweeps of a run in one cooperative launch (DMB_PERSISTENT=1 / option "persistent"); measured SLOWER than the captured graph on B200 (vqe_uccsd_n8: 10.1 vs 7.8 ms, profiles/README.md): off by default
 // run-time specialised sweep kernels (jit.cu): 0 off, 1 tiered (the interpreter kernel runs a sweep until its compiled kernel
-// is ready), 2 wait for the compiler (DMB_JIT / option "jit"); only for shards of >= 2^jit_min_bits elements (sweeps of
-// smaller states take microseconds; DMB_JIT_MIN_BITS / option "jit_min_bits")
+// is ready), 2 wait for the compiler (DMB_JIT / option "jit"); only for shards of >= 2^jit_min_bits elements
+// (DMB_JIT_MIN_BITS / option "jit_min_bits")
 static int g_jit = 1;
-static int g_jit_min_bits = 24;
+static int g_jit_min_bits = 16;
 // tiered mode: a plan's kernels are only compiled from its `jit_hot`-th run on (DMB_JIT_HOT / option "jit_hot").  A one-shot
 // run, or a circuit that continues from the layout its previous run left (planned anew every time), would never get to
 // use them: compiling for those only burns host cores
 static int g_jit_hot = 2;
+static int g_jit_hot_small = 8; // ... of shards below 2^24 elements (their sweeps take microseconds: only a real loop over one circuit pays for
+                                // a compilation; DMB_JIT_HOT_SMALL / option "jit_hot_small")
 static int g_tma_prefetch = 0;  // L2 prefetch of a CTA's next tile (DMB_TMA_PREFETCH=0 / option "tma_prefetch")
 static int g_grid_per_sm = 0;   // experiments: resident CTAs per SM of the sweep kernel (0 = what the occupancy query says)
 static int g_sparse_start = 1; // skip the tiles that are still all-zero after dmb_reset_dm (DMB_SPARSE=0 / option "sparse")
@@ -80,6 +82,7 @@ static void init_options()
     if (const char* e = getenv("DMB_JIT")) g_jit = atoi(e);
     if (const char* e = getenv("DMB_JIT_MIN_BITS")) g_jit_min_bits = atoi(e);
     if (const char* e = getenv("DMB_JIT_HOT")) g_jit_hot = atoi(e);
+    if (const char* e = getenv("DMB_JIT_HOT_SMALL")) g_jit_hot_small = atoi(e);
     if (const char* e = getenv("DMB_PLAN_CACHE")) g_plan_cache = atoi(e);
     if (const char* e = getenv("DMB_DIRECT_STORE")) set_sweep_direct_store(atoi(e) != 0);
     if (const char* e = getenv("DMB_HEAVY_LAST")) set_sweep_heavy_last(atoi(e) != 0);
@@ -491,6 +494,7 @@ int dmb_set_option(const char* name, int64_t value)
     else if (!strcmp(name, "jit")) g_jit = (int)value;
     else if (!strcmp(name, "jit_min_bits")) g_jit_min_bits = (int)value;
     else if (!strcmp(name, "jit_hot")) g_jit_hot = (int)value;
+    else if (!strcmp(name, "jit_hot_small")) g_jit_hot_small = (int)value;
     else if (!strcmp(name, "plan_cache")) g_plan_cache = (int)value;
     else return fail(DMB_EINVAL, std::string("unknown option ") + name);
     return DMB_OK;
@@ -895,11 +899,13 @@ static int fill_sweep_args(const dmb_sim* s, size_t step, const double2* in, dou
     return DMB_OK;
 }
 
+static int jit_hot_of(const dmb_sim* s) { return s->M >= 24 ? g_jit_hot : g_jit_hot_small; }
+
 // the run-time specialised kernel of sweep `step` with the I/O variant of `a`, or nullptr (interpreter kernel)
 static const void* jit_resolve(dmb_sim* s, size_t step, const SweepArgs& a)
 {
     if (!g_jit || s->M < g_jit_min_bits) return nullptr;
-    if (g_jit == 1 && (int)s->plan_runs < g_jit_hot)
+    if (g_jit == 1 && (int)s->plan_runs < jit_hot_of(s))
     {
         s->jit_missing++; // (cold plan: interpreted for now)
         return nullptr;
@@ -911,11 +917,19 @@ static const void* jit_resolve(dmb_sim* s, size_t step, const SweepArgs& a)
     if (it != s->jit_memo.end()) k = it->second;
     else
     {
-        std::string defines, program;
-        if (jit_available(nullptr) &&
-            jit_generate(a, s->host_ops.data() + s->op_offset[step], s->host_rounds.data() + s->round_offset[step],
-                         s->host_groups.data() + s->group_offset[step], defines, program))
-            k = jit_request(defines, program);
+        const unsigned char* stream = s->host_ops.data() + s->op_offset[step];
+        const DevRound* rounds = s->host_rounds.data() + s->round_offset[step];
+        const DevGroup* groups = s->host_groups.data() + s->group_offset[step];
+        unsigned long long sk[2];
+        bool known = false;
+        const bool keyed = jit_struct_key(a, stream, rounds, groups, sk);
+        if (keyed) k = jit_lookup_struct(sk, &known);
+        if (!known)
+        {
+            std::string defines, program;
+            if (jit_available(nullptr) && jit_generate(a, stream, rounds, groups, defines, program)) k = jit_request(defines, program);
+            if (keyed) jit_remember_struct(sk, k);
+        }
         s->jit_memo[key] = k;
     }
     if (!k || s->jit_mode == 1) return nullptr;
@@ -1341,7 +1355,7 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
     else if (graphable)
     {
         // (tiered execution: sweeps captured on the interpreter kernel move to their specialised kernel once it is compiled)
-        if (s->graph_exec && g_jit == 1 && (int)s->plan_runs == g_jit_hot && s->jit_memo.empty())
+        if (s->graph_exec && g_jit == 1 && (int)s->plan_runs == jit_hot_of(s) && s->jit_memo.empty())
         {
             int rcj = jit_dry_pass(s, 1); // the plan has turned hot: queue its compilations (the graph is refreshed when they are done)
             if (rcj) return rcj;

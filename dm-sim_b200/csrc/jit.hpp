@@ -29,6 +29,11 @@ struct JitKernel
 // false: something the generator does not cover (the interpreter kernel runs the sweep)
 bool jit_generate(const SweepArgs& a, const unsigned char* stream, const DevRound* rounds, const DevGroup* groups, std::string& defines,
                   std::string& program);
+// hash of everything the generated text depends on (structural parameters, round / group tables, the ops' vid and aux) without
+// generating it: the process-wide map  key -> cache entry  spares a re-planned circuit of known structure the text generation
+bool jit_struct_key(const SweepArgs& a, const unsigned char* stream, const DevRound* rounds, const DevGroup* groups, unsigned long long (&key)[2]);
+JitKernel* jit_lookup_struct(const unsigned long long (&key)[2], bool* known); // (a known structure may map to nullptr: not covered)
+void jit_remember_struct(const unsigned long long (&key)[2], JitKernel* k);
 bool jit_available(std::string* why);
 // cache lookup by the hash of the text; a miss queues the compilation on the worker threads and returns the pending entry
 JitKernel* jit_request(const std::string& defines, const std::string& program);

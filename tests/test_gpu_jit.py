@@ -24,7 +24,7 @@ def jit(dm):
         for k, v in kw.items():
             dm.set_option(k, v)
     yield set_
-    dm.set_option("jit", 1); dm.set_option("jit_min_bits", 24); dm.set_option("tma", 1)
+    dm.set_option("jit", 1); dm.set_option("jit_min_bits", 16); dm.set_option("jit_hot_small", 8); dm.set_option("tma", 1)
     dm.set_option("persistent", 0); dm.set_option("graph", 1)
 
 
@@ -67,11 +67,11 @@ def test_specialised_each_op_alone(dm, oracle_mod, jit):
 
 
 def test_tiered_execution_switches_to_specialised_kernels(dm, oracle_mod, jit):
-    """jit = 1: the first run may still be interpreted; once the compiler is done the same circuit runs specialised (the
+    """jit = 1: the first run is interpreted (the compiler starts when the plan runs a second time); once the compiler is done the same circuit runs specialised (the
     captured graph is refreshed), with the same result, and a second circuit of the same STRUCTURE (other angles) reuses
     the kernels without compiling."""
     n = 9
-    jit(1, persistent=0)
+    jit(1, persistent=0, jit_hot_small=2)  # (small shards are only compiled for from their 8th run on by default)
 
     def circuit(scale):
         rng = np.random.default_rng(77)

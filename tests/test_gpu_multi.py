@@ -189,7 +189,7 @@ def test_group_on_specialised_kernels(dm, oracle_mod, world, n):
         assert max(np.abs(gre - re).max(), np.abs(gim - im).max()) < 1e-12
         del sim
     finally:
-        dm.set_option("jit", 1); dm.set_option("jit_min_bits", 24)
+        dm.set_option("jit", 1); dm.set_option("jit_min_bits", 16)
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
