@@ -1357,8 +1357,11 @@ int dmb_run(dmb_handle s, dmb_stats* stats)
         // (tiered execution: sweeps captured on the interpreter kernel move to their specialised kernel once it is compiled)
         if (s->graph_exec && g_jit == 1 && (int)s->plan_runs == jit_hot_of(s) && s->jit_memo.empty())
         {
-            int rcj = jit_dry_pass(s, 1); // the plan has turned hot: queue its compilations (the graph is refreshed when they are done)
+            // the plan has turned hot: queue its compilations and capture again -- kernels of a known structure are ready at once,
+            // the others move in when they are done (the `stale` test below)
+            int rcj = jit_dry_pass(s, 1);
             if (rcj) return rcj;
+            drop_graph(s);
         }
         const bool stale = s->graph_exec && s->graph_jit_missing > 0 && jit_ready_count() != s->graph_jit_epoch;
         if (!s->graph_exec || s->graph_cur != s->cur || s->graph_support != s->support || stale)

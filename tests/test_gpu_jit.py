@@ -105,6 +105,9 @@ def test_tiered_execution_switches_to_specialised_kernels(dm, oracle_mod, jit):
     compiled = dm.query("jit_compiled")
     gates2 = circuit(0.7)
     sim2 = run_gpu(dm, n, gates2)
+    assert dm.query("jit_sweeps", sim2._h) == 0, "a plan's first run is interpreted (tiered by hotness)"
+    sim2.reset_dm()
+    sim2.run()  # second run of the plan: it is hot now, and its kernels exist already
     re, im = sim2.get_dm()
     ore, oim = oracle_mod.Oracle(n).sim(gates2).dm()
     assert max(np.abs(re - ore).max(), np.abs(im - oim).max()) < TOL
