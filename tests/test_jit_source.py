@@ -88,3 +88,29 @@ def test_library_compiler_builds_caches_and_survives_exit(dm, tmp_path):
     assert b.returncode == 0 and "COUNTERS 0 1" in b.stdout, b.stdout + b.stderr  # second process: disk cache hit, nothing compiled
     c = subprocess.run([sys.executable, "-c", code, "exit"], env=env, capture_output=True, text=True, timeout=300)
     assert c.returncode == 0 and "QUEUED" in c.stdout, (c.returncode, c.stdout + c.stderr)
+
+
+def test_disk_cache_is_bounded(dm, tmp_path):
+    """DMB_JIT_CACHE_MAX_MB: when the cache directory holds more, the oldest kernels go (checked when a process first uses it)."""
+    import subprocess
+    import sys
+    import time
+    if not dm.query("jit_available"):
+        pytest.skip("libnvrtc not loadable here")
+    cache = tmp_path / "jitcache"
+    cache.mkdir()
+    now = time.time()
+    for i in range(8):  # 8 x 256 KiB of old "kernels", the first ones the oldest
+        f = cache / ("%032x.cubin" % i)
+        f.write_bytes(b"\0" * (256 << 10))
+        os.utime(f, (now - 10000 + i, now - 10000 + i))
+    code = ("import sys, importlib\nsys.path.insert(0, %r)\n"
+            "dm = importlib.import_module('dm-sim_b200'); circuits = importlib.import_module('dm-sim_b200.circuits')\n"
+            "assert dm.jit_compile(6, 1, circuits.qft(6), 0) == 1\n" % ROOT)
+    env = dict(os.environ, DMB_JIT_CACHE=str(cache), DMB_JIT_CACHE_MAX_MB="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    left = sorted(p.name for p in cache.glob("*.cubin"))
+    old = [n for n in left if n.startswith("0000000000000000000000000000000")]
+    assert len(old) <= 2 and all(int(n[:32], 16) >= 6 for n in old), left   # 2 MiB > 1 MiB cap: pruned to <= 0.5 MiB, newest kept
+    assert len(left) == len(old) + 1                                         # + the kernel this process compiled
