@@ -86,6 +86,7 @@ static void init_options()
     if (const char* e = getenv("DMB_PLAN_CACHE")) g_plan_cache = atoi(e);
     if (const char* e = getenv("DMB_DIRECT_STORE")) set_sweep_direct_store(atoi(e) != 0);
     if (const char* e = getenv("DMB_HEAVY_LAST")) set_sweep_heavy_last(atoi(e) != 0);
+    if (const char* e = getenv("DMB_SPREAD_PEERS")) g_opt.spread_peers = atoi(e) != 0;
     if (const char* e = getenv("DMB_LIGHT_FIRST")) set_sweep_light_first(atoi(e) != 0);
     if (const char* e = getenv("DMB_TMA_PREFETCH")) g_tma_prefetch = atoi(e);
 }
@@ -484,6 +485,7 @@ int dmb_set_option(const char* name, int64_t value)
     else if (!strcmp(name, "dense2_lu")) set_sweep_dense2_lu(value != 0);
     else if (!strcmp(name, "tma_prefetch")) g_tma_prefetch = (int)value;
     else if (!strcmp(name, "direct_store")) set_sweep_direct_store(value != 0);
+    else if (!strcmp(name, "spread_peers")) g_opt.spread_peers = value != 0;
     else if (!strcmp(name, "heavy_last")) set_sweep_heavy_last(value != 0);
     else if (!strcmp(name, "light_first")) set_sweep_light_first(value != 0);
     else if (!strcmp(name, "persistent"))

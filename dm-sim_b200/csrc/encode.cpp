@@ -977,12 +977,17 @@ void fill_sweep_tables(const Sweep& sw, int M, SweepArgs& a)
     }
     std::vector<char> used_in(M, 0), used_out(M, 0);
     for (int i = 0; i < k; i++) { used_in[sw.in_pos[i]] = 1; used_out[sw.out_pos[i]] = 1; }
+    // the positions the tile id enumerates, lowest id bit first: ascending -- except that a remap pack sweep takes the
+    // rank-selecting top local bits first (Sweep::spread_top).  Any order is a valid enumeration as long as loading and storing
+    // use the same one (a sweep only permutes bits INSIDE its tile: the unused positions are the same set on both sides)
     int ci = 0, co = 0;
-    for (int p = 0; p < M; p++)
-    {
-        if (!used_in[p]) a.cin[ci++] = (unsigned char)p;
-        if (!used_out[p]) a.cout[co++] = (unsigned char)p;
-    }
+    const int top = sw.spread_top > 0 && sw.spread_top < M ? M - sw.spread_top : M;
+    for (int pass = 0; pass < 2; pass++)
+        for (int p = pass == 0 ? top : 0; p < (pass == 0 ? M : top); p++)
+        {
+            if (!used_in[p]) a.cin[ci++] = (unsigned char)p;
+            if (!used_out[p]) a.cout[co++] = (unsigned char)p;
+        }
 }
 
 void fill_base_tables(SweepArgs& a)

@@ -1064,6 +1064,7 @@ Plan make_plan(int n, int world_size, const dmb_gate* gates, size_t n_gates, con
             }
             if ((int)tile.size() > kmax) throw std::logic_error("remap permutation does not fit one tile");
             emit_sweep(tile, {}, moves);
+            if (opt.spread_peers) plan.steps.back().sweep.spread_top = g;
         }
         Step ex;
         ex.kind = 1;

@@ -357,3 +357,39 @@ def test_rounds_planned_from_the_back(dm, oracle_mod, family, n):
     finally:
         dm.set_option("heavy_last", 0)
     assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - to_complex(re, im)).max() < TOL
+
+
+@pytest.mark.parametrize("n,world,o", [(7, 4, dict(tile_bits=6, low_bits=2, min_tiles_log2=2)), (8, 4, dict(tile_bits=8, low_bits=3, min_tiles_log2=2)),
+                                       (8, 8, dict(tile_bits=7, low_bits=2, min_tiles_log2=2))])
+def test_remap_pack_sweep_enumerates_rank_bits_first(dm, oracle_mod, opts, n, world, o):
+    """Pack sweep of a qubit remap: the rank-selecting top local bits that are not tile bits are the LOWEST bits of the tile id
+    (concurrent CTAs store to different peers); the enumeration is the same on the load and the store side and the result is
+    unchanged (kernel mirror vs oracle), with the option on and off."""
+    rng = np.random.default_rng(900 + n + world)
+    gates = random_gates(n, 60, rng, exclude=("SRN",))
+    re, im = oracle_mod.Oracle(n).sim(gates).dm()
+    g = world.bit_length() - 1
+    M = 2 * n - g
+    seen_spread = False
+    for spread in (1, 0):
+        opts(spread_peers=spread, **o)
+        try:
+            plan = dm.plan_json(n, world, gates)
+        finally:
+            dm.set_option("spread_peers", 1)
+        assert plan["n_exchanges"] >= 1
+        for st in plan["steps"]:
+            if st["kind"] != "sweep":
+                continue
+            d = st["dev"]
+            cin, cout = d["cin"][:d["n_comp"]], d["cout"][:d["n_comp"]]
+            assert cin == cout and sorted(cin) == sorted(set(range(M)) - set(st["in_pos"]))
+            top = [p for p in cin if p >= M - g]
+            if st["out_of_place"] and spread and top:
+                assert cin[:len(top)] == top and cin[len(top):] == sorted(cin[len(top):])
+                seen_spread = seen_spread or cin != sorted(cin)
+            else:
+                assert cin == sorted(cin) or (st["out_of_place"] and spread)
+        assert np.abs(ke.run_plan_dev(plan, zero_state(n)) - to_complex(re, im)).max() < TOL
+    if (n, world) == (7, 4):
+        assert seen_spread, "this case must exercise a reordered enumeration (a rank-selecting bit outside the tile)"
