@@ -58,6 +58,10 @@ static int g_jit_min_bits = 16;
 static int g_jit_hot = 2;
 static int g_jit_hot_small = 8; // ... of shards below 2^24 elements (their sweeps take microseconds: only a real loop over one circuit pays for
                                 // a compilation; DMB_JIT_HOT_SMALL / option "jit_hot_small")
+// experiment for the next round (never measured: no GPU time was left): L2 promotion of the tile maps' requests (0 none, 1 / 2 /
+// 3 = 64 / 128 / 256 bytes).  Sweeps whose tile has only the 3 lowest bits contiguous read 128-byte runs and reach 0.69 of the HBM
+// peak where a sweep with 1-KiB runs reaches 0.86; 256-byte promotion would fetch the neighbouring tile's run with each request
+static int g_tma_l2_promotion = 0;
 static int g_tma_prefetch = 0;  // L2 prefetch of a CTA's next tile (DMB_TMA_PREFETCH=0 / option "tma_prefetch")
 static int g_grid_per_sm = 0;   // experiments: resident CTAs per SM of the sweep kernel (0 = what the occupancy query says)
 static int g_sparse_start = 1; // skip the tiles that are still all-zero after dmb_reset_dm (DMB_SPARSE=0 / option "sparse")
@@ -89,6 +93,7 @@ static void init_options()
     if (const char* e = getenv("DMB_SPREAD_PEERS")) g_opt.spread_peers = atoi(e) != 0;
     if (const char* e = getenv("DMB_LIGHT_FIRST")) set_sweep_light_first(atoi(e) != 0);
     if (const char* e = getenv("DMB_TMA_PREFETCH")) g_tma_prefetch = atoi(e);
+    if (const char* e = getenv("DMB_TMA_L2_PROMOTION")) g_tma_l2_promotion = atoi(e);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -131,7 +136,10 @@ static bool make_tile_map(const TmaGeom& g, int M, const void* buf, TmaDesc& out
     box[0] *= 2;
     CUtensorMap m;
     const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, const_cast<void*>(buf), dim, stride, box, estride,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           g_tma_l2_promotion == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                           : g_tma_l2_promotion == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                           : g_tma_l2_promotion == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
     {
@@ -484,6 +492,7 @@ int dmb_set_option(const char* name, int64_t value)
     else if (!strcmp(name, "tma_box_bits")) set_sweep_tma_box_bits((int)value);
     else if (!strcmp(name, "dense2_lu")) set_sweep_dense2_lu(value != 0);
     else if (!strcmp(name, "tma_prefetch")) g_tma_prefetch = (int)value;
+    else if (!strcmp(name, "tma_l2_promotion")) g_tma_l2_promotion = (int)value;
     else if (!strcmp(name, "direct_store")) set_sweep_direct_store(value != 0);
     else if (!strcmp(name, "spread_peers")) g_opt.spread_peers = value != 0;
     else if (!strcmp(name, "heavy_last")) set_sweep_heavy_last(value != 0);
